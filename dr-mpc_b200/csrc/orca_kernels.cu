@@ -1,0 +1,134 @@
+// orca_kernels.cu -- stand-alone batched ORCA pass (replaces CrowdSim.get_human_actions,
+// reference crowd_sim.py:264-284 -> orca.py:64-117). Compile with -fmad=false (see orca_device.cuh).
+//
+// Grid: one CTA per EPB consecutive envs. The CTA stages its envs' agents (humans + robot) in shared
+// memory as an fp32 structure-of-arrays tile (the fp64 -> fp32 cast is the Cython boundary of the
+// reference), then every lane-group of G lanes solves one human's LP against the tile.
+#include "orca_device.cuh"
+#include "launch.cuh"
+
+struct OrcaTileLayout {
+    int nA, NG, EPB;
+    size_t off_lines, off_agents, off_dist, bytes;
+};
+
+static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads, int EPB)
+{
+    OrcaTileLayout l;
+    l.nA = Nh + (robot_visible ? 1 : 0);
+    l.NG = threads / G;
+    l.EPB = EPB;
+    l.off_lines = 0;
+    l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
+    l.off_dist = l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float);
+    l.bytes = l.off_dist + (size_t)l.NG * l.nA * sizeof(float);
+    return l;
+}
+
+template <int G>
+__global__ void __launch_bounds__(1024)
+orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__restrict__ hpos,
+                    const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
+                    const double2 *__restrict__ rpos, const uint8_t *__restrict__ is_static,
+                    float2 *__restrict__ vnew, dre_orca_stats *__restrict__ stats,
+                    size_t off_agents, size_t off_dist)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nA = Nh + (p.robot_visible ? 1 : 0);
+    const int NG = blockDim.x / G;
+    OLine *lines = reinterpret_cast<OLine *>(smem_raw);
+    float *agents = reinterpret_cast<float *>(smem_raw + off_agents);
+    float *dist = reinterpret_cast<float *>(smem_raw + off_dist);
+    const int env0 = blockIdx.x * EPB;
+
+    // stage the tile: agents[e_local][field][a]
+    for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
+        const int el = t / nA, a = t - el * nA, e = env0 + el;
+        float *A = agents + (size_t)el * 5 * nA;
+        float x = 0.f, y = 0.f, vx = 0.f, vy = 0.f;
+        if (e < E) {
+            if (a < Nh) {
+                const double2 q = hpos[(size_t)e * Nh + a];
+                const float2 v = hvel[(size_t)e * Nh + a];
+                x = (float)q.x; y = (float)q.y; vx = v.x; vy = v.y;
+            } else {
+                const double2 q = rpos[e];
+                x = (float)q.x; y = (float)q.y;   // robot seen at rest (agent.py:43,96-97)
+            }
+        }
+        A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = p.radius;
+    }
+    __syncthreads();
+
+    cg::thread_block blk = cg::this_thread_block();
+    TileGroup<G> g(cg::tiled_partition<G>(blk));
+    const int gi = threadIdx.x / G;
+    OLine *L = lines + (size_t)gi * 2 * nA;
+    float *sd = dist + (size_t)gi * nA;
+    const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
+    const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
+
+    for (int ag = gi; ag < EPB * Nh; ag += NG) {
+        const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
+        if (e >= E) break;
+        const size_t gidx = (size_t)e * Nh + i;
+        float ox = 0.f, oy = 0.f;
+        if (is_static != nullptr && is_static[gidx]) {
+            if (g.rank() == 0 && stats) { dre_orca_stats z = {0, 0, 0, 0, 0u, 0}; stats[gidx] = z; }
+        } else {
+            // preferred velocity in fp64, then cast (orca.py:97-100,108)
+            const double2 P = hpos[gidx], Gl = goal[gidx];
+            const double dx = Gl.x - P.x, dy = Gl.y - P.y;
+            const double speed = sqrt(dx * dx + dy * dy);
+            double pvx = dx, pvy = dy;
+            if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
+            const float *A = agents + (size_t)el * 5 * nA;
+            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+                             p.max_speed_self, p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy,
+                             stats ? &stats[gidx] : nullptr);
+        }
+        if (g.rank() == 0) vnew[gidx] = make_float2(ox, oy);
+        g.sync();
+    }
+}
+
+template <int G>
+static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
+                       const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
+{
+    int per_env = Nh * G;
+    int EPB = per_env >= 384 ? 1 : 384 / per_env;
+    if (EPB > E) EPB = E;
+    int threads = EPB * per_env;
+    threads = (threads + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);
+    auto kern = orca_predict_kernel<G>;
+    if (l.bytes > 48 * 1024) {
+        if (l.bytes > 220 * 1024) return DRE_ERR_INVALID;
+        DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.bytes));
+    }
+    const int blocks = (E + EPB - 1) / EPB;
+    kern<<<blocks, threads, l.bytes, s>>>(p, E, Nh, EPB, (const double2 *)hpos, (const float2 *)hvel, (const double2 *)goal,
+                                           (const double2 *)rpos, is_static, (float2 *)vnew, stats, l.off_agents, l.off_dist);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+int dre_orca_pick_group(const dre_orca_params &p, int Nh)
+{
+    if (p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
+    const int nA = Nh + (p.robot_visible ? 1 : 0);
+    return nA <= 12 ? 8 : (nA <= 40 ? 16 : 32);
+}
+
+int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
+                    const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
+{
+    if (E <= 0 || Nh <= 0 || Nh > DRE_MAX_HUMANS) return DRE_ERR_INVALID;
+    switch (dre_orca_pick_group(p, Nh)) {
+    case 8: return launch_orca<8>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 16: return launch_orca<16>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    default: return launch_orca<32>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    }
+}

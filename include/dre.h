@@ -1,0 +1,222 @@
+/*
+ * include/dre.h -- C ABI of libdre.so, the B200-native batched step engine for DR-MPC's hot path
+ * (ORCA human step + path-tracking MPC + the env step that wraps them).
+ *
+ * The reference has no FFI or plugin registry for this path (it is duck-typed Python); each entry
+ * point below cites the reference interface it replaces. Conventions: plain pointers and sizes, no
+ * exceptions across the ABI (0 = DRE_OK, negative = error, dre_strerror() for text); "dev" pointers
+ * are CUDA device pointers owned by the caller (e.g. torch tensors), "host" pointers are host
+ * memory (pinned for best speed); `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream). A handle is bound to one GPU and is not thread-safe: one handle per GPU / per process.
+ * Solver failures are reported through per-env status words, never by aborting
+ * (reference mpc.py:188-190 swallows solver exceptions the same way).
+ */
+#ifndef DRE_H
+#define DRE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRE_OK 0
+#define DRE_ERR_INVALID (-1)   /* bad argument / unsupported size                     */
+#define DRE_ERR_CUDA (-2)      /* a CUDA runtime call failed (dre_last_cuda_error())  */
+#define DRE_ERR_NOMEM (-3)
+#define DRE_ERR_STATE (-4)     /* call order violated (e.g. step before reset)        */
+
+#define DRE_MAX_HUMANS 64      /* per env, excluding the robot                         */
+#define DRE_MAX_HORIZON 40     /* MPC horizon K                                        */
+#define DRE_PT_STATE_DIM 100   /* 25 nodes x (x,y,cos,sin), reference config_PT.py:40-45 */
+
+/* ---------------------------------------------------------------------------------------------
+ * ORCA parameters. Mirrors what scripts/policy/orca.py:79-89 passes to rvo2.PyRVOSimulator/addAgent
+ * (neighbor_dist, max_neighbors, time_horizon, radius = r + 0.01 + safety_space, max_speed) with the
+ * defaults of scripts/configs/config_HA.py:100-106.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dre_orca_params {
+    float neighbor_dist;   /* config_HA.orca.neighbor_dist (10)                          */
+    float time_horizon;    /* config_HA.orca.time_horizon (5)                            */
+    float time_step;       /* config_general.env.time_step (0.25)                        */
+    float radius;          /* ORCA radius of every agent: 0.3 + 0.01 + 0.175             */
+    float max_speed_self;  /* human v_max (orca.py:86)                                   */
+    int32_t max_neighbors; /* <=0: all others (orca.py:77: len(state.human_states))      */
+    int32_t robot_visible; /* config_HA.robot.visible                                    */
+    int32_t group_lanes;   /* lanes cooperating on one agent: 8, 16 or 32 (0 = auto)     */
+} dre_orca_params;
+
+/* per-solve diagnostics, used to count "LP-branch divergences" against the oracle */
+typedef struct dre_orca_stats {
+    int32_t n_lines, lp2_fail, n_lp1, lp1_work;
+    uint32_t branch_mask;  /* bit0 cut-off circle, bit1 left leg, bit2 right leg, bit3 collision */
+    int32_t n_lp3_proj;
+} dre_orca_stats;
+
+/*
+ * Batched replacement of CrowdSim.get_human_actions (crowd_sim.py:264-284) ->
+ * Human.act -> ORCA.predict (orca.py:64-117): one ORCA solve per human per env.
+ *   hpos  dev double[E][Nh][2]  human positions        hvel dev float[E][Nh][2] current velocities
+ *   goal  dev double[E][Nh][2]  goals                  rpos dev double[E][2]   robot position
+ *   is_static dev uint8[E][Nh] or NULL (static humans return (0,0), crowd_sim.py:270-272)
+ *   vnew  dev float[E][Nh][2]   OUT new velocities     stats dev dre_orca_stats[E][Nh] or NULL
+ */
+int dre_orca_predict(const dre_orca_params *p, int32_t num_envs, int32_t num_humans,
+                     const double *hpos, const float *hvel, const double *goal, const double *rpos,
+                     const uint8_t *is_static, float *vnew, dre_orca_stats *stats, void *stream);
+/* same call on HOST buffers: copies in, launches, copies out, synchronises */
+int dre_orca_predict_host(const dre_orca_params *p, int32_t num_envs, int32_t num_humans,
+                          const double *hpos, const float *hvel, const double *goal, const double *rpos,
+                          const uint8_t *is_static, float *vnew, dre_orca_stats *stats);
+
+/* ---------------------------------------------------------------------------------------------
+ * Path-tracking MPC. Replaces MPC(config_master, K, dt, continuous_task, max_v, max_w) /
+ * .reset() / .act({'path','interp_index','pose'}) (environment/path_tracking/utils/mpc.py:21,55,58)
+ * and the solver in pysteam_augmented/lev_marq_gauss_newton_custom_solver.py for N problems at once.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dre_mpc_params {
+    int32_t horizon;          /* K, config_PT.MPC.planning_horizon (4); <= DRE_MAX_HORIZON      */
+    double time_step;         /* 0.25                                                           */
+    double v_max, w_max;      /* config_general.robot.v_max / w_max (1, 1); v_min = 0, w_min=-w_max */
+    double node_separation;   /* config_PT.env.node_separation (0.2)                            */
+    int32_t max_iterations;   /* mpc.py:144 (1500)                                              */
+    double abs_change_tol;    /* pysteam Solver default absolute_cost_change_threshold (1e-4)   */
+    double rel_change_tol;    /* mpc.py:144 relative_cost_change_threshold (1e-4)               */
+    int32_t pose_jac_exact;   /* 0: STEAM's -J_l^-1(e) pose-error Jacobian, 1: exact -J_r^-1(e) */
+    int32_t max_retries;      /* cap on mpc.py:188-190's pose_error_scaling*=5 loop (default 20) */
+} dre_mpc_params;
+
+typedef struct dre_mpc_status {
+    int32_t iterations;  /* outer LM iterations of the final attempt            */
+    int32_t retries;     /* pose_error_scaling *= 5 retries                     */
+    int32_t lm_solves;   /* damped linear solves, all attempts                  */
+    int32_t cost_evals;  /* trial cost evaluations, all attempts                */
+    int32_t term;        /* 1 zero-gradient, 3 max iterations, 4 zero cost, 5 abs change, 6 rel change, -1 gave up */
+    int32_t pad;
+    double final_cost;
+} dre_mpc_status;
+
+typedef struct dre_mpc dre_mpc;
+
+int dre_mpc_create(const dre_mpc_params *p, int32_t num_problems, dre_mpc **out);
+int dre_mpc_destroy(dre_mpc *h);
+/* path table: host double[num_paths][3][path_stride] (rows x, y, theta like the reference's 3xL arrays), lens[num_paths] */
+int dre_mpc_set_paths(dre_mpc *h, const double *paths_host, int32_t num_paths, int32_t path_stride, const int32_t *lens_host);
+/* MPC.reset(): mask dev uint8[N] or NULL (= all) */
+int dre_mpc_reset(dre_mpc *h, const uint8_t *mask, void *stream);
+/*
+ * MPC.act(): path_id dev int32[N] (NULL = path 0), interp_index dev double[N], pose dev double[N][3]
+ * -> controls dev double[N][2K] = [v0,w0,...]; status dev dre_mpc_status[N] or NULL.
+ */
+int dre_mpc_act(dre_mpc *h, const int32_t *path_id, const double *interp_index, const double *pose,
+                double *controls, dre_mpc_status *status, void *stream);
+int dre_mpc_act_host(dre_mpc *h, const int32_t *path_id, const double *interp_index, const double *pose,
+                     double *controls, dre_mpc_status *status);
+/* warm-start state for parity tests / checkpoints: host double[N][K][4] (c,s,x,y of the inverse poses),
+ * host double[N][K][2], host uint8[N] */
+int dre_mpc_get_warm(dre_mpc *h, double *warm_T, double *warm_u, uint8_t *iteration0);
+int dre_mpc_set_warm(dre_mpc *h, const double *warm_T, const double *warm_u, const uint8_t *iteration0);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full environment. Replaces HAAndPTEnv(config_master, seed_addition) / .reset() / .step()
+ * (environment/HA_and_PT/human_avoidance_and_path_tracking_env.py:32,243,305) for E envs at once.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dre_env_config {
+    int32_t num_envs, num_humans, lookback;      /* lookback: config_general.env.lookback (6)           */
+    dre_orca_params orca;
+    dre_mpc_params mpc;
+    double time_step, time_limit;                /* config_general.env.time_step / time_limit            */
+    double human_radius, robot_radius;           /* config_HA.humans.radius / robot.radius (0.3)         */
+    double circle_radius, circle_radius_humans;  /* config_HA.sim.circle_radius (4) / _humans (5)        */
+    int32_t end_goal_changing;                   /* config_HA.humans.end_goal_changing                   */
+    /* HA rewards, config_HA.py:27-36 */
+    double collision_penalty, safety_dist, safety_penalty;
+    double disturbance_radius, disturbance_factor_v, disturbance_factor_th;
+    double actuation_min_vel, actuation_penalty;
+    /* PT rewards, config_PT.py:11-22 */
+    double pt_overall_scaling, goal_radius, goal_angle, goal_reward;
+    double path_advancement_scaling, deviation_xy, deviation_th, deviation_scale;
+    double corridor_penalty, corridor_max_dev, end_of_path_penalty, safety_corridor_penalty, safety_corridor_max_dev;
+    int32_t lookahead, lookbehind;               /* config_PT.py:38-39 (20, 5): lookahead+lookbehind = 25 */
+    int32_t mpc_actions_in_input;                /* config_PT.MPC.actions_in_input (4)                   */
+    int32_t auto_path_switch;                    /* 1: advance to the next path on goal / end-of-path inside step()
+                                                    (what soft_reset does at HA_and_PT env.py:130-141)   */
+    uint64_t seed;                               /* Philox key for device-side spawning / goal resampling */
+    int64_t env_id_offset;                       /* global id of env 0 of this shard (multi-GPU)         */
+} dre_env_config;
+
+/* Device pointers into the engine's structure-of-arrays env state (for parity tests, checkpoints and
+ * zero-copy consumers). Layouts in DESIGN.md "Data layout in HBM". */
+typedef struct dre_env_state_view {
+    double *hpos;      /* [E][Nh][2]            */
+    float *hvel;       /* [E][Nh][2]            */
+    double *hgoal;     /* [E][Nh][2]            */
+    uint8_t *hstatic;  /* [E][Nh]               */
+    double *hhist;     /* [E][Nh][LB+1][2] global position history, oldest first      */
+    int32_t *hvalid;   /* [E][Nh]               */
+    double *rpose;     /* [E][4] x,y,theta,pad  */
+    double *rprev;     /* [E][4]                */
+    double *rhist;     /* [E][LB+1][4]          */
+    double *rpastv;    /* [E][LB][2]            */
+    int32_t *rvalid;   /* [E]                   */
+    double *gtime;     /* [E]                   */
+    int32_t *path_idx; /* [E]                   */
+    uint8_t *loc_to_start; /* [E]               */
+    int64_t *step_count;   /* [E]               */
+} dre_env_state_view;
+
+/* One step's outputs: device pointers into ONE contiguous slab (so that a single D2H copy moves it).
+ * Observation layout = the reference's S dict (HA_and_PT env.py:325; human_avoidance_env.py:24-77;
+ * path_tracking_env.py:190-204) with the leading batch dim E instead of 1. */
+typedef struct dre_step_out {
+    double *pt_state;        /* [E][100]            S['PT']['PT_state']            */
+    double *mpc_actions;     /* [E][2*min(K,A)]     S['PT']['MPC_actions']         */
+    double *robot_node;      /* [E][2*LB]           S['HA']['robot_node']          */
+    double *past_robot_vel;  /* [E][2*LB]           S['HA']['past_robot_velocities'] */
+    double *percent_episode; /* [E]                 S['HA']['percent_episode']     */
+    double *spatial_edges;   /* [E][Nh][2*(LB+1)]   S['HA']['spatial_edges']       */
+    double *human_valid;     /* [E][Nh]             S['HA']['human_valid_history'] */
+    double *detected_humans; /* [E]                 S['HA']['detected_human_num']  */
+    double *rewards;         /* [E][3]  R_PT, R_DO(HA), R      (env.py:413)        */
+    double *info;            /* [E][8]  disturbance_v, disturbance_th, path_advancement, deviation, dmin, interp_index, xy_dev, spare */
+    uint32_t *done_bits;     /* [E]     DRE_DONE_* bits        (env.py:391-414)    */
+    dre_mpc_status *mpc_status; /* [E]                                              */
+    void *slab;              /* start of the contiguous slab                        */
+    size_t slab_bytes;
+} dre_step_out;
+
+typedef struct dre_env dre_env;
+
+int dre_env_create(const dre_env_config *cfg, dre_env **out);
+int dre_env_destroy(dre_env *h);
+int dre_env_set_paths(dre_env *h, const double *paths_host, int32_t num_paths, int32_t path_stride, const int32_t *lens_host);
+int dre_env_state(dre_env *h, dre_env_state_view *view);
+int dre_env_outputs(dre_env *h, dre_step_out *out);   /* device pointers of the output slab */
+dre_mpc *dre_env_mpc(dre_env *h);                     /* the env's MPC instance (warm-start access) */
+/*
+ * reset(): robot at (0,-circle_radius, pi) (env.py:286-303), humans spawned by device-side rejection
+ * sampling (crowd_sim.py:232-262 with Philox instead of np.random), first MPC solve, LB warm-start
+ * steps (human_avoidance_env.py:79-125). If `hpos_init`/`hgoal_init` (dev double[E][Nh][2]) are given
+ * they replace the spawning (parity runs upload the oracle's humans).
+ */
+int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream);
+/* step(): actions dev double[E][2] = ActionRot(v,w) per env; results in the output slab. */
+int dre_env_step(dre_env *h, const double *actions, void *stream);
+/* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab) */
+int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
+/* regenerate observations only (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148) */
+int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
+/* episode statistics accumulated on device since the last call: int64[16]
+ * {steps, success, collision, safety_human_raise, timeout, deviation_end_of_path, corridor_hit,
+ *  safety_corridor_raise, actuation_termination, mpc_retries, mpc_gave_up, orca_lp3, 4 spare} and
+ * double[4] {sum R, sum R_PT, sum R_HA, spare}; `reset` clears them. Feed to NCCL all-reduce. */
+int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream);
+
+const char *dre_strerror(int code);
+const char *dre_last_cuda_error(void);
+int dre_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRE_H */

@@ -1,0 +1,5 @@
+from . import _Anything
+
+
+def __getattr__(name):
+    return _Anything()

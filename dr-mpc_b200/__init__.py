@@ -1,0 +1,13 @@
+"""B200-native batched step engine for DR-MPC's hot path (ORCA human step + path-tracking MPC +
+the env step around them). Host side: Python mirror of the reference's interfaces over the C ABI of
+libdre.so (include/dre.h). No CPU fallback: importing works anywhere, calling needs the CUDA library."""
+from .config import EngineConfig
+from .orca import BatchedORCA
+from .mpc import BatchedMPC
+from . import paths
+try:
+    from .env import BatchedHAAndPTEnv
+except ImportError:   # env module not present in minimal builds
+    pass
+
+__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "paths"]

@@ -1,0 +1,230 @@
+// capi.cu -- extern "C" entry points of libdre.so for the ORCA pass and the MPC (include/dre.h).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "launch.cuh"
+
+static thread_local char g_cuda_err[512] = "";
+
+void dre_set_cuda_error(cudaError_t e, const char *file, int line)
+{
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+
+extern "C" const char *dre_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" const char *dre_strerror(int code)
+{
+    switch (code) {
+    case DRE_OK: return "ok";
+    case DRE_ERR_INVALID: return "invalid argument or unsupported size";
+    case DRE_ERR_CUDA: return "CUDA runtime error (see dre_last_cuda_error)";
+    case DRE_ERR_NOMEM: return "out of memory";
+    case DRE_ERR_STATE: return "call order violated";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int dre_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// ORCA
+// ------------------------------------------------------------------------------------------------
+extern "C" int dre_orca_predict(const dre_orca_params *p, int32_t E, int32_t Nh, const double *hpos, const float *hvel,
+                                const double *goal, const double *rpos, const uint8_t *is_static, float *vnew,
+                                dre_orca_stats *stats, void *stream)
+{
+    if (!p || !hpos || !hvel || !goal || !vnew || (p->robot_visible && !rpos)) return DRE_ERR_INVALID;
+    return dre_orca_launch(*p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, (cudaStream_t)stream);
+}
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? DRE_OK : DRE_ERR_NOMEM; }
+};
+}  // namespace
+
+extern "C" int dre_orca_predict_host(const dre_orca_params *p, int32_t E, int32_t Nh, const double *hpos, const float *hvel,
+                                     const double *goal, const double *rpos, const uint8_t *is_static, float *vnew,
+                                     dre_orca_stats *stats)
+{
+    if (!p || E <= 0 || Nh <= 0) return DRE_ERR_INVALID;
+    const size_t n = (size_t)E * Nh;
+    DevBuf dpos, dvel, dgoal, drp, dst, dv, dstats;
+    if (dpos.alloc(n * 16) || dvel.alloc(n * 8) || dgoal.alloc(n * 16) || drp.alloc((size_t)E * 16) || dv.alloc(n * 8)) return DRE_ERR_NOMEM;
+    if (is_static && dst.alloc(n)) return DRE_ERR_NOMEM;
+    if (stats && dstats.alloc(n * sizeof(dre_orca_stats))) return DRE_ERR_NOMEM;
+    cudaStream_t s = 0;
+    DRE_CUDA_TRY(cudaMemcpyAsync(dpos.p, hpos, n * 16, cudaMemcpyHostToDevice, s));
+    DRE_CUDA_TRY(cudaMemcpyAsync(dvel.p, hvel, n * 8, cudaMemcpyHostToDevice, s));
+    DRE_CUDA_TRY(cudaMemcpyAsync(dgoal.p, goal, n * 16, cudaMemcpyHostToDevice, s));
+    if (rpos) DRE_CUDA_TRY(cudaMemcpyAsync(drp.p, rpos, (size_t)E * 16, cudaMemcpyHostToDevice, s));
+    if (is_static) DRE_CUDA_TRY(cudaMemcpyAsync(dst.p, is_static, n, cudaMemcpyHostToDevice, s));
+    const int rc = dre_orca_launch(*p, E, Nh, (const double *)dpos.p, (const float *)dvel.p, (const double *)dgoal.p,
+                                   (const double *)drp.p, is_static ? (const uint8_t *)dst.p : nullptr, (float *)dv.p,
+                                   stats ? (dre_orca_stats *)dstats.p : nullptr, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaMemcpyAsync(vnew, dv.p, n * 8, cudaMemcpyDeviceToHost, s));
+    if (stats) DRE_CUDA_TRY(cudaMemcpyAsync(stats, dstats.p, n * sizeof(dre_orca_stats), cudaMemcpyDeviceToHost, s));
+    DRE_CUDA_TRY(cudaStreamSynchronize(s));
+    return DRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MPC
+// ------------------------------------------------------------------------------------------------
+struct dre_mpc {
+    dre_mpc_params prm;
+    MpcDeviceState st;
+    double *d_paths = nullptr;
+    int32_t *d_lens = nullptr;
+    // staging for the *_host entry point
+    int32_t *d_pid = nullptr;
+    double *d_interp = nullptr, *d_pose = nullptr, *d_ctrl = nullptr;
+    dre_mpc_status *d_status = nullptr;
+};
+
+extern "C" int dre_mpc_create(const dre_mpc_params *p, int32_t N, dre_mpc **out)
+{
+    if (!p || !out || N <= 0 || p->horizon < 1 || p->horizon > DRE_MAX_HORIZON) return DRE_ERR_INVALID;
+    if (!(p->time_step > 0) || !(p->v_max > 0) || !(p->w_max > 0) || !(p->node_separation > 0)) return DRE_ERR_INVALID;
+    dre_mpc *h = new (std::nothrow) dre_mpc();
+    if (!h) return DRE_ERR_NOMEM;
+    h->prm = *p;
+    if (h->prm.max_retries <= 0) h->prm.max_retries = 20;
+    if (h->prm.max_iterations <= 0) h->prm.max_iterations = 1500;
+    memset(&h->st, 0, sizeof h->st);
+    h->st.N = N; h->st.K = p->horizon;
+    const size_t K = (size_t)p->horizon;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&h->st.warm_T, K * N * 4 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&h->st.warm_u, K * N * 2 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&h->st.iteration0, (size_t)N)) != cudaSuccess ||
+        (e = cudaMemset(h->st.warm_T, 0, K * N * 4 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMemset(h->st.warm_u, 0, K * N * 2 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMemset(h->st.iteration0, 1, (size_t)N)) != cudaSuccess) {
+        dre_set_cuda_error(e, __FILE__, __LINE__);
+        dre_mpc_destroy(h);
+        return DRE_ERR_CUDA;
+    }
+    *out = h;
+    return DRE_OK;
+}
+
+extern "C" int dre_mpc_destroy(dre_mpc *h)
+{
+    if (!h) return DRE_OK;
+    cudaFree(h->st.warm_T); cudaFree(h->st.warm_u); cudaFree(h->st.iteration0);
+    cudaFree(h->d_paths); cudaFree(h->d_lens);
+    cudaFree(h->d_pid); cudaFree(h->d_interp); cudaFree(h->d_pose); cudaFree(h->d_ctrl); cudaFree(h->d_status);
+    delete h;
+    return DRE_OK;
+}
+
+extern "C" int dre_mpc_set_paths(dre_mpc *h, const double *paths_host, int32_t num_paths, int32_t path_stride,
+                                 const int32_t *lens_host)
+{
+    if (!h || !paths_host || !lens_host || num_paths <= 0 || path_stride <= 1) return DRE_ERR_INVALID;
+    for (int i = 0; i < num_paths; ++i)
+        if (lens_host[i] < 2 || lens_host[i] > path_stride) return DRE_ERR_INVALID;
+    cudaFree(h->d_paths); cudaFree(h->d_lens);
+    h->d_paths = nullptr; h->d_lens = nullptr;
+    const size_t nb = (size_t)num_paths * 3 * path_stride * sizeof(double);
+    DRE_CUDA_TRY(cudaMalloc(&h->d_paths, nb));
+    DRE_CUDA_TRY(cudaMalloc(&h->d_lens, (size_t)num_paths * sizeof(int32_t)));
+    DRE_CUDA_TRY(cudaMemcpy(h->d_paths, paths_host, nb, cudaMemcpyHostToDevice));
+    DRE_CUDA_TRY(cudaMemcpy(h->d_lens, lens_host, (size_t)num_paths * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->st.paths = h->d_paths; h->st.lens = h->d_lens; h->st.num_paths = num_paths; h->st.path_stride = path_stride;
+    return DRE_OK;
+}
+
+extern "C" int dre_mpc_reset(dre_mpc *h, const uint8_t *mask, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    return dre_mpc_reset_launch(h->st, mask, (cudaStream_t)stream);
+}
+
+extern "C" int dre_mpc_act(dre_mpc *h, const int32_t *path_id, const double *interp_index, const double *pose,
+                           double *controls, dre_mpc_status *status, void *stream)
+{
+    if (!h || !interp_index || !pose || !controls) return DRE_ERR_INVALID;
+    if (!h->st.paths) return DRE_ERR_STATE;
+    return dre_mpc_launch(h->prm, h->st, path_id, interp_index, pose, 3, controls, 2 * h->prm.horizon, 2 * h->prm.horizon,
+                          status, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dre_mpc_act_host(dre_mpc *h, const int32_t *path_id, const double *interp_index, const double *pose,
+                                double *controls, dre_mpc_status *status)
+{
+    if (!h || !interp_index || !pose || !controls) return DRE_ERR_INVALID;
+    if (!h->st.paths) return DRE_ERR_STATE;
+    const size_t N = (size_t)h->st.N, K2 = 2 * (size_t)h->prm.horizon;
+    if (!h->d_interp) {
+        DRE_CUDA_TRY(cudaMalloc(&h->d_pid, N * sizeof(int32_t)));
+        DRE_CUDA_TRY(cudaMalloc(&h->d_interp, N * sizeof(double)));
+        DRE_CUDA_TRY(cudaMalloc(&h->d_pose, N * 3 * sizeof(double)));
+        DRE_CUDA_TRY(cudaMalloc(&h->d_ctrl, N * K2 * sizeof(double)));
+        DRE_CUDA_TRY(cudaMalloc(&h->d_status, N * sizeof(dre_mpc_status)));
+    }
+    cudaStream_t s = 0;
+    if (path_id) DRE_CUDA_TRY(cudaMemcpyAsync(h->d_pid, path_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    DRE_CUDA_TRY(cudaMemcpyAsync(h->d_interp, interp_index, N * sizeof(double), cudaMemcpyHostToDevice, s));
+    DRE_CUDA_TRY(cudaMemcpyAsync(h->d_pose, pose, N * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    const int rc = dre_mpc_launch(h->prm, h->st, path_id ? h->d_pid : nullptr, h->d_interp, h->d_pose, 3, h->d_ctrl, (int)K2,
+                                  (int)K2, status ? h->d_status : nullptr, nullptr, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaMemcpyAsync(controls, h->d_ctrl, N * K2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (status) DRE_CUDA_TRY(cudaMemcpyAsync(status, h->d_status, N * sizeof(dre_mpc_status), cudaMemcpyDeviceToHost, s));
+    DRE_CUDA_TRY(cudaStreamSynchronize(s));
+    return DRE_OK;
+}
+
+// host views use the reference-like problem-major layout [N][K][*]; the device keeps [K][N][*]
+extern "C" int dre_mpc_get_warm(dre_mpc *h, double *warm_T, double *warm_u, uint8_t *iteration0)
+{
+    if (!h) return DRE_ERR_INVALID;
+    const size_t N = (size_t)h->st.N, K = (size_t)h->st.K;
+    DRE_CUDA_TRY(cudaDeviceSynchronize());
+    if (warm_T) {
+        std::vector<double> t(K * N * 4);
+        DRE_CUDA_TRY(cudaMemcpy(t.data(), h->st.warm_T, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < K; ++k)
+            for (size_t n = 0; n < N; ++n) memcpy(warm_T + (n * K + k) * 4, t.data() + (k * N + n) * 4, 4 * sizeof(double));
+    }
+    if (warm_u) {
+        std::vector<double> t(K * N * 2);
+        DRE_CUDA_TRY(cudaMemcpy(t.data(), h->st.warm_u, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < K; ++k)
+            for (size_t n = 0; n < N; ++n) memcpy(warm_u + (n * K + k) * 2, t.data() + (k * N + n) * 2, 2 * sizeof(double));
+    }
+    if (iteration0) DRE_CUDA_TRY(cudaMemcpy(iteration0, h->st.iteration0, N, cudaMemcpyDeviceToHost));
+    return DRE_OK;
+}
+
+extern "C" int dre_mpc_set_warm(dre_mpc *h, const double *warm_T, const double *warm_u, const uint8_t *iteration0)
+{
+    if (!h) return DRE_ERR_INVALID;
+    const size_t N = (size_t)h->st.N, K = (size_t)h->st.K;
+    DRE_CUDA_TRY(cudaDeviceSynchronize());
+    if (warm_T) {
+        std::vector<double> t(K * N * 4);
+        for (size_t k = 0; k < K; ++k)
+            for (size_t n = 0; n < N; ++n) memcpy(t.data() + (k * N + n) * 4, warm_T + (n * K + k) * 4, 4 * sizeof(double));
+        DRE_CUDA_TRY(cudaMemcpy(h->st.warm_T, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (warm_u) {
+        std::vector<double> t(K * N * 2);
+        for (size_t k = 0; k < K; ++k)
+            for (size_t n = 0; n < N; ++n) memcpy(t.data() + (k * N + n) * 2, warm_u + (n * K + k) * 2, 2 * sizeof(double));
+        DRE_CUDA_TRY(cudaMemcpy(h->st.warm_u, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (iteration0) DRE_CUDA_TRY(cudaMemcpy(h->st.iteration0, iteration0, N, cudaMemcpyHostToDevice));
+    return DRE_OK;
+}
+
+// accessors used by env_capi.cu
+const dre_mpc_params &dre_mpc_params_of(const dre_mpc *h) { return h->prm; }
+const MpcDeviceState &dre_mpc_state_of(const dre_mpc *h) { return h->st; }

@@ -1,0 +1,260 @@
+// env_capi.cu -- extern "C" entry points of the batched environment (include/dre.h: dre_env_*).
+// Replaces HAAndPTEnv.reset/step (reference environment/HA_and_PT/human_avoidance_and_path_tracking_env.py:243-416).
+#include <cstring>
+#include <new>
+#include <vector>
+#include "env_launch.cuh"
+
+struct dre_env {
+    dre_env_config cfg;
+    EnvDev D;
+    dre_mpc *mpc = nullptr;
+    void *state_block = nullptr;   // one allocation for the whole SoA state
+    void *slab = nullptr;          // one allocation for all outputs of a step
+    size_t slab_bytes = 0;
+    dre_step_out out;
+    double *d_actions = nullptr;   // staging for step_host
+    cudaStream_t own_stream = nullptr;
+    bool was_reset = false;
+};
+
+namespace {
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <class T> T *take(size_t n)
+    {
+        off = (off + 255) / 256 * 256;
+        T *p = base ? (T *)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+void carve_state(EnvDev &D, void *base, size_t &bytes)
+{
+    Carver c(base);
+    const size_t E = D.E, Nh = D.Nh, H = D.LB + 1, LB = D.LB;
+    D.hpos = c.take<double2>(E * Nh);
+    D.hvel = c.take<float2>(E * Nh);
+    D.hgoal = c.take<double2>(E * Nh);
+    D.hstatic = c.take<uint8_t>(E * Nh);
+    D.hhist = c.take<double2>(E * Nh * H);
+    D.hvalid = c.take<int32_t>(E * Nh);
+    D.rpose = c.take<double>(E * 4);
+    D.rprev = c.take<double>(E * 4);
+    D.rhist = c.take<double>(E * H * 4);
+    D.rpastv = c.take<double>(E * LB * 2);
+    D.rvalid = c.take<int32_t>(E);
+    D.gtime = c.take<double>(E);
+    D.path_idx = c.take<int32_t>(E);
+    D.loc_to_start = c.take<uint8_t>(E);
+    D.step_count = c.take<int64_t>(E);
+    D.reset_epoch = c.take<int32_t>(E);
+    D.mpc_interp = c.take<double>(E);
+    D.stat_counters = c.take<unsigned long long>(16);
+    D.stat_sums = c.take<double>(4);
+    bytes = (c.off + 255) / 256 * 256;
+}
+
+void carve_slab(const EnvDev &D, int n_mpc_act, void *base, dre_step_out &o, EnvOutDev &od, size_t &bytes)
+{
+    Carver c(base);
+    const size_t E = D.E, Nh = D.Nh, H = D.LB + 1, LB = D.LB;
+    o.pt_state = od.pt_state = c.take<double>(E * 4 * (D.lookahead + D.lookbehind));
+    o.mpc_actions = od.mpc_actions = c.take<double>(E * n_mpc_act);
+    o.robot_node = od.robot_node = c.take<double>(E * 2 * LB);
+    o.past_robot_vel = od.past_robot_vel = c.take<double>(E * 2 * LB);
+    o.percent_episode = od.percent_episode = c.take<double>(E);
+    o.spatial_edges = od.spatial_edges = c.take<double>(E * Nh * 2 * H);
+    o.human_valid = od.human_valid = c.take<double>(E * Nh);
+    o.detected_humans = od.detected_humans = c.take<double>(E);
+    o.rewards = od.rewards = c.take<double>(E * 3);
+    o.info = od.info = c.take<double>(E * 8);
+    o.done_bits = od.done_bits = c.take<uint32_t>(E);
+    o.mpc_status = od.mpc_status = c.take<dre_mpc_status>(E);
+    bytes = (c.off + 255) / 256 * 256;
+    o.slab = base;
+    o.slab_bytes = bytes;
+}
+
+int n_mpc_actions(const dre_env_config &c)
+{
+    const int a = c.mpc_actions_in_input > 0 ? c.mpc_actions_in_input : 4;
+    return 2 * (c.mpc.horizon < a ? c.mpc.horizon : a);
+}
+}  // namespace
+
+extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
+{
+    if (!cfg || !out) return DRE_ERR_INVALID;
+    if (cfg->num_envs <= 0 || cfg->num_humans <= 0 || cfg->num_humans > DRE_MAX_HUMANS || cfg->lookback < 1 || cfg->lookback > 32)
+        return DRE_ERR_INVALID;
+    if (cfg->lookahead + cfg->lookbehind <= 0 || !(cfg->time_step > 0)) return DRE_ERR_INVALID;
+    dre_env *h = new (std::nothrow) dre_env();
+    if (!h) return DRE_ERR_NOMEM;
+    h->cfg = *cfg;
+    EnvDev &D = h->D;
+    memset(&D, 0, sizeof D);
+    D.E = cfg->num_envs; D.Nh = cfg->num_humans; D.LB = cfg->lookback;
+    D.orca = cfg->orca;
+    D.dt = cfg->time_step; D.time_limit = cfg->time_limit; D.human_radius = cfg->human_radius; D.robot_radius = cfg->robot_radius;
+    D.circle_radius = cfg->circle_radius; D.circle_radius_humans = cfg->circle_radius_humans;
+    D.end_goal_changing = cfg->end_goal_changing;
+    D.collision_penalty = cfg->collision_penalty; D.safety_dist = cfg->safety_dist; D.safety_penalty = cfg->safety_penalty;
+    D.dist_radius = cfg->disturbance_radius; D.dist_factor_v = cfg->disturbance_factor_v; D.dist_factor_th = cfg->disturbance_factor_th;
+    D.act_min_vel = cfg->actuation_min_vel; D.act_penalty = cfg->actuation_penalty;
+    D.pt_overall_scaling = cfg->pt_overall_scaling; D.goal_radius = cfg->goal_radius; D.goal_angle = cfg->goal_angle;
+    D.goal_reward = cfg->goal_reward; D.path_adv_scaling = cfg->path_advancement_scaling; D.dev_xy = cfg->deviation_xy;
+    D.dev_th = cfg->deviation_th; D.dev_scale = cfg->deviation_scale; D.corridor_penalty = cfg->corridor_penalty;
+    D.corridor_max_dev = cfg->corridor_max_dev; D.eop_penalty = cfg->end_of_path_penalty;
+    D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
+    D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
+    D.seed = cfg->seed; D.env_id_offset = cfg->env_id_offset;
+
+    int rc = dre_mpc_create(&cfg->mpc, cfg->num_envs, &h->mpc);
+    if (rc) { delete h; return rc; }
+    size_t sbytes = 0, obytes = 0;
+    carve_state(D, nullptr, sbytes);
+    EnvOutDev od;
+    carve_slab(D, n_mpc_actions(*cfg), nullptr, h->out, od, obytes);
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->state_block, sbytes)) != cudaSuccess || (e = cudaMemset(h->state_block, 0, sbytes)) != cudaSuccess ||
+        (e = cudaMalloc(&h->slab, obytes)) != cudaSuccess || (e = cudaMemset(h->slab, 0, obytes)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_actions, (size_t)D.E * 2 * sizeof(double))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        dre_set_cuda_error(e, __FILE__, __LINE__);
+        dre_env_destroy(h);
+        return DRE_ERR_CUDA;
+    }
+    carve_state(D, h->state_block, sbytes);
+    carve_slab(D, n_mpc_actions(*cfg), h->slab, h->out, D.out, obytes);
+    h->slab_bytes = obytes;
+    D.mpc_iteration0 = dre_mpc_state_of(h->mpc).iteration0;
+    *out = h;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_destroy(dre_env *h)
+{
+    if (!h) return DRE_OK;
+    cudaDeviceSynchronize();
+    dre_mpc_destroy(h->mpc);
+    cudaFree(h->state_block); cudaFree(h->slab); cudaFree(h->d_actions);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_set_paths(dre_env *h, const double *paths_host, int32_t num_paths, int32_t path_stride, const int32_t *lens_host)
+{
+    if (!h) return DRE_ERR_INVALID;
+    const int rc = dre_mpc_set_paths(h->mpc, paths_host, num_paths, path_stride, lens_host);
+    if (rc) return rc;
+    const MpcDeviceState &st = dre_mpc_state_of(h->mpc);
+    h->D.paths = st.paths; h->D.lens = st.lens; h->D.num_paths = st.num_paths; h->D.path_stride = st.path_stride;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_state(dre_env *h, dre_env_state_view *v)
+{
+    if (!h || !v) return DRE_ERR_INVALID;
+    const EnvDev &D = h->D;
+    v->hpos = (double *)D.hpos; v->hvel = (float *)D.hvel; v->hgoal = (double *)D.hgoal; v->hstatic = D.hstatic;
+    v->hhist = (double *)D.hhist; v->hvalid = D.hvalid; v->rpose = D.rpose; v->rprev = D.rprev; v->rhist = D.rhist;
+    v->rpastv = D.rpastv; v->rvalid = D.rvalid; v->gtime = D.gtime; v->path_idx = D.path_idx; v->loc_to_start = D.loc_to_start;
+    v->step_count = D.step_count;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_outputs(dre_env *h, dre_step_out *out)
+{
+    if (!h || !out) return DRE_ERR_INVALID;
+    *out = h->out;
+    return DRE_OK;
+}
+
+extern "C" dre_mpc *dre_env_mpc(dre_env *h) { return h ? h->mpc : nullptr; }
+
+static int env_solve_mpc(dre_env *h, cudaStream_t s)
+{
+    const EnvDev &D = h->D;
+    const int nact = n_mpc_actions(h->cfg);
+    int rc = dre_mpc_launch(dre_mpc_params_of(h->mpc), dre_mpc_state_of(h->mpc), D.path_idx, D.mpc_interp, D.rpose, 4,
+                            D.out.mpc_actions, nact, nact, D.out.mpc_status, nullptr, s);
+    if (rc) return rc;
+    return dre_env_launch_mpc_stats(D, s);
+}
+
+extern "C" int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (!h->D.paths) return DRE_ERR_STATE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = dre_env_launch_ha(h->D, 2, 1, s);
+    if (rc) return rc;
+    rc = dre_env_launch_pt(h->D, 1, s);
+    if (rc) return rc;
+    return solve_mpc ? env_solve_mpc(h, s) : DRE_OK;
+}
+
+extern "C" int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (!h->D.paths) return DRE_ERR_STATE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = dre_env_launch_reset(h->D, hpos_init, hgoal_init, s);
+    if (rc) return rc;
+    // S_PT = PT_env.reset(...) incl. the first MPC solve (HA_and_PT env.py:268)
+    rc = dre_env_launch_pt(h->D, 1, s);
+    if (rc) return rc;
+    rc = env_solve_mpc(h, s);
+    if (rc) return rc;
+    // HA_env.reset + warm_start(lookback) (HA_and_PT env.py:274-276)
+    for (int w = 0; w < h->D.LB; ++w) {
+        rc = dre_env_launch_ha(h->D, 1, w == h->D.LB - 1 ? 1 : 0, s);
+        if (rc) return rc;
+    }
+    h->was_reset = true;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
+{
+    if (!h || !actions) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    cudaStream_t s = (cudaStream_t)stream;
+    EnvDev D = h->D;
+    D.actions = actions;
+    int rc = dre_env_launch_ha(D, 0, 1, s);
+    if (rc) return rc;
+    rc = dre_env_launch_pt(D, 0, s);
+    if (rc) return rc;
+    return env_solve_mpc(h, s);
+}
+
+extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host)
+{
+    if (!h || !actions_host || !slab_host) return DRE_ERR_INVALID;
+    cudaStream_t s = h->own_stream;
+    DRE_CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)h->D.E * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    const int rc = dre_env_step(h, h->d_actions, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaMemcpyAsync(slab_host, h->slab, h->slab_bytes, cudaMemcpyDeviceToHost, s));
+    DRE_CUDA_TRY(cudaStreamSynchronize(s));
+    return DRE_OK;
+}
+
+extern "C" int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (counters_dev16) DRE_CUDA_TRY(cudaMemcpyAsync(counters_dev16, h->D.stat_counters, 16 * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    if (sums_dev4) DRE_CUDA_TRY(cudaMemcpyAsync(sums_dev4, h->D.stat_sums, 4 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (reset) {
+        DRE_CUDA_TRY(cudaMemsetAsync(h->D.stat_counters, 0, 16 * sizeof(int64_t), s));
+        DRE_CUDA_TRY(cudaMemsetAsync(h->D.stat_sums, 0, 4 * sizeof(double), s));
+    }
+    return DRE_OK;
+}

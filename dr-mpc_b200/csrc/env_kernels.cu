@@ -1,0 +1,587 @@
+// env_kernels.cu -- the batched env step around the ORCA pass and the MPC solve.
+// Compile with -fmad=false (bit-faithful fp32 ORCA, once-rounded fp64 env arithmetic).
+//
+//   ha_step_kernel : HAEnv.step / warm_start (reference human_avoidance_env.py:128-186, 79-125) for EPB envs per CTA:
+//                    ORCA pass 1 -> robot unicycle + human Euler integration -> history roll -> ORCA pass 2
+//                    (disturbance look-ahead, :245) -> collision / safety / disturbance / actuation rewards (:189-291)
+//                    -> observation (:24-77) -> goal resampling (:181-184, crowd_sim.py:114-144 with Philox).
+//                    The env's agents live in a shared-memory fp32 SoA tile for both ORCA passes.
+//   pt_step_kernel : PTEnv.step (path_tracking_env.py:80-101): 5 intermediate poses, 2 localisations, PT rewards
+//                    (reward_comp.py:20-116), optional path switch (HA_and_PT env.py:130-141), PT state
+//                    (path_tracking_core.py:94-145), merge of rewards / dones (HA_and_PT env.py:311-416), episode stats.
+//   env_reset_kernel : reset_continuous_task (HA_and_PT env.py:263-280) + HAEnv.reset (:297-338) + spawning
+//                    (crowd_sim.py:232-262 with Philox).
+#include "orca_device.cuh"
+#include "env_device.cuh"
+#include "env_launch.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory layout of ha_step_kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct HaLayout {
+    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, bytes;
+};
+static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
+{
+    HaLayout l;
+    size_t o = 0;
+    l.off_lines = o;  o += (size_t)NG * 2 * nA * sizeof(OLine);
+    l.off_pos = o;    o += (size_t)EPB * Nh * sizeof(double2);          // new human positions (fp64)
+    l.off_pen = o;    o += (size_t)EPB * Nh * 3 * sizeof(double);       // pen_v, pen_th, closest_dist per human
+    l.off_agents = o; o += (size_t)EPB * 5 * nA * sizeof(float);
+    l.off_dist = o;   o += (size_t)NG * nA * sizeof(float);
+    l.off_vnew = o;   o += (size_t)EPB * Nh * sizeof(float2);
+    l.off_flags = o;  o += (size_t)EPB * 4 * sizeof(int);
+    l.bytes = (o + 15) / 16 * 16;
+    return l;
+}
+
+template <int G>
+__device__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
+                               const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
+                               bool pos_from_smem, unsigned long long *lp3_count)
+{
+    const int Nh = D.Nh;
+    OLine *L = lines + (size_t)gi * 2 * nA;
+    float *sd = dist + (size_t)gi * nA;
+    const float invTH = 1.0f / D.orca.time_horizon, invDt = 1.0f / D.orca.time_step;
+    const int maxNb = D.orca.max_neighbors > 0 ? D.orca.max_neighbors : nA - 1;
+    for (int ag = gi; ag < EPB * Nh; ag += NG) {
+        const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
+        if (e >= D.E) break;
+        const size_t gidx = (size_t)e * Nh + i;
+        float ox = 0.f, oy = 0.f;
+        if (!D.hstatic[gidx]) {
+            const double2 P = pos_from_smem ? posd[el * Nh + i] : D.hpos[gidx];
+            const double2 Gl = D.hgoal[gidx];
+            const double dx = Gl.x - P.x, dy = Gl.y - P.y;
+            const double speed = sqrt(dx * dx + dy * dy);
+            double pvx = dx, pvy = dy;
+            if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
+            const float *A = agents + (size_t)el * 5 * nA;
+            dre_orca_stats st;
+            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+                             D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy,
+                             lp3_count ? &st : nullptr);
+            if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1ull);
+        }
+        if (g.rank() == 0) vout[el * Nh + i] = make_float2(ox, oy);
+        g.sync();
+    }
+}
+
+// mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
+template <int G>
+__global__ void __launch_bounds__(512)
+ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0), H = D.LB + 1;
+    const int NG = blockDim.x / G;
+    OLine *lines = reinterpret_cast<OLine *>(smem_raw + lay.off_lines);
+    double2 *posd = reinterpret_cast<double2 *>(smem_raw + lay.off_pos);
+    double *pen = reinterpret_cast<double *>(smem_raw + lay.off_pen);
+    float *agents = reinterpret_cast<float *>(smem_raw + lay.off_agents);
+    float *dist = reinterpret_cast<float *>(smem_raw + lay.off_dist);
+    float2 *vnew = reinterpret_cast<float2 *>(smem_raw + lay.off_vnew);
+    int *flags = reinterpret_cast<int *>(smem_raw + lay.off_flags);
+    const int env0 = blockIdx.x * EPB;
+    const double dt = D.dt;
+
+    cg::thread_block blk = cg::this_thread_block();
+    TileGroup<G> g(cg::tiled_partition<G>(blk));
+    const int gi = threadIdx.x / G;
+
+    if (mode != 2) {
+        // ---- stage tile ----
+        for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
+            const int el = t / nA, a = t - el * nA, e = env0 + el;
+            float *A = agents + (size_t)el * 5 * nA;
+            float x = 0.f, y = 0.f, vx = 0.f, vy = 0.f;
+            if (e < D.E) {
+                if (a < Nh) {
+                    const double2 q = D.hpos[(size_t)e * Nh + a];
+                    const float2 v = D.hvel[(size_t)e * Nh + a];
+                    x = (float)q.x; y = (float)q.y; vx = v.x; vy = v.y;
+                } else {
+                    x = (float)D.rpose[(size_t)e * 4]; y = (float)D.rpose[(size_t)e * 4 + 1];
+                }
+            }
+            A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = D.orca.radius;
+        }
+        for (int t = threadIdx.x; t < EPB * 4; t += blockDim.x) flags[t] = 0;
+        __syncthreads();
+
+        // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
+        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false, D.stat_counters ? D.stat_counters + 11 : nullptr);
+        __syncthreads();
+
+        // ---- integrate: robot (unicycle, agent.py:169-176) and humans (Euler, agent.py:164-168); histories ----
+        for (int t = threadIdx.x; t < EPB * (Nh + 1); t += blockDim.x) {
+            const int el = t / (Nh + 1), a = t - el * (Nh + 1), e = env0 + el;
+            if (e >= D.E) continue;
+            if (a < Nh) {
+                const size_t gidx = (size_t)e * Nh + a;
+                const double2 q = D.hpos[gidx];
+                const float2 v = vnew[el * Nh + a];
+                double2 np_;
+                np_.x = q.x + (double)v.x * dt;
+                np_.y = q.y + (double)v.y * dt;
+                D.hpos[gidx] = np_;
+                D.hvel[gidx] = v;
+                posd[el * Nh + a] = np_;
+                float *A = agents + (size_t)el * 5 * nA;
+                A[a] = (float)np_.x; A[nA + a] = (float)np_.y; A[2 * nA + a] = v.x; A[3 * nA + a] = v.y;
+                // history roll (human_avoidance_env.py:149-158 / :92-100)
+                double2 *hh = D.hhist + gidx * H;
+                const int valid = D.hvalid[gidx];
+                if (valid == H) {
+                    for (int s = 0; s < H - 1; ++s) hh[s] = hh[s + 1];
+                    hh[H - 1] = np_;
+                } else {
+                    hh[valid] = np_;
+                    D.hvalid[gidx] = valid + 1 < H ? valid + 1 : H;
+                }
+            } else {
+                double *rp = D.rpose + (size_t)e * 4;
+                double av = 0.0, aw = 0.0;
+                if (mode == 0) {
+                    av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1];
+                    double nx, ny, nth;
+                    D.rprev[(size_t)e * 4] = rp[0]; D.rprev[(size_t)e * 4 + 1] = rp[1]; D.rprev[(size_t)e * 4 + 2] = rp[2];
+                    unicycle_step(rp[0], rp[1], rp[2], av, aw, dt, nx, ny, nth);
+                    rp[0] = nx; rp[1] = ny; rp[2] = nth;
+                    if (D.orca.robot_visible) {
+                        float *A = agents + (size_t)el * 5 * nA;
+                        A[Nh] = (float)nx; A[nA + Nh] = (float)ny;
+                    }
+                    D.gtime[e] += dt;
+                    D.step_count[e] += 1;
+                }
+                // robot history (human_avoidance_env.py:133-141 / :114-122)
+                double *rh = D.rhist + (size_t)e * H * 4;
+                double *pv = D.rpastv + (size_t)e * D.LB * 2;
+                const int valid = D.rvalid[e];
+                if (valid == H) {
+                    for (int s = 0; s < (H - 1) * 4; ++s) rh[s] = rh[s + 4];
+                    rh[(H - 1) * 4] = rp[0]; rh[(H - 1) * 4 + 1] = rp[1]; rh[(H - 1) * 4 + 2] = rp[2];
+                    for (int s = 0; s < (D.LB - 1) * 2; ++s) pv[s] = pv[s + 2];
+                    pv[(D.LB - 1) * 2] = av; pv[(D.LB - 1) * 2 + 1] = aw;
+                } else {
+                    rh[valid * 4] = rp[0]; rh[valid * 4 + 1] = rp[1]; rh[valid * 4 + 2] = rp[2];
+                    if (valid - 1 >= 0 && valid - 1 < D.LB) { pv[(valid - 1) * 2] = av; pv[(valid - 1) * 2 + 1] = aw; }
+                    D.rvalid[e] = valid + 1 < H ? valid + 1 : H;
+                }
+            }
+        }
+        __syncthreads();
+
+        if (mode == 0) {
+            // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
+            float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
+            orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr);
+            __syncthreads();
+
+            // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
+            for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+                const int el = t / Nh, i = t - el * Nh, e = env0 + el;
+                if (e >= D.E) continue;
+                const double2 hp = posd[el * Nh + i];
+                const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
+                const double dx = hp.x - rx, dy = hp.y - ry;
+                const double closest = sqrt(dx * dx + dy * dy) - D.human_radius - D.robot_radius;
+                double pv_ = 0.0, pth_ = 0.0;
+                if (!D.hstatic[(size_t)e * Nh + i] && !(closest > D.dist_radius || closest <= 0.0)) {
+                    const float *A = agents + (size_t)el * 5 * nA;
+                    const double cvx = (double)A[2 * nA + i], cvy = (double)A[3 * nA + i];
+                    const double fvx = (double)vnext[el * Nh + i].x, fvy = (double)vnext[el * Nh + i].y;
+                    const double curr_v = sqrt(cvx * cvx + cvy * cvy), fut_v = sqrt(fvx * fvx + fvy * fvy);
+                    const double curr_th = atan2(cvy, cvx), fut_th = atan2(fvy, fvx);
+                    const double dvm = fut_v - curr_v;
+                    const double pen_v_i = D.dist_factor_v * (dvm < 0.0 ? dvm : 0.0);
+                    const double th_diff = wrap_pi(fut_th - curr_th);
+                    const double pen_th_i = -D.dist_factor_th * fabs(th_diff);
+                    const double scaling = 1.0 - closest / D.dist_radius;
+                    pv_ = pen_v_i * scaling; pth_ = pen_th_i * scaling;
+                }
+                pen[(el * Nh + i) * 3] = pv_; pen[(el * Nh + i) * 3 + 1] = pth_; pen[(el * Nh + i) * 3 + 2] = closest;
+            }
+            __syncthreads();
+
+            // ---- per-env reward / done (one thread per env sums in human order, like the reference loop) ----
+            for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
+                const int e = env0 + el;
+                if (e >= D.E) continue;
+                double dmin = INFINITY, pen_v = 0.0, pen_th = 0.0;
+                bool collision = false;
+                for (int i = 0; i < Nh; ++i) {
+                    const double c = pen[(el * Nh + i) * 3 + 2];
+                    if (c <= 0.0) collision = true;
+                    else if (c < dmin) dmin = c;
+                    pen_v += pen[(el * Nh + i) * 3]; pen_th += pen[(el * Nh + i) * 3 + 1];
+                }
+                if (collision) dmin = 0.0;
+                double reward = 0.0;
+                uint32_t bits = 0;
+                if (collision) { reward += D.collision_penalty; bits |= DRE_DONE_COLLISION | DRE_DONE_HA; }
+                if (dmin < D.safety_dist) { reward += D.safety_penalty; bits |= DRE_DONE_SAFETY_HUMAN | DRE_DONE_HA; }
+                reward += (pen_v + pen_th);
+                double total_v = 0.0;
+                const double *pv = D.rpastv + (size_t)e * D.LB * 2;
+                for (int s = 0; s < D.LB; ++s) total_v += fabs(pv[s * 2]);
+                if (total_v < D.act_min_vel) { reward += D.act_penalty; bits |= DRE_DONE_ACTUATION | DRE_DONE_HA; }
+                D.out.rewards[(size_t)e * 3 + 1] = reward;
+                D.out.info[(size_t)e * 8 + 0] = pen_v; D.out.info[(size_t)e * 8 + 1] = pen_th; D.out.info[(size_t)e * 8 + 4] = dmin;
+                D.out.done_bits[e] = bits;
+            }
+        }
+    }
+
+    // ---- observation (human_avoidance_env.py:24-77), frame = 'robot' ----
+    if (write_obs) {
+        if (mode != 2) __syncthreads();
+        const int W = 2 * H;
+        for (int t = threadIdx.x; t < EPB * Nh * H; t += blockDim.x) {
+            const int el = t / (Nh * H), r = t - el * Nh * H, i = r / H, s = r - i * H, e = env0 + el;
+            if (e >= D.E) continue;
+            double st, ct;
+            sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
+            const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
+            const double2 q = D.hhist[((size_t)e * Nh + i) * H + s];
+            const double dx = q.x - rx, dy = q.y - ry;
+            double *o = D.out.spatial_edges + ((size_t)e * Nh + i) * W + 2 * s;
+            o[0] = ct * dx + st * dy;
+            o[1] = -st * dx + ct * dy;
+        }
+        for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+            const int el = t / Nh, i = t - el * Nh, e = env0 + el;
+            if (e >= D.E) continue;
+            D.out.human_valid[(size_t)e * Nh + i] = (double)D.hvalid[(size_t)e * Nh + i];
+        }
+        for (int t = threadIdx.x; t < EPB * D.LB; t += blockDim.x) {
+            const int el = t / D.LB, s = t - el * D.LB, e = env0 + el;
+            if (e >= D.E) continue;
+            double st, ct;
+            sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
+            const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
+            const double *rh = D.rhist + ((size_t)e * H + s) * 4;
+            const double dx = rh[0] - rx, dy = rh[1] - ry;
+            D.out.robot_node[(size_t)e * 2 * D.LB + 2 * s] = ct * dx + st * dy;
+            D.out.robot_node[(size_t)e * 2 * D.LB + 2 * s + 1] = -st * dx + ct * dy;
+            D.out.past_robot_vel[(size_t)e * 2 * D.LB + 2 * s] = D.rpastv[((size_t)e * D.LB + s) * 2];
+            D.out.past_robot_vel[(size_t)e * 2 * D.LB + 2 * s + 1] = D.rpastv[((size_t)e * D.LB + s) * 2 + 1];
+        }
+        for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
+            const int e = env0 + el;
+            if (e >= D.E) continue;
+            D.out.percent_episode[e] = D.gtime[e] / D.time_limit * 10.0 - 5.0;
+            D.out.detected_humans[e] = (double)Nh;
+        }
+    }
+
+    // ---- goal resampling for humans that reached their goal (human_avoidance_env.py:181-184 / :109-112) ----
+    if (mode != 2 && D.end_goal_changing) {
+        for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+            const int el = t / Nh, i = t - el * Nh, e = env0 + el;
+            if (e >= D.E || D.hstatic[(size_t)e * Nh + i]) continue;
+            const double2 p = posd[el * Nh + i], gl = D.hgoal[(size_t)e * Nh + i];
+            const double dx = gl.x - p.x, dy = gl.y - p.y;
+            if (sqrt(dx * dx + dy * dy) < D.human_radius) atomicOr(&flags[el * 4], 1);
+        }
+        __syncthreads();
+        for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
+            const int e = env0 + el;
+            if (e >= D.E || !flags[el * 4]) continue;
+            const uint64_t gid = (uint64_t)(D.env_id_offset + e);
+            const uint64_t stp = (uint64_t)D.step_count[e] + ((uint64_t)D.reset_epoch[e] << 20) + (mode == 1 ? (1ull << 19) + (uint64_t)D.rvalid[e] : 0ull);
+            const double rgx = 0.0, rgy = D.circle_radius;   // robot goal, HA_and_PT env.py:293-299
+            const double rpx = D.rpose[(size_t)e * 4], rpy = D.rpose[(size_t)e * 4 + 1];
+            for (int i = 0; i < Nh; ++i) {
+                if (D.hstatic[(size_t)e * Nh + i]) continue;
+                const double2 p = posd[el * Nh + i];
+                double2 gl = D.hgoal[(size_t)e * Nh + i];
+                const double ddx = gl.x - p.x, ddy = gl.y - p.y;
+                if (!(sqrt(ddx * ddx + ddy * ddy) < D.human_radius)) continue;
+                const double md_r = D.human_radius + D.robot_radius + 0.2, md_h = D.human_radius + D.human_radius + 0.2;
+                double gx = gl.x, gy = gl.y;
+                for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
+                    double u0, u1, u2, u3;
+                    env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt, u0, u1);
+                    env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt + 1, u2, u3);
+                    const double angle = u0 * DRE_PI * 2.0;
+                    double sa, ca;
+                    sincos(angle, &sa, &ca);
+                    gx = D.circle_radius_humans * ca + (u1 - 0.5);
+                    gy = D.circle_radius_humans * sa + (u2 - 0.5);
+                    bool collide = false;
+                    {
+                        const double a = gx - rgx, b = gy - rgy, c = gx - rpx, d = gy - rpy;
+                        if (sqrt(a * a + b * b) < md_r || sqrt(c * c + d * d) < md_r) collide = true;
+                    }
+                    for (int j = 0; j < Nh && !collide; ++j) {
+                        if (j == i) continue;
+                        const double2 op = posd[el * Nh + j], og = D.hgoal[(size_t)e * Nh + j];
+                        const double a = gx - og.x, b = gy - og.y, c = gx - op.x, d = gy - op.y;
+                        if (sqrt(a * a + b * b) < md_h || sqrt(c * c + d * d) < md_h) collide = true;
+                    }
+                    if (!collide) break;
+                }
+                D.hgoal[(size_t)e * Nh + i] = make_double2(gx, gy);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PT step: one thread per env
+// ---------------------------------------------------------------------------------------------------------------
+// mode 0: step; mode 1: observe only (reset / soft reset: localise + state, no rewards)
+__global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cnt[10];
+    double sums[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < 10; ++i) cnt[i] = 0;
+    if (e < D.E) {
+        int pid = D.path_idx[e];
+        PathView P = path_view(D.paths, D.path_stride, pid, D.lens);
+        const double cx = D.rpose[(size_t)e * 4], cy = D.rpose[(size_t)e * 4 + 1], cth = D.rpose[(size_t)e * 4 + 2];
+        bool lts = D.loc_to_start[e] != 0;
+        Localization cur;
+        if (mode == 0) {
+            const double px = D.rprev[(size_t)e * 4], py = D.rprev[(size_t)e * 4 + 1], pth = D.rprev[(size_t)e * 4 + 2];
+            const double av = D.actions[(size_t)e * 2], aw = D.actions[(size_t)e * 2 + 1];
+            const Localization prv = localize_on_path(P, px, py, lts);
+            cur = localize_on_path(P, cx, cy, lts);
+            if (cur.index >= (double)(P.L / 3) && cur.index < (double)(2 * P.L / 3)) lts = false;
+            // ---- rewards in strategy order (config_PT.py:12; reward_comp.py:20-32), each scaled by overall_scaling ----
+            double reward = 0.0;
+            uint32_t bits = 0;
+            const double sc = D.pt_overall_scaling;
+            {   // goal (reward_comp.py:34-54)
+                const double gx = P.x[P.L - 1], gy = P.y[P.L - 1], gth = P.th[P.L - 1];
+                bool hit = false;
+                for (int i = 1; i <= 5; ++i) {
+                    double qx, qy, qth;
+                    unicycle_step(px, py, pth, av, aw, D.dt * (double)i / 5.0, qx, qy, qth);
+                    const double ddx = qx - gx, ddy = qy - gy;
+                    const double ad = fabs(np_mod(qth - gth + DRE_PI, 2.0 * DRE_PI) - DRE_PI);
+                    if (sqrt(ddx * ddx + ddy * ddy) < D.goal_radius && ad < D.goal_angle) hit = true;
+                }
+                if (hit) { reward += sc * D.goal_reward; bits |= DRE_DONE_GOAL | DRE_DONE_PT; }
+                else reward += sc * 0.0;
+            }
+            double adv;
+            {   // path_advancement (reward_comp.py:101-116)
+                double pi_ = prv.index, ci_ = cur.index;
+                if (fabs(ci_ - pi_) > 10.0) {
+                    const double half = (double)(P.L / 2);
+                    pi_ = np_mod(pi_ + half, (double)P.L);
+                    ci_ = np_mod(ci_ + half, (double)P.L);
+                }
+                adv = sc * (D.path_adv_scaling * (ci_ - pi_));
+                reward += adv;
+            }
+            const double ddx = cx - cur.ix, ddy = cy - cur.iy;
+            const double xy_dev = sqrt(ddx * ddx + ddy * ddy);
+            double devr;
+            {   // deviation (reward_comp.py:89-99)
+                const double th_dev = np_mod(cth - cur.ith + DRE_PI, 2.0 * DRE_PI) - DRE_PI;
+                const double th_reward = -D.dev_th * fabs(th_dev);
+                const double xy_reward = -xy_dev * D.dev_xy;
+                devr = sc * ((xy_reward + th_reward) * D.dev_scale);
+                reward += devr;
+            }
+            if (P.L - 1 == (int)prv.index) { reward += sc * D.eop_penalty; bits |= DRE_DONE_END_OF_PATH | DRE_DONE_PT; }
+            else reward += sc * 0.0;
+            if (D.corridor_max_dev < xy_dev) { reward += sc * D.corridor_penalty; bits |= DRE_DONE_CORRIDOR_HIT | DRE_DONE_PT; }
+            else reward += sc * 0.0;
+            if (D.safety_corridor_max_dev < xy_dev) { reward += sc * D.safety_corridor_penalty; bits |= DRE_DONE_SAFETY_CORRIDOR | DRE_DONE_PT; }
+            else reward += sc * 0.0;
+            // ---- merge with the HA part (HA_and_PT env.py:322-331, 391-414) ----
+            const double r_ha = D.out.rewards[(size_t)e * 3 + 1];
+            uint32_t all = D.out.done_bits[e] | bits;
+            if (all & (DRE_DONE_HA | DRE_DONE_PT)) all |= DRE_DONE_ANY | DRE_DONE_FOR_REPLAY;
+            D.out.rewards[(size_t)e * 3] = reward;
+            D.out.rewards[(size_t)e * 3 + 2] = reward + r_ha;
+            D.out.done_bits[e] = all;
+            D.out.info[(size_t)e * 8 + 2] = adv; D.out.info[(size_t)e * 8 + 3] = devr;
+            D.out.info[(size_t)e * 8 + 5] = cur.index; D.out.info[(size_t)e * 8 + 6] = xy_dev; D.out.info[(size_t)e * 8 + 7] = prv.index;
+            cnt[0] = 1;
+            cnt[1] = (all & DRE_DONE_GOAL) ? 1 : 0; cnt[2] = (all & DRE_DONE_COLLISION) ? 1 : 0;
+            cnt[3] = (all & DRE_DONE_SAFETY_HUMAN) ? 1 : 0; cnt[4] = (all & DRE_DONE_TIMEOUT) ? 1 : 0;
+            cnt[5] = (all & DRE_DONE_END_OF_PATH) ? 1 : 0; cnt[6] = (all & DRE_DONE_CORRIDOR_HIT) ? 1 : 0;
+            cnt[7] = (all & DRE_DONE_SAFETY_CORRIDOR) ? 1 : 0; cnt[8] = (all & DRE_DONE_ACTUATION) ? 1 : 0;
+            sums[0] = reward + r_ha; sums[1] = reward; sums[2] = r_ha;
+            // ---- path switch on goal / end of path (what soft_reset does, HA_and_PT env.py:130-141) ----
+            if (D.auto_path_switch && (bits & (DRE_DONE_GOAL | DRE_DONE_END_OF_PATH))) {
+                pid = (pid + 1) % D.num_paths;
+                D.path_idx[e] = pid;
+                lts = true;
+                D.mpc_iteration0[e] = 1;
+                P = path_view(D.paths, D.path_stride, pid, D.lens);
+                cur = localize_on_path(P, cx, cy, lts);
+            }
+            D.loc_to_start[e] = lts ? 1 : 0;
+        } else {
+            cur = localize_on_path(P, cx, cy, lts);
+        }
+        pt_state_gen(P, cx, cy, cth, cur.index, D.lookahead, D.lookbehind, D.out.pt_state + (size_t)e * (4 * (D.lookahead + D.lookbehind)), 1);
+        D.mpc_interp[e] = cur.index;
+    }
+    if (mode == 0 && D.stat_counters) {
+        // block reduction of the episode statistics, then one atomic per counter per CTA
+        __shared__ unsigned long long s_cnt[9];
+        __shared__ double s_sum[3];
+        if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0;
+        if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
+        __syncthreads();
+        for (int i = 0; i < 9; ++i) {
+            unsigned long long v = cnt[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[i], v);
+        }
+        for (int i = 0; i < 3; ++i) {
+            double v = sums[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[i], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < 9 && s_cnt[threadIdx.x]) atomicAdd(D.stat_counters + threadIdx.x, s_cnt[threadIdx.x]);
+        if (threadIdx.x < 3) atomicAdd(D.stat_sums + threadIdx.x, s_sum[threadIdx.x]);
+    }
+}
+
+// MPC retry / give-up statistics after the solve
+__global__ void mpc_stats_kernel(EnvDev D)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long r = 0, gup = 0;
+    if (e < D.E) { r = (unsigned long long)D.out.mpc_status[e].retries; gup = D.out.mpc_status[e].term < 0 ? 1 : 0; }
+    for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); gup += __shfl_xor_sync(0xffffffffu, gup, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (r) atomicAdd(D.stat_counters + 9, r);
+        if (gup) atomicAdd(D.stat_counters + 10, gup);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset: one thread per env
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 *hpos_init, const double2 *hgoal_init)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D.E) return;
+    const int Nh = D.Nh, H = D.LB + 1;
+    const double rx = 0.0, ry = -D.circle_radius, rth = DRE_PI;   // set_robot_reset(start_angle=pi), HA_and_PT env.py:264,286-299
+    double *rp = D.rpose + (size_t)e * 4;
+    rp[0] = rx; rp[1] = ry; rp[2] = rth; rp[3] = 0.0;
+    double *rv = D.rprev + (size_t)e * 4;
+    rv[0] = rx; rv[1] = ry; rv[2] = rth; rv[3] = 0.0;
+    for (int s = 0; s < H; ++s) {
+        double *rh = D.rhist + ((size_t)e * H + s) * 4;
+        rh[0] = rx; rh[1] = ry; rh[2] = rth; rh[3] = 0.0;
+    }
+    for (int s = 0; s < D.LB * 2; ++s) D.rpastv[(size_t)e * D.LB * 2 + s] = 0.0;
+    D.rvalid[e] = 1;
+    D.gtime[e] = 0.0;
+    D.step_count[e] = 0;
+    D.reset_epoch[e] += 1;
+    D.path_idx[e] = 0;
+    D.loc_to_start[e] = 1;
+    D.mpc_iteration0[e] = 1;
+    const uint64_t gid = (uint64_t)(D.env_id_offset + e);
+    const uint64_t stp = ((uint64_t)D.reset_epoch[e] << 20) + (1ull << 18);
+    for (int i = 0; i < Nh; ++i) {
+        const size_t gidx = (size_t)e * Nh + i;
+        double px, py, gx, gy;
+        if (hpos_init) {
+            px = hpos_init[gidx].x; py = hpos_init[gidx].y;
+            gx = hgoal_init ? hgoal_init[gidx].x : -px; gy = hgoal_init ? hgoal_init[gidx].y : -py;
+        } else {
+            // generate_circle_crossing_human (crowd_sim.py:232-262)
+            px = 0.0; py = 0.0;
+            for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
+                double u0, u1, u2, u3;
+                env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt, u0, u1);
+                env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt + 1, u2, u3);
+                double sa, ca;
+                sincos(u0 * DRE_PI * 2.0, &sa, &ca);
+                px = D.circle_radius_humans * ca + u1 * 1.0;
+                py = D.circle_radius_humans * sa + u2 * 1.0;
+                bool collide = false;
+                {
+                    const double a = px - rx, b = py - ry;
+                    if (sqrt(a * a + b * b) < D.human_radius + D.robot_radius + 0.5) collide = true;
+                }
+                for (int j = 0; j < i && !collide; ++j) {
+                    const double2 q = D.hpos[(size_t)e * Nh + j];
+                    const double a = px - q.x, b = py - q.y;
+                    if (sqrt(a * a + b * b) < D.human_radius + D.human_radius + 0.2) collide = true;
+                }
+                if (!collide) break;
+            }
+            gx = -px; gy = -py;
+        }
+        D.hpos[gidx] = make_double2(px, py);
+        D.hgoal[gidx] = make_double2(gx, gy);
+        D.hvel[gidx] = make_float2(0.f, 0.f);
+        D.hvalid[gidx] = 1;
+        for (int s = 0; s < H; ++s) D.hhist[gidx * H + s] = make_double2(px, py);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
+{
+    const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
+    const int per_env = Nh * G;
+    int EPB = per_env >= 384 ? 1 : 384 / per_env;
+    if (EPB > D.E) EPB = D.E;
+    int threads = (EPB * per_env + 31) / 32 * 32;
+    if (threads > 512) threads = 512;
+    if (threads < 64) threads = 64;
+    const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
+    auto kern = ha_step_kernel<G>;
+    if (lay.bytes > 48 * 1024) {
+        if (lay.bytes > 220 * 1024) return DRE_ERR_INVALID;
+        DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    }
+    kern<<<(D.E + EPB - 1) / EPB, threads, lay.bytes, s>>>(D, EPB, mode, write_obs, lay);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
+{
+    switch (dre_orca_pick_group(D.orca, D.Nh)) {
+    case 8: return launch_ha<8>(D, mode, write_obs, s);
+    case 16: return launch_ha<16>(D, mode, write_obs, s);
+    default: return launch_ha<32>(D, mode, write_obs, s);
+    }
+}
+
+int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s)
+{
+    pt_step_kernel<<<(D.E + 63) / 64, 64, 0, s>>>(D, mode);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s)
+{
+    if (!D.stat_counters) return DRE_OK;
+    mpc_stats_kernel<<<(D.E + 255) / 256, 256, 0, s>>>(D);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s)
+{
+    env_reset_kernel<<<(D.E + 127) / 128, 128, 0, s>>>(D, (const double2 *)hpos_init, (const double2 *)hgoal_init);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}

@@ -1,0 +1,61 @@
+// env_launch.cuh -- the env's device-side view (all pointers into HBM) shared by env_kernels.cu and env_capi.cu.
+#pragma once
+#include "launch.cuh"
+
+struct EnvOutDev {
+    double *pt_state, *mpc_actions, *robot_node, *past_robot_vel, *percent_episode, *spatial_edges, *human_valid,
+        *detected_humans, *rewards, *info;
+    uint32_t *done_bits;
+    dre_mpc_status *mpc_status;
+};
+
+struct EnvDev {
+    int E, Nh, LB;
+    dre_orca_params orca;
+    double dt, time_limit, human_radius, robot_radius, circle_radius, circle_radius_humans;
+    int end_goal_changing;
+    double collision_penalty, safety_dist, safety_penalty, dist_radius, dist_factor_v, dist_factor_th, act_min_vel, act_penalty;
+    double pt_overall_scaling, goal_radius, goal_angle, goal_reward, path_adv_scaling, dev_xy, dev_th, dev_scale;
+    double corridor_penalty, corridor_max_dev, eop_penalty, safety_corridor_penalty, safety_corridor_max_dev;
+    int lookahead, lookbehind, auto_path_switch;
+    uint64_t seed;
+    int64_t env_id_offset;
+    // ---- state (structure of arrays, env-major) ----
+    double2 *hpos;      // [E][Nh]
+    float2 *hvel;       // [E][Nh]
+    double2 *hgoal;     // [E][Nh]
+    uint8_t *hstatic;   // [E][Nh]
+    double2 *hhist;     // [E][Nh][LB+1]
+    int32_t *hvalid;    // [E][Nh]
+    double *rpose;      // [E][4]
+    double *rprev;      // [E][4]
+    double *rhist;      // [E][LB+1][4]
+    double *rpastv;     // [E][LB][2]
+    int32_t *rvalid;    // [E]
+    double *gtime;      // [E]
+    int32_t *path_idx;  // [E]
+    uint8_t *loc_to_start;  // [E]
+    int64_t *step_count;    // [E]
+    int32_t *reset_epoch;   // [E]
+    double *mpc_interp;     // [E]
+    uint8_t *mpc_iteration0; // [E] (aliases the MPC object's flags)
+    // ---- paths ----
+    const double *paths;
+    const int32_t *lens;
+    int num_paths, path_stride;
+    // ---- per-step input / output ----
+    const double *actions;  // [E][2]
+    EnvOutDev out;
+    unsigned long long *stat_counters;  // [16]
+    double *stat_sums;                  // [4]
+};
+
+int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s);
+int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s);
+int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s);
+int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s);
+
+// capi.cu accessors
+struct dre_mpc;
+const dre_mpc_params &dre_mpc_params_of(const dre_mpc *h);
+const MpcDeviceState &dre_mpc_state_of(const dre_mpc *h);

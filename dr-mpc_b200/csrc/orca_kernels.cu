@@ -26,7 +26,7 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
 }
 
 template <int G>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__restrict__ hpos,
                     const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
                     const double2 *__restrict__ rpos, const uint8_t *__restrict__ is_static,
@@ -101,7 +101,7 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
     if (EPB > E) EPB = E;
     int threads = EPB * per_env;
     threads = (threads + 31) / 32 * 32;
-    if (threads > 1024) threads = 1024;
+    if (threads > 512) threads = 512;
     const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);
     auto kern = orca_predict_kernel<G>;
     if (l.bytes > 48 * 1024) {

@@ -1,0 +1,201 @@
+"""Batched combined environment: mirrors reference
+environment/HA_and_PT/human_avoidance_and_path_tracking_env.py (`HAAndPTEnv(config_master, seed_addition)`,
+`.reset() -> S`, `.step(action) -> (S', reward_return, done_return, info, eps_done_info)`) for E envs at once.
+
+Same names and dict keys as the reference; every value carries a leading batch dim E instead of 1 and is a
+torch CUDA tensor that views the engine's output slab in HBM (no copy), ready for a batched actor/critic.
+"""
+import ctypes
+import numpy as np
+from . import _lib
+from .config import EngineConfig
+from .paths import continuous_task_paths, pack_paths
+from .mpc import MPC_STATUS_DTYPE
+
+DONE_BITS = {'collision': 1 << 0, 'safety_human_raise': 1 << 1, 'actuation_termination': 1 << 2, 'timeout': 1 << 3,
+             'goal': 1 << 4, 'deviation_end_of_path': 1 << 5, 'corridor_hit': 1 << 6, 'safety_corridor_raise': 1 << 7,
+             'done_HA': 1 << 16, 'done_PT': 1 << 17, 'done': 1 << 18, 'done_for_replay': 1 << 19}
+STAT_NAMES = ['steps', 'success', 'collision', 'safety_human_raise', 'timeout', 'deviation_end_of_path', 'corridor_hit',
+              'safety_corridor_raise', 'actuation_termination', 'mpc_retries', 'mpc_gave_up', 'orca_lp3']
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view engine-owned HBM without copying."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+_TYPESTR = {"f8": "<f8", "f4": "<f4", "i4": "<i4", "u4": "<u4", "u1": "|u1", "i8": "<i8"}
+
+
+def _view(ptr, shape, kind, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape, _TYPESTR[kind]), device=device)
+
+
+class BatchedHAAndPTEnv:
+    def __init__(self, config_master=None, num_envs=None, seed_addition=0, device="cuda:0", **overrides):
+        import torch
+        if isinstance(config_master, EngineConfig):
+            cfg = config_master
+            for k, v in overrides.items():
+                setattr(cfg, k, v)
+            self.config_master = None
+        elif config_master is not None:
+            cfg = EngineConfig.from_config_master(config_master, **overrides)
+            self.config_master = config_master
+        else:
+            cfg = EngineConfig(**overrides)
+            self.config_master = None
+        if num_envs is not None:
+            cfg.num_envs = int(num_envs)
+        cfg.seed = (cfg.seed + seed_addition) & 0xFFFFFFFFFFFFFFFF
+        self.cfg = cfg
+        self.E, self.Nh, self.K, self.LB = cfg.num_envs, cfg.num_humans, cfg.horizon, cfg.lookback
+        self.device = torch.device(device)
+        self.time_step = cfg.time_step
+        self._L = _lib.load()
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)   # make sure the primary context exists before the library allocates
+        h = ctypes.c_void_p()
+        c = cfg.env_config()
+        _lib.check(self._L.dre_env_create(ctypes.byref(c), ctypes.byref(h)))
+        self._h = h
+        self.paths = continuous_task_paths(cfg.circle_radius, cfg.time_step, cfg.node_separation)
+        tab, lens = pack_paths(self.paths)
+        _lib.check(self._L.dre_env_set_paths(self._h, tab.ctypes.data_as(ctypes.c_void_p), tab.shape[0], tab.shape[2],
+                                             lens.ctypes.data_as(ctypes.c_void_p)))
+        self._bind_views()
+        self._host_slab = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._L is not None:
+            self._L.dre_env_destroy(self._h)
+            self._h = None
+
+    # ---- zero-copy views ----
+    def _bind_views(self):
+        E, Nh, LB, H = self.E, self.Nh, self.LB, self.LB + 1
+        d = self.device
+        o = _lib.StepOut()
+        _lib.check(self._L.dre_env_outputs(self._h, ctypes.byref(o)))
+        self._out = o
+        self.slab_bytes = int(o.slab_bytes)
+        nact = 2 * min(self.K, self.cfg.actions_in_input)
+        npt = 4 * (self.cfg.lookahead + self.cfg.lookbehind)
+        self._layout = [("pt_state", o.pt_state, (E, npt), "f8"), ("mpc_actions", o.mpc_actions, (E, nact), "f8"),
+                        ("robot_node", o.robot_node, (E, 2 * LB), "f8"), ("past_robot_vel", o.past_robot_vel, (E, 2 * LB), "f8"),
+                        ("percent_episode", o.percent_episode, (E, 1), "f8"),
+                        ("spatial_edges", o.spatial_edges, (E, Nh, 2 * H), "f8"), ("human_valid", o.human_valid, (E, Nh), "f8"),
+                        ("detected_humans", o.detected_humans, (E,), "f8"), ("rewards", o.rewards, (E, 3), "f8"),
+                        ("info", o.info, (E, 8), "f8"), ("done_bits", o.done_bits, (E,), "i4"),
+                        ("mpc_status", o.mpc_status, (E, 8), "i4")]
+        self.out = {name: _view(ptr, shape, kind, d) for name, ptr, shape, kind in self._layout}
+        s = _lib.EnvStateView()
+        _lib.check(self._L.dre_env_state(self._h, ctypes.byref(s)))
+        self.state = {
+            "hpos": _view(s.hpos, (E, Nh, 2), "f8", d), "hvel": _view(s.hvel, (E, Nh, 2), "f4", d),
+            "hgoal": _view(s.hgoal, (E, Nh, 2), "f8", d), "hstatic": _view(s.hstatic, (E, Nh), "u1", d),
+            "hhist": _view(s.hhist, (E, Nh, H, 2), "f8", d), "hvalid": _view(s.hvalid, (E, Nh), "i4", d),
+            "rpose": _view(s.rpose, (E, 4), "f8", d), "rprev": _view(s.rprev, (E, 4), "f8", d),
+            "rhist": _view(s.rhist, (E, H, 4), "f8", d), "rpastv": _view(s.rpastv, (E, LB, 2), "f8", d),
+            "rvalid": _view(s.rvalid, (E,), "i4", d), "gtime": _view(s.gtime, (E,), "f8", d),
+            "path_idx": _view(s.path_idx, (E,), "i4", d), "loc_to_start": _view(s.loc_to_start, (E,), "u1", d),
+            "step_count": _view(s.step_count, (E,), "i8", d),
+        }
+
+    def _stream(self):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs(self):
+        o = self.out
+        return {'PT': {'PT_state': o["pt_state"], 'MPC_actions': o["mpc_actions"]},
+                'HA': {'robot_node': o["robot_node"], 'past_robot_velocities': o["past_robot_vel"],
+                       'percent_episode': o["percent_episode"], 'spatial_edges': o["spatial_edges"],
+                       'detected_human_num': o["detected_humans"], 'human_valid_history': o["human_valid"]}}
+
+    # ---- reference interface ----
+    def reset(self, hpos_init=None, hgoal_init=None):
+        """HAAndPTEnv.reset (env.py:243-280). Optional [E,Nh,2] float64 CUDA tensors replace the device-side spawning."""
+        p = ctypes.c_void_p(hpos_init.contiguous().data_ptr()) if hpos_init is not None else None
+        g = ctypes.c_void_p(hgoal_init.contiguous().data_ptr()) if hgoal_init is not None else None
+        _lib.check(self._L.dre_env_reset(self._h, p, g, self._stream()))
+        return self._obs()
+
+    def step(self, action, update=True, soft_reset=False, model_info=None):
+        """HAAndPTEnv.step (env.py:305-416). `action`: [E,2] float64 CUDA tensor of (v, w)."""
+        import torch
+        a = action.to(device=self.device, dtype=torch.float64).contiguous()
+        _lib.check(self._L.dre_env_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()))
+        return self._package()
+
+    def _package(self):
+        o = self.out
+        bits = o["done_bits"]
+        r = o["rewards"]
+        reward_return = {'R_PT': r[:, 0], 'R_DO': r[:, 1], 'R': r[:, 2]}
+        done_return = {k: (bits & DONE_BITS[k]) != 0 for k in ('done_PT', 'done_HA', 'done', 'done_for_replay')}
+        info = {'done_bits': bits, 'disturbance_v': o["info"][:, 0], 'disturbance_th': o["info"][:, 1],
+                'path_advancement': o["info"][:, 2], 'deviation': o["info"][:, 3], 'dmin': o["info"][:, 4],
+                'interp_index': o["info"][:, 5], 'xy_dev': o["info"][:, 6], 'mpc_status': o["mpc_status"]}
+        eps_done_info = {'success': (bits & DONE_BITS['goal']) != 0}
+        for k in ('collision', 'safety_human_raise', 'timeout', 'deviation_end_of_path', 'corridor_hit',
+                  'safety_corridor_raise', 'actuation_termination'):
+            eps_done_info[k] = (bits & DONE_BITS[k]) != 0
+        return self._obs(), reward_return, done_return, info, eps_done_info
+
+    def observe(self, solve_mpc=False):
+        """Regenerate S from the current state (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148)."""
+        _lib.check(self._L.dre_env_observe(self._h, int(solve_mpc), self._stream()))
+        return self._obs()
+
+    # ---- host-buffer entry point (end-to-end drop-in for a CPU-side caller) ----
+    def step_host(self, actions_np):
+        """actions: numpy [E,2] float64 (pinned for best speed) -> dict of numpy views into one pinned host slab."""
+        import torch
+        if self._host_slab is None:
+            self._host_slab = torch.empty(self.slab_bytes, dtype=torch.uint8).pin_memory()
+            base = self._host_slab.numpy()
+            self._host_views = {}
+            for name, ptr, shape, kind in self._layout:
+                off = int(ptr) - int(self._out.slab)
+                n = int(np.prod(shape))
+                dt = np.dtype(_TYPESTR[kind])
+                self._host_views[name] = base[off:off + n * dt.itemsize].view(dt).reshape(shape)
+        a = np.ascontiguousarray(actions_np, dtype=np.float64)
+        _lib.check(self._L.dre_env_step_host(self._h, a.ctypes.data_as(ctypes.c_void_p),
+                                             ctypes.c_void_p(self._host_slab.data_ptr())))
+        return self._host_views
+
+    def stats(self, reset=False):
+        """Episode statistics accumulated on device -> (int64[16], float64[4]) CUDA tensors (feed to all_reduce)."""
+        import torch
+        c = torch.zeros(16, dtype=torch.int64, device=self.device)
+        s = torch.zeros(4, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.dre_env_stats(self._h, ctypes.c_void_p(c.data_ptr()), ctypes.c_void_p(s.data_ptr()), int(reset),
+                                         self._stream()))
+        return c, s
+
+    @property
+    def MPC(self):
+        return self
+
+    def mpc_get_warm(self):
+        T = np.empty((self.E, self.K, 4)); u = np.empty((self.E, self.K, 2)); it0 = np.empty(self.E, dtype=np.uint8)
+        m = self._L.dre_env_mpc(self._h)
+        _lib.check(self._L.dre_mpc_get_warm(m, T.ctypes.data_as(ctypes.c_void_p), u.ctypes.data_as(ctypes.c_void_p),
+                                            it0.ctypes.data_as(ctypes.c_void_p)))
+        return T, u, it0
+
+    def mpc_set_warm(self, T=None, u=None, it0=None):
+        m = self._L.dre_env_mpc(self._h)
+        f = lambda a, dt: np.ascontiguousarray(a, dtype=dt).ctypes.data_as(ctypes.c_void_p) if a is not None else None
+        T_, u_, i_ = (np.ascontiguousarray(T, dtype=np.float64) if T is not None else None,
+                      np.ascontiguousarray(u, dtype=np.float64) if u is not None else None,
+                      np.ascontiguousarray(it0, dtype=np.uint8) if it0 is not None else None)
+        _lib.check(self._L.dre_mpc_set_warm(m, T_.ctypes.data_as(ctypes.c_void_p) if T_ is not None else None,
+                                            u_.ctypes.data_as(ctypes.c_void_p) if u_ is not None else None,
+                                            i_.ctypes.data_as(ctypes.c_void_p) if i_ is not None else None))

@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the reference's OWN, UNMODIFIED Python
+(/root/reference: scripts/policy/orca.py, environment/path_tracking/utils/mpc.py, pysteam_augmented/*, the env
+classes) on the API shims in oracle/shims. Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The GPU box never runs this; it only reads the committed fixtures.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("DRE_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, REF)
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+def _config(num_humans=6):
+    from scripts.configs import ConfigMaster
+    cm = ConfigMaster()
+    cm.config_HA.sim.human_num = num_humans
+    cm.config_HA.sim.max_allowable_humans = num_humans
+    return cm
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 1. ORCA: CrowdSim.get_human_actions on hand-built crowds (crowd_sim.py:264-284 -> human.py:16-25 -> orca.py:64-117)
+# ------------------------------------------------------------------------------------------------------------
+def golden_orca():
+    from environment.human_avoidance.human_avoidance_env import HAEnv
+    from environment.human_avoidance.utils.human import Human
+    rng = np.random.default_rng(20241019)
+    out = {}
+    for Nh, spread, C in ((1, 2.0, 24), (6, 3.0, 48), (6, 1.2, 48), (10, 4.0, 32), (10, 1.8, 32), (20, 5.0, 24),
+                          (20, 2.5, 24), (50, 8.0, 8), (50, 4.5, 8)):
+        cm = _config(Nh)
+        env = HAEnv()
+        env.configure(cm, cm.config_HA)
+        hpos = np.zeros((C, Nh, 2)); hvel = np.zeros((C, Nh, 2), dtype=np.float32); goal = np.zeros((C, Nh, 2))
+        rpos = np.zeros((C, 2)); vnew = np.zeros((C, Nh, 2), dtype=np.float32)
+        for c in range(C):
+            ang = rng.uniform(0, 2 * np.pi, Nh); rad = spread * np.sqrt(rng.uniform(0, 1, Nh))
+            P = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+            V = (rng.uniform(-1, 1, (Nh, 2)) * rng.uniform(0, 1, (Nh, 1))).astype(np.float32)
+            if c % 4 == 0:
+                G = P + rng.uniform(-0.6, 0.6, (Nh, 2))          # goal closer than 1 m: un-normalised pref velocity
+            elif c % 4 == 1:
+                G = -P                                           # circle crossing
+            else:
+                G = rng.uniform(-6, 6, (Nh, 2))
+            if c % 5 == 0 and Nh >= 2:
+                P[1] = P[0] + np.array([0.5, 0.1])               # overlapping pair -> collision branch
+            if c % 7 == 0 and Nh >= 3:
+                V[:] = 0                                         # everybody at rest
+            R = rng.uniform(-spread, spread, 2)
+            env.robot.set(R[0], R[1], 0, 4, 0, 0, 0.3)
+            env.humans = []
+            for i in range(Nh):
+                h = Human(cm.config_HA, 'humans')
+                h.set(P[i, 0], P[i, 1], G[i, 0], G[i, 1], float(V[i, 0]), float(V[i, 1]), 0)
+                env.humans.append(h)
+            acts = env.get_human_actions()
+            hpos[c], hvel[c], goal[c], rpos[c] = P, V, G, R
+            vnew[c] = np.array([[a.vx, a.vy] for a in acts], dtype=np.float32)
+        key = f"n{Nh}_s{spread}"
+        out[key + "_hpos"], out[key + "_hvel"], out[key + "_goal"], out[key + "_rpos"], out[key + "_vnew"] = hpos, hvel, goal, rpos, vnew
+    np.savez_compressed(os.path.join(OUT, "orca_crowds.npz"), **out)
+    print("orca_crowds.npz", {k: v.shape for k, v in out.items() if k.endswith("_vnew")})
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 2. MPC: MPC.act sequences (mpc.py:58-206) along the four continuous-task paths
+# ------------------------------------------------------------------------------------------------------------
+def _warm_of(mpc, K):
+    """(warm_T [K,4] = c,s,x,y of the stored inverse poses, warm_u [K,2], iteration0) before an act() call."""
+    T = np.zeros((K, 4)); u = np.zeros((K, 2))
+    if not mpc.iteration0 and mpc.next_se3_state_vars != 0:
+        for k in range(K):
+            M = mpc.next_se3_state_vars[k].value.matrix()
+            T[k] = [M[0, 0], M[1, 0], M[0, 3], M[1, 3]]
+            u[k] = mpc.next_vspace_state_vars[k].value[:, 0]
+    return T, u, int(mpc.iteration0)
+
+
+def golden_mpc():
+    from environment.path_tracking.utils.mpc import MPC
+    from environment.path_tracking.path_tracking_env import PTEnv
+    from environment.path_tracking.utils import RewardComputationPT, Unicycle
+    from pysteam.pysteam.solver import solver as SV
+    SV.TRACE = []
+    cm = _config()
+    pt = PTEnv(cm, RewardComputationPT(cm.config_PT.rewards, True))
+    pt.reset(np.array([0, -4.0, np.pi]))
+    out = {f"path{i}": p for i, p in enumerate(pt.paths)}
+    for K, steps in ((4, 70), (10, 24)):
+        rec = {k: [] for k in ("path_id", "interp", "pose", "warm_T", "warm_u", "it0", "u", "iters", "cost")}
+        for pid in range(4):
+            mpc = MPC(cm, K, 0.25, True, 1.0, 1.0)
+            rng = np.random.default_rng(100 * K + pid)
+            path = pt.paths[pid]
+            pose = path[:, 0] + np.array([0.1, -0.2, 0.15])
+            for step in range(steps):
+                if step == steps // 2:
+                    mpc.reset()                                       # iteration0 again mid-sequence
+                    pose = pose + np.array([0.25, 0.2, -0.3])
+                _, interp_idx, _ = pt.localize_on_path(pt.kd_trees[pid], pose[:2], path, localize_to_start=(step < 20))
+                wT, wu, it0 = _warm_of(mpc, K)
+                SV.TRACE.clear()
+                u = mpc.act({'path': path, 'interp_index': interp_idx, 'pose': pose})
+                rec["path_id"].append(pid); rec["interp"].append(float(interp_idx)); rec["pose"].append(pose.copy())
+                rec["warm_T"].append(wT); rec["warm_u"].append(wu); rec["it0"].append(it0); rec["u"].append(u.copy())
+                rec["iters"].append(SV.TRACE[-1][0]); rec["cost"].append(SV.TRACE[-1][1])
+                a = u[:2] + rng.normal(0, 0.05, 2)
+                a[0] = np.clip(a[0], 0, 1); a[1] = np.clip(a[1], -1, 1)
+                pose = Unicycle.step_external(pose, a, 0.25)
+        for k, v in rec.items():
+            out[f"K{K}_{k}"] = np.array(v)
+    SV.TRACE = None
+    np.savez_compressed(os.path.join(OUT, "mpc_sequences.npz"), **out)
+    print("mpc_sequences.npz", {k: v.shape for k, v in out.items() if k.endswith("_u")})
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 3. Full env: HAAndPTEnv.reset/step (HA_and_PT env.py:243-416) teacher-forcing fixtures
+# ------------------------------------------------------------------------------------------------------------
+def _snapshot(env, K):
+    ha, pt, mpc = env.HA_env, env.PT_env, env.MPC
+    Nh = len(ha.humans)
+    s = {
+        "hpos": np.array([[h.px, h.py] for h in ha.humans]), "hvel": np.array([[h.vx, h.vy] for h in ha.humans], dtype=np.float32),
+        "hgoal": np.array([[h.gx, h.gy] for h in ha.humans]),
+        "hhist": ha.human_history_global.copy(), "hvalid": ha.human_valid_history[:Nh].astype(np.int32),
+        "rpose": np.array([env.robot.px, env.robot.py, env.robot.theta, 0.0]),
+        "rprev": np.concatenate([env.prev_robot_pose, [0.0]]),
+        "rhist": np.concatenate([ha.robot_pose_history_global, np.zeros((ha.lookback + 1, 1))], 1),
+        "rpastv": ha.robot_past_velocities.copy(), "rvalid": np.int32(ha.robot_valid_history),
+        "gtime": np.float64(ha.global_time), "path_idx": np.int32(pt.path_idx), "loc_to_start": np.uint8(pt.localize_to_start),
+    }
+    s["warm_T"], s["warm_u"], s["it0"] = _warm_of(mpc, K)
+    return s
+
+
+def _flatten_S(S):
+    return {"pt_state": S['PT']['PT_state'][0], "mpc_actions": S['PT']['MPC_actions'][0], "robot_node": S['HA']['robot_node'][0],
+            "past_robot_vel": S['HA']['past_robot_velocities'][0], "percent_episode": S['HA']['percent_episode'][0],
+            "spatial_edges": S['HA']['spatial_edges'][0], "human_valid": S['HA']['human_valid_history'][0],
+            "detected_humans": np.float64(S['HA']['detected_human_num'][0])}
+
+
+_BITS = {'collision': 1 << 0, 'safety_human_raise': 1 << 1, 'actuation_termination': 1 << 2, 'timeout': 1 << 3,
+         'goal': 1 << 4, 'deviation_end_of_path': 1 << 5, 'corridor_hit': 1 << 6, 'safety_corridor_raise': 1 << 7}
+
+
+def golden_env():
+    from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
+    from environment.human_avoidance.utils.action import ActionRot
+    out = {}
+    for tag, Nh, seed, steps in (("h6", 6, 0, 260), ("h10", 10, 1, 90), ("h20", 20, 2, 50)):
+        cm = _config(Nh)
+        env = HAAndPTEnv(cm, seed_addition=seed)
+        env.case_counter['train'] = seed
+        K = cm.config_PT.MPC.planning_horizon
+        S = env.reset()
+        rng = np.random.default_rng(seed)
+        rec_pre, rec_post, rec_out = [], [], []
+        out[f"{tag}_reset_hpos"] = None
+        # the spawn (needed to replay reset() on the device): positions/goals before warm start are not kept by the
+        # reference, so re-run the spawning with the same seed
+        np.random.seed(seed)
+        env2 = HAAndPTEnv(cm, seed_addition=seed)
+        env2.case_counter['train'] = seed
+        env2.config_HA.sim.warm_start = False
+        S2 = env2.reset()
+        env2.config_HA.sim.warm_start = True
+        out[f"{tag}_reset_hpos"] = np.array([[h.px, h.py] for h in env2.HA_env.humans])
+        out[f"{tag}_reset_hgoal"] = np.array([[h.gx, h.gy] for h in env2.HA_env.humans])
+        for k, v in _flatten_S(S).items():
+            out[f"{tag}_reset_{k}"] = np.asarray(v)
+        post_reset = _snapshot(env, K)
+        for k, v in post_reset.items():
+            out[f"{tag}_postreset_{k}"] = np.asarray(v)
+        done_return, info = {'done': False}, None
+        n = 0
+        while n < steps:
+            if done_return['done']:
+                S = env.soft_reset(done_return, info, S)
+                if S is None:
+                    break
+            a = np.array(S['PT']['MPC_actions'][0, :2], dtype=np.float64)
+            # perturb the MPC action now and then so that the robot meets humans, leaves the corridor, stalls ...
+            phase = (n // 15) % 4
+            if phase == 1:
+                a = a + rng.normal(0, 0.3, 2)
+            elif phase == 3 and Nh == 6:
+                a = np.array([0.0, 0.0]) if (n // 5) % 2 else a * 0.3
+            a[0] = float(np.clip(a[0], 0, 1)); a[1] = float(np.clip(a[1], -1, 1))
+            pre = _snapshot(env, K)
+            S, R, D, info, eps = env.step(ActionRot(a[0], a[1]))
+            done_return = D
+            post = _snapshot(env, K)
+            bits = sum(b for name, b in _BITS.items() if name in info['done'])
+            o = _flatten_S(S)
+            o.update({"action": a, "rewards": np.array([R['R_PT'], R['R_DO'], R['R']]), "bits": np.int64(bits),
+                      "done_PT": np.uint8(D['done_PT']), "done_HA": np.uint8(D['done_HA']),
+                      "disturbance_v": np.float64(info['disturbance_v']), "disturbance_th": np.float64(info['disturbance_th']),
+                      "path_advancement": np.float64(info['path_advancement']), "deviation": np.float64(info['deviation'])})
+            rec_pre.append(pre); rec_post.append(post); rec_out.append(o)
+            n += 1
+        for name, rec in (("pre", rec_pre), ("post", rec_post), ("out", rec_out)):
+            for k in rec[0]:
+                out[f"{tag}_{name}_{k}"] = np.stack([np.asarray(r[k]) for r in rec])
+        allbits = out[f"{tag}_out_bits"]
+        print(tag, "steps", len(rec_pre), "done events", {k: int(((allbits & b) != 0).sum()) for k, b in _BITS.items()})
+    np.savez_compressed(os.path.join(OUT, "env_rollouts.npz"), **out)
+    print("env_rollouts.npz", os.path.getsize(os.path.join(OUT, "env_rollouts.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["orca", "mpc", "env"]
+    if "orca" in which:
+        golden_orca()
+    if "mpc" in which:
+        golden_mpc()
+    if "env" in which:
+        golden_env()

@@ -1,0 +1,153 @@
+"""GPU parity of the full env step: every recorded transition of the reference's own HAAndPTEnv.step (run unmodified on
+the shims, tests/golden/env_rollouts.npz) is replayed as ONE env of a batch: upload the reference's pre-step state,
+step once on the device, compare observations / rewards / done reasons / post-step state (teacher forcing).
+Tolerances: fp32 human velocities bit-exact; fp64 positions 1e-12; observations / rewards 1e-9; MPC controls 1e-6
+(LM-branch divergences counted)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TAGS = [("h6", 6), ("h10", 10), ("h20", 20)]
+
+
+def _make_env(Nh, E, **kw):
+    import dr_mpc_b200 as d
+    return d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, **kw), num_envs=E)
+
+
+def _upload(env, g, tag, prefix, sel=slice(None)):
+    import torch
+    dev = env.device
+    for name in ("hpos", "hvel", "hgoal", "hhist", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime", "path_idx", "loc_to_start"):
+        a = g[f"{tag}_{prefix}_{name}"][sel]
+        env.state[name].copy_(torch.as_tensor(np.ascontiguousarray(a), device=dev).reshape(env.state[name].shape))
+    env.state["hstatic"].zero_()
+    env.mpc_set_warm(g[f"{tag}_{prefix}_warm_T"][sel], g[f"{tag}_{prefix}_warm_u"][sel], g[f"{tag}_{prefix}_it0"][sel].astype(np.uint8))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("tag,Nh", TAGS)
+def test_step_matches_reference_teacher_forced(golden_env, tag, Nh):
+    import torch
+    g = golden_env
+    T = g[f"{tag}_out_action"].shape[0]
+    env = _make_env(Nh, T, auto_path_switch=False)
+    env.reset()                                   # allocates / arms the engine; state is overwritten below
+    _upload(env, g, tag, "pre")
+    S, R, D, info, eps = env.step(torch.as_tensor(g[f"{tag}_out_action"], device=env.device))
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in env.out.items()}
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    # --- human step: fp32 velocities bit-exact, fp64 positions exact-ish ---
+    assert np.array_equal(st["hvel"].view(np.uint32), g[f"{tag}_post_hvel"].view(np.uint32))
+    assert np.abs(st["hpos"] - g[f"{tag}_post_hpos"]).max() <= 1e-12
+    assert np.abs(st["hhist"] - g[f"{tag}_post_hhist"]).max() <= 1e-12
+    assert np.array_equal(st["hvalid"], g[f"{tag}_post_hvalid"])
+    # --- robot ---
+    assert np.abs(st["rpose"][:, :3] - g[f"{tag}_post_rpose"][:, :3]).max() <= 1e-12
+    assert np.abs(st["rhist"][:, :, :3] - g[f"{tag}_post_rhist"][:, :, :3]).max() <= 1e-12
+    assert np.abs(st["rpastv"] - g[f"{tag}_post_rpastv"]).max() <= 1e-15
+    assert np.abs(st["gtime"] - g[f"{tag}_post_gtime"]).max() <= 1e-12
+    assert np.array_equal(st["loc_to_start"], g[f"{tag}_post_loc_to_start"])
+    # --- goals: unchanged where the reference did not resample; resampled (to a valid goal) where it did ---
+    changed = np.abs(g[f"{tag}_post_hgoal"] - g[f"{tag}_pre_hgoal"]).max(-1) > 0
+    assert np.array_equal(st["hgoal"][~changed], g[f"{tag}_post_hgoal"][~changed])
+    if changed.any():
+        assert (np.abs(st["hgoal"][changed] - g[f"{tag}_pre_hgoal"][changed]).max(-1) > 0).all()
+        rg = np.linalg.norm(st["hgoal"][changed], axis=-1)
+        assert (rg > 5 - 0.71).all() and (rg < 5 + 0.71).all()
+    # --- observations ---
+    for name, tol in (("pt_state", 1e-9), ("robot_node", 1e-9), ("past_robot_vel", 1e-15), ("percent_episode", 1e-12),
+                      ("spatial_edges", 1e-9), ("human_valid", 0), ("detected_humans", 0)):
+        ref = g[f"{tag}_out_{name}"].reshape(o[name].shape)
+        assert np.abs(o[name] - ref).max() <= tol, name
+    # --- rewards / done reasons ---
+    assert np.abs(o["rewards"] - g[f"{tag}_out_rewards"]).max() <= 1e-9
+    assert np.abs(o["info"][:, 0] - g[f"{tag}_out_disturbance_v"]).max() <= 1e-9
+    assert np.abs(o["info"][:, 1] - g[f"{tag}_out_disturbance_th"]).max() <= 1e-9
+    assert np.abs(o["info"][:, 2] - g[f"{tag}_out_path_advancement"]).max() <= 1e-9
+    assert np.abs(o["info"][:, 3] - g[f"{tag}_out_deviation"]).max() <= 1e-9
+    assert np.array_equal(o["done_bits"] & 0xFF, g[f"{tag}_out_bits"].astype(np.int64) & 0xFF)
+    assert np.array_equal((o["done_bits"] >> 16) & 1, g[f"{tag}_out_done_HA"]) and np.array_equal((o["done_bits"] >> 17) & 1, g[f"{tag}_out_done_PT"])
+    # --- MPC controls ---
+    d = np.abs(o["mpc_actions"] - g[f"{tag}_out_mpc_actions"]).max(1)
+    print(f"{tag}: {T} transitions, MPC max|du|={d.max():.2e}, >1e-6: {int((d > 1e-6).sum())}")
+    assert (d > 1e-6).sum() <= 0.1 * T and d.max() < 0.2
+
+
+@pytest.mark.parametrize("tag,Nh", TAGS)
+def test_reset_matches_reference(golden_env, tag, Nh):
+    """reset(): first MPC solve + the lookback warm-start steps, from the reference's spawn positions."""
+    import torch
+    g = golden_env
+    env = _make_env(Nh, 3, end_goal_changing=False)   # no goal is reached during the 6 warm-start steps of these seeds
+    hp = torch.as_tensor(np.broadcast_to(g[f"{tag}_reset_hpos"], (3, Nh, 2)).copy(), device=env.device)
+    hg = torch.as_tensor(np.broadcast_to(g[f"{tag}_reset_hgoal"], (3, Nh, 2)).copy(), device=env.device)
+    env.reset(hp, hg)
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in env.out.items()}
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    assert np.array_equal(st["hvel"][0].view(np.uint32), g[f"{tag}_postreset_hvel"].view(np.uint32))
+    assert np.abs(st["hpos"][0] - g[f"{tag}_postreset_hpos"]).max() <= 1e-12
+    assert np.abs(st["hhist"][0] - g[f"{tag}_postreset_hhist"]).max() <= 1e-12
+    assert np.abs(st["rhist"][0, :, :3] - g[f"{tag}_postreset_rhist"][:, :3]).max() <= 1e-12
+    assert st["rvalid"][0] == g[f"{tag}_postreset_rvalid"] and np.array_equal(st["hvalid"][0], g[f"{tag}_postreset_hvalid"])
+    for name, tol in (("pt_state", 1e-9), ("robot_node", 1e-9), ("past_robot_vel", 0), ("percent_episode", 0),
+                      ("spatial_edges", 1e-9), ("human_valid", 0), ("mpc_actions", 1e-6)):
+        ref = g[f"{tag}_reset_{name}"].reshape(o[name][0].shape)
+        assert np.abs(o[name][0] - ref).max() <= tol, name
+    assert (o["pt_state"][0] == o["pt_state"][2]).all()
+
+
+def test_auto_path_switch_follows_soft_reset(golden_env):
+    """After 'goal' the reference's soft_reset advances to the next path, re-arms the MPC and localises to the start
+    (HA_and_PT env.py:130-141); the engine does this inside step() when auto_path_switch is on."""
+    import torch
+    g = golden_env
+    tag, Nh = "h6", 6
+    bits = g[f"{tag}_out_bits"]
+    idx = np.nonzero(bits & (1 << 4))[0]
+    assert len(idx) > 0
+    env = _make_env(Nh, len(idx), auto_path_switch=True)
+    env.reset()
+    _upload(env, g, tag, "pre", idx)
+    env.step(torch.as_tensor(g[f"{tag}_out_action"][idx], device=env.device))
+    torch.cuda.synchronize()
+    st = {k: v.cpu().numpy() for k, v in env.state.items()}
+    nxt = idx + 1
+    ok = nxt < len(bits)
+    assert np.array_equal(st["path_idx"][ok], g[f"{tag}_pre_path_idx"][nxt[ok]])
+    assert (st["loc_to_start"] == 1).all()
+    assert (st["path_idx"] == (g[f"{tag}_pre_path_idx"][idx] + 1) % 4).all()
+
+
+def test_free_running_full_size_invariants():
+    """C3 size, 30 free-running steps with the MPC action as policy: finite outputs, speed bounds, consistent
+    done bits, episode statistics add up, and the run is deterministic."""
+    import torch
+    import dr_mpc_b200 as d
+    runs = []
+    for rep in range(2):
+        env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=20), num_envs=16384)
+        S = env.reset()
+        env.stats(reset=True)
+        tot_done = 0
+        for t in range(30):
+            a = S['PT']['MPC_actions'][:, :2].clone()
+            S, R, D, info, eps = env.step(a)
+            tot_done += int(D['done'].sum())
+        torch.cuda.synchronize()
+        for k, v in env.out.items():
+            if v.dtype == torch.float64:
+                assert torch.isfinite(v).all(), k
+        assert (env.state["hvel"].double().norm(dim=-1) <= 1.01).all()
+        a = env.out["mpc_actions"]
+        assert (a[:, 0::2] > 0).all() and (a[:, 0::2] < 1).all() and (a[:, 1::2].abs() < 1).all()
+        c, s = env.stats()
+        c = c.cpu().numpy()
+        assert c[0] == 16384 * 30
+        bits = env.out["done_bits"]
+        assert (((bits & 0xFF) != 0) == ((bits & (1 << 18)) != 0)).all()
+        runs.append((env.state["hpos"].clone(), env.out["rewards"].clone(), c.copy()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])

@@ -1,0 +1,101 @@
+"""GPU parity: the CUDA MPC kernel (through the C ABI) against the reference golden sequences and the C oracle.
+fp64; tolerance on the controls 1e-6 (K<=10) / 5e-6 (K>10) whenever the LM decision sequence is the same; decision
+divergences (chaotic end-of-path regime, see tests/test_oracle_mpc.py) are counted and bounded."""
+import numpy as np
+import pytest
+from conftest import mpc_path_table
+
+pytestmark = pytest.mark.gpu
+
+
+def _mpc(K, N, paths):
+    import dr_mpc_b200 as d
+    m = d.BatchedMPC(None, K, 0.25, True, 1.0, 1.0, num_problems=N)
+    m.set_paths(paths)
+    return m
+
+
+@pytest.mark.parametrize("K", [4, 10])
+def test_cuda_matches_reference_golden(golden_mpc, K):
+    g = golden_mpc
+    paths, tab, lens = mpc_path_table(g)
+    n = g[f"K{K}_u"].shape[0]
+    m = _mpc(K, n, paths)
+    m.set_warm(g[f"K{K}_warm_T"], g[f"K{K}_warm_u"], g[f"K{K}_it0"])
+    u = m.act({'path_id': g[f"K{K}_path_id"], 'interp_index': g[f"K{K}_interp"], 'pose': g[f"K{K}_pose"]}, want_status=True)
+    st = m.last_status
+    d = np.abs(u - g[f"K{K}_u"]).max(axis=1)
+    same = st["iterations"] == g[f"K{K}_iters"]
+    regular = g[f"K{K}_interp"] < lens[g[f"K{K}_path_id"]] - 1 - 1.2375 * K
+    tight = d <= (1e-6 if K == 4 else 2e-6)
+    print(f"K={K}: max|du| same-branch={d[same & regular].max():.2e}, divergences={int((~tight).sum())}/{n}, max={d.max():.2e}")
+    assert tight[regular & same].all()
+    assert (~tight).sum() <= 0.12 * n and d.max() < 0.2
+    assert (st["term"] > 0).all()
+
+
+@pytest.mark.parametrize("K,N", [(4, 4096), (10, 2048), (20, 1024), (40, 512), (3, 257), (1, 64)])
+def test_cuda_matches_oracle_warm_sequences(oracle, golden_mpc, K, N):
+    """iteration0 solve + 3 warm re-solves, teacher-forcing the oracle's warm state every step."""
+    import torch
+    g = golden_mpc
+    paths, tab, lens = mpc_path_table(g)
+    rng = np.random.default_rng(K * 1000 + N)
+    pid = rng.integers(0, 4, N).astype(np.int32)
+    idx = rng.uniform(0, lens[pid] - 1)
+    lo = np.floor(idx).astype(int)
+    pose = np.stack([tab[pid, r, lo] for r in range(3)], 1) + rng.uniform(-0.3, 0.3, (N, 3))
+    ob = oracle.MpcBatch(N, oracle.mpc_params(K=K), tab, lens)
+    m = _mpc(K, N, paths)
+    tol = 1e-6 if K <= 10 else 5e-6
+    for step in range(4):
+        m.set_warm(ob.warm_T, ob.warm_u, ob.iteration0.astype(np.uint8))
+        u_o, st_o = ob.act(pid, idx, pose)
+        dev = "cuda:0"
+        u = m.act({'path_id': torch.tensor(pid, device=dev), 'interp_index': torch.tensor(idx, device=dev),
+                   'pose': torch.tensor(pose, device=dev)}, want_status=True)
+        torch.cuda.synchronize()
+        u = u.cpu().numpy(); st = m.last_status.cpu().numpy()
+        same = (st[:, 0] == st_o["iterations"]) & (st[:, 2] == st_o["lm_solves"]) & (st[:, 3] == st_o["cost_evals"]) & (st[:, 1] == st_o["retries"])
+        d = np.abs(u - u_o).max(1)
+        print(f"K={K} step {step}: same-branch max|du|={d[same].max():.2e}, LM-branch divergences {int((~same).sum())}/{N}, "
+              f"mean iters {st_o['iterations'].mean():.2f}, retries {int(st_o['retries'].sum())}")
+        assert (d[same] <= tol).all()
+        assert (~same).sum() <= max(3, 0.01 * N)
+        T, uu, it0 = m.get_warm()
+        assert np.abs(T - ob.warm_T)[same].max() <= 10 * tol and np.abs(uu - ob.warm_u)[same].max() <= 10 * tol
+        assert (it0 == 0).all()
+        v, w = u_o[:, 0], u_o[:, 1]
+        w_ = np.where(w == 0, 1e-12, w)
+        dx = (v / w_) * np.sin(w_ * 0.25); dy = (v / w_) * (1 - np.cos(w_ * 0.25))
+        c, s = np.cos(pose[:, 2]), np.sin(pose[:, 2])
+        pose = pose + np.stack([c * dx - s * dy, s * dx + c * dy, w * 0.25], 1)
+        idx = np.minimum(idx + v * 0.25 / 0.2, lens[pid] - 1)
+
+
+def test_reset_mask_and_full_size_properties(golden_mpc):
+    """1M-problem C5 size (K=4): determinism, bounds, status sanity; reset(mask) re-arms iteration0 only where asked."""
+    import torch
+    g = golden_mpc
+    paths, tab, lens = mpc_path_table(g)
+    N, K, dev = 1 << 20, 4, "cuda:0"
+    gen = torch.Generator(device=dev).manual_seed(1)
+    node = torch.randint(0, 125, (N,), generator=gen, device=dev)
+    p0 = torch.tensor(paths[0], device=dev)
+    pose = p0[:, node].T.contiguous() + (torch.rand((N, 3), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 0.6
+    interp = node.double()
+    outs = []
+    for rep in range(2):
+        m = _mpc(K, N, paths)
+        u = m.act({'interp_index': interp, 'pose': pose}, want_status=True)
+        torch.cuda.synchronize()
+        outs.append(u.clone())
+        st = m.last_status
+        assert (st[:, 4] != 0).all() and (st[:, 0] >= 1).all()
+    assert torch.equal(outs[0], outs[1])
+    v, w = outs[0][:, 0::2], outs[0][:, 1::2]
+    assert (v > 0).all() and (v < 1).all() and (w.abs() < 1).all()
+    mask = torch.zeros(N, dtype=torch.uint8, device=dev); mask[::2] = 1
+    m.reset(mask)
+    _, _, it0 = m.get_warm()
+    assert (it0[::2] == 1).all() and (it0[1::2] == 0).all()

@@ -1,0 +1,46 @@
+"""CPU: the C ORCA oracle (oracle/rvo2_ref.c, brute-force neighbour order) against the golden vectors produced by the
+reference's own crowd_sim.get_human_actions -> orca.py -> rvo2 shim (full simulator with RVO2's kd-tree)."""
+import numpy as np
+import pytest
+from conftest import ORCA_KEYS
+
+
+@pytest.mark.parametrize("key", ORCA_KEYS)
+def test_oracle_crowd_pass_matches_reference_bit_exact(oracle, golden_orca, key):
+    g = golden_orca
+    v, st = oracle.orca_crowd_pass(g[key + "_hpos"], g[key + "_hvel"], g[key + "_goal"], g[key + "_rpos"], want_stats=True)
+    ref = g[key + "_vnew"]
+    # fp32 both sides, same operation order: bit-exact (kd-tree visit order only matters on exact distSq ties)
+    assert np.array_equal(v.view(np.uint32), ref.view(np.uint32)), np.abs(v - ref).max()
+
+
+def test_golden_covers_all_branches(oracle, golden_orca):
+    g = golden_orca
+    mask, lp3, nlp1 = 0, 0, 0
+    for key in ORCA_KEYS:
+        _, st = oracle.orca_crowd_pass(g[key + "_hpos"], g[key + "_hvel"], g[key + "_goal"], g[key + "_rpos"], want_stats=True)
+        mask |= int(np.bitwise_or.reduce(st["branch_mask"].ravel()))
+        lp3 += int((st["lp2_fail"] < st["n_lines"]).sum())
+        nlp1 += int(st["n_lp1"].sum())
+    assert mask == 0b1111          # cut-off circle, left leg, right leg, collision
+    assert lp3 > 0 and nlp1 > 0    # infeasible LP2 -> LP3 exercised
+
+
+def test_speed_limit_and_static(oracle):
+    rng = np.random.default_rng(0)
+    E, Nh = 64, 12
+    hpos = rng.uniform(-4, 4, (E, Nh, 2)); goal = -hpos
+    hvel = rng.uniform(-1, 1, (E, Nh, 2)).astype(np.float32)
+    rpos = rng.uniform(-4, 4, (E, 2))
+    static = rng.uniform(size=(E, Nh)) < 0.2
+    v, st = oracle.orca_crowd_pass(hpos, hvel, goal, rpos, is_static=static, want_stats=True)
+    assert np.all(v[static] == 0)
+    speed = np.linalg.norm(v.astype(np.float64), axis=-1)
+    feasible = st["lp2_fail"] == st["n_lines"]
+    assert np.all(speed[feasible] <= 1.0 + 1e-5)      # LP2 result lies in the max-speed disc
+    assert np.all(speed <= 1.01)                      # LP3 (infeasible) results may overshoot by fp32 error only
+
+
+def test_single_agent_moves_to_goal(oracle):
+    v, st = oracle.orca_solve([0, 0, 0, 0, 0.6, 0.8, 0.485, 1.0], np.zeros((0, 5)))
+    assert np.allclose(v, [0.6, 0.8]) and st["n_lines"] == 0

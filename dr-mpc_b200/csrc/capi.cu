@@ -182,24 +182,13 @@ extern "C" int dre_mpc_act_host(dre_mpc *h, const int32_t *path_id, const double
     return DRE_OK;
 }
 
-// host views use the reference-like problem-major layout [N][K][*]; the device keeps [K][N][*]
 extern "C" int dre_mpc_get_warm(dre_mpc *h, double *warm_T, double *warm_u, uint8_t *iteration0)
 {
     if (!h) return DRE_ERR_INVALID;
     const size_t N = (size_t)h->st.N, K = (size_t)h->st.K;
     DRE_CUDA_TRY(cudaDeviceSynchronize());
-    if (warm_T) {
-        std::vector<double> t(K * N * 4);
-        DRE_CUDA_TRY(cudaMemcpy(t.data(), h->st.warm_T, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < K; ++k)
-            for (size_t n = 0; n < N; ++n) memcpy(warm_T + (n * K + k) * 4, t.data() + (k * N + n) * 4, 4 * sizeof(double));
-    }
-    if (warm_u) {
-        std::vector<double> t(K * N * 2);
-        DRE_CUDA_TRY(cudaMemcpy(t.data(), h->st.warm_u, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < K; ++k)
-            for (size_t n = 0; n < N; ++n) memcpy(warm_u + (n * K + k) * 2, t.data() + (k * N + n) * 2, 2 * sizeof(double));
-    }
+    if (warm_T) DRE_CUDA_TRY(cudaMemcpy(warm_T, h->st.warm_T, N * K * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (warm_u) DRE_CUDA_TRY(cudaMemcpy(warm_u, h->st.warm_u, N * K * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     if (iteration0) DRE_CUDA_TRY(cudaMemcpy(iteration0, h->st.iteration0, N, cudaMemcpyDeviceToHost));
     return DRE_OK;
 }
@@ -209,18 +198,8 @@ extern "C" int dre_mpc_set_warm(dre_mpc *h, const double *warm_T, const double *
     if (!h) return DRE_ERR_INVALID;
     const size_t N = (size_t)h->st.N, K = (size_t)h->st.K;
     DRE_CUDA_TRY(cudaDeviceSynchronize());
-    if (warm_T) {
-        std::vector<double> t(K * N * 4);
-        for (size_t k = 0; k < K; ++k)
-            for (size_t n = 0; n < N; ++n) memcpy(t.data() + (k * N + n) * 4, warm_T + (n * K + k) * 4, 4 * sizeof(double));
-        DRE_CUDA_TRY(cudaMemcpy(h->st.warm_T, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    if (warm_u) {
-        std::vector<double> t(K * N * 2);
-        for (size_t k = 0; k < K; ++k)
-            for (size_t n = 0; n < N; ++n) memcpy(t.data() + (k * N + n) * 2, warm_u + (n * K + k) * 2, 2 * sizeof(double));
-        DRE_CUDA_TRY(cudaMemcpy(h->st.warm_u, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-    }
+    if (warm_T) DRE_CUDA_TRY(cudaMemcpy(h->st.warm_T, warm_T, N * K * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    if (warm_u) DRE_CUDA_TRY(cudaMemcpy(h->st.warm_u, warm_u, N * K * 2 * sizeof(double), cudaMemcpyHostToDevice));
     if (iteration0) DRE_CUDA_TRY(cudaMemcpy(h->st.iteration0, iteration0, N, cudaMemcpyHostToDevice));
     return DRE_OK;
 }

@@ -25,13 +25,14 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
 {
     HaLayout l;
     size_t o = 0;
-    l.off_lines = o;  o += (size_t)NG * 2 * nA * sizeof(OLine);
-    l.off_pos = o;    o += (size_t)EPB * Nh * sizeof(double2);          // new human positions (fp64)
-    l.off_pen = o;    o += (size_t)EPB * Nh * 3 * sizeof(double);       // pen_v, pen_th, closest_dist per human
-    l.off_agents = o; o += (size_t)EPB * 5 * nA * sizeof(float);
-    l.off_dist = o;   o += (size_t)NG * nA * sizeof(float);
-    l.off_vnew = o;   o += (size_t)EPB * Nh * sizeof(float2);
-    l.off_flags = o;  o += (size_t)EPB * 4 * sizeof(int);
+    auto seg = [&o](size_t bytes) { const size_t at = o; o = (o + bytes + 15) / 16 * 16; return at; };   // 16 B aligned segments
+    l.off_lines = seg((size_t)NG * 2 * nA * sizeof(OLine));
+    l.off_pos = seg((size_t)EPB * Nh * sizeof(double2));          // new human positions (fp64)
+    l.off_pen = seg((size_t)EPB * Nh * 3 * sizeof(double));       // pen_v, pen_th, closest_dist per human
+    l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
+    l.off_dist = seg((size_t)NG * nA * sizeof(float));
+    l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
+    l.off_flags = seg((size_t)EPB * 4 * sizeof(int));
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -558,6 +559,8 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     switch (dre_orca_pick_group(D.orca, D.Nh)) {
+    case 2: return launch_ha<2>(D, mode, write_obs, s);
+    case 4: return launch_ha<4>(D, mode, write_obs, s);
     case 8: return launch_ha<8>(D, mode, write_obs, s);
     case 16: return launch_ha<16>(D, mode, write_obs, s);
     default: return launch_ha<32>(D, mode, write_obs, s);

@@ -22,8 +22,8 @@ int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos,
 // ---- mpc_kernels.cu ----
 struct MpcDeviceState {
     int N, K;
-    double *warm_T;      // [K][N][4]  (c,s,x,y) of the inverse-pose guesses, horizon-major so a warp's loads coalesce
-    double *warm_u;      // [K][N][2]
+    double *warm_T;      // [N][K][4]  (c,s,x,y) of the inverse-pose guesses T_1..T_K
+    double *warm_u;      // [N][K][2]
     uint8_t *iteration0; // [N]
     const double *paths; // [P][3][stride]
     const int32_t *lens; // [P]

@@ -1,10 +1,48 @@
-// mpc_kernels.cu -- batched MPC.act: one thread per problem runs the whole LM solve (mpc_device.cuh).
+// mpc_kernels.cu -- batched MPC.act (reference environment/path_tracking/utils/mpc.py:58-206).
 //
-// Data layout: warm-start poses/controls are horizon-major ([K][N]) so that the 32 problems of a warp
-// read/write consecutive 32 B / 16 B elements (coalesced double4 / double2 accesses); per-problem
-// inputs (path id, interpolation index, pose) and outputs are problem-major.
-#include "mpc_device.cuh"
+// Two kernels:
+//   mpc_coop_kernel<G> : K <= 32. A group of G lanes per problem, lane k = horizon step k, everything in registers
+//                        (mpc_coop.cuh). This is the fast path.
+//   mpc_act_kernel<KC> : K > 32 fallback, one thread per problem with the system in local memory.
+// Data layout: warm-start poses/controls are problem-major ([N][K] double4 / double2), so the lanes of a warp
+// (G-lane groups of consecutive problems) read/write one contiguous run; per-problem inputs and outputs likewise.
+#include <cstdlib>
+#include "mpc_coop.cuh"
 #include "launch.cuh"
+
+template <int G>
+__global__ void __launch_bounds__(128)
+mpc_coop_kernel(dre_mpc_params prm, MpcDeviceState st, const int32_t *__restrict__ path_id,
+                const double *__restrict__ interp_index, const double *__restrict__ pose, int pose_stride,
+                double *__restrict__ controls, int controls_stride, int controls_count,
+                dre_mpc_status *__restrict__ status, const uint8_t *__restrict__ active_mask)
+{
+    const int n = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+    LaneGroup<G> g;
+    if (n >= st.N) return;                                   // group-uniform exits
+    if (active_mask != nullptr && !active_mask[n]) return;
+    int pid = path_id ? path_id[n] : 0;
+    if (pid < 0 || pid >= st.num_paths) pid = 0;
+    const double *path = st.paths + (size_t)pid * 3 * st.path_stride;
+    const size_t K = (size_t)prm.horizon;
+    mpc_act_coop<G>(g, prm, path, st.path_stride, st.lens[pid], interp_index[n], pose[(size_t)n * pose_stride],
+                    pose[(size_t)n * pose_stride + 1], pose[(size_t)n * pose_stride + 2],
+                    reinterpret_cast<double4 *>(st.warm_T) + (size_t)n * K, reinterpret_cast<double2 *>(st.warm_u) + (size_t)n * K,
+                    st.iteration0 + n, controls + (size_t)n * controls_stride, controls_count, status ? status + n : nullptr);
+}
+
+template <int G>
+static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, const int32_t *path_id, const double *interp_index,
+                           const double *pose, int pose_stride, double *controls, int controls_stride, int controls_count,
+                           dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
+{
+    const int threads = 128, per_block = threads / G;
+    const int blocks = (st.N + per_block - 1) / per_block;
+    mpc_coop_kernel<G><<<blocks, threads, 0, s>>>(p, st, path_id, interp_index, pose, pose_stride, controls, controls_stride,
+                                                  controls_count, status, active_mask);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
 
 template <int KC>
 __global__ void __launch_bounds__(128)
@@ -22,7 +60,8 @@ mpc_act_kernel(dre_mpc_params prm, MpcDeviceState st, const int32_t *__restrict_
     MpcSystem<KC> S;
     mpc_act_one<KC>(prm, path, st.path_stride, st.lens[pid], interp_index[n], pose[(size_t)n * pose_stride],
                     pose[(size_t)n * pose_stride + 1], pose[(size_t)n * pose_stride + 2],
-                    reinterpret_cast<double4 *>(st.warm_T) + n, reinterpret_cast<double2 *>(st.warm_u) + n, (size_t)st.N,
+                    reinterpret_cast<double4 *>(st.warm_T) + (size_t)n * prm.horizon,
+                    reinterpret_cast<double2 *>(st.warm_u) + (size_t)n * prm.horizon, (size_t)1,
                     st.iteration0 + n, controls + (size_t)n * controls_stride, controls_count,
                     status ? status + n : nullptr, S);
 }
@@ -46,19 +85,32 @@ static int launch_mpc(const dre_mpc_params &p, const MpcDeviceState &st, const i
     return DRE_OK;
 }
 
+// DRE_MPC_SERIAL=1 selects the one-thread-per-problem kernel for every K (A/B measurements, tests)
+static bool dre_mpc_force_serial()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DRE_MPC_SERIAL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int dre_mpc_launch(const dre_mpc_params &p, const MpcDeviceState &st, const int32_t *path_id, const double *interp_index,
                    const double *pose, int pose_stride, double *controls, int controls_stride, int controls_count,
                    dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
 {
     const int K = p.horizon;
     if (K < 1 || K > DRE_MAX_HORIZON || st.N <= 0 || st.paths == nullptr) return DRE_ERR_INVALID;
-#define DRE_MPC_CASE(KC) return launch_mpc<KC>(p, st, path_id, interp_index, pose, pose_stride, controls, controls_stride, controls_count, status, active_mask, s)
-    if (K == 4) DRE_MPC_CASE(4);
-    if (K <= 10) DRE_MPC_CASE(10);
-    if (K <= 20) DRE_MPC_CASE(20);
-    if (K <= 30) DRE_MPC_CASE(30);
-    DRE_MPC_CASE(40);
-#undef DRE_MPC_CASE
+#define DRE_MPC_ARGS p, st, path_id, interp_index, pose, pose_stride, controls, controls_stride, controls_count, status, active_mask, s
+    if (!dre_mpc_force_serial()) {
+        if (K <= 4) return launch_mpc_coop<4>(DRE_MPC_ARGS);
+        if (K <= 8) return launch_mpc_coop<8>(DRE_MPC_ARGS);
+        if (K <= 16) return launch_mpc_coop<16>(DRE_MPC_ARGS);
+        if (K <= 32) return launch_mpc_coop<32>(DRE_MPC_ARGS);
+    }
+    if (K <= 4) return launch_mpc<4>(DRE_MPC_ARGS);
+    if (K <= 10) return launch_mpc<10>(DRE_MPC_ARGS);
+    if (K <= 20) return launch_mpc<20>(DRE_MPC_ARGS);
+    return launch_mpc<40>(DRE_MPC_ARGS);
+#undef DRE_MPC_ARGS
 }
 
 int dre_mpc_reset_launch(const MpcDeviceState &st, const uint8_t *mask, cudaStream_t s)

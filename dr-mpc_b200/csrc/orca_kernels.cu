@@ -20,8 +20,8 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
     l.EPB = EPB;
     l.off_lines = 0;
     l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
-    l.off_dist = l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float);
-    l.bytes = l.off_dist + (size_t)l.NG * l.nA * sizeof(float);
+    l.off_dist = (l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float) + 15) / 16 * 16;
+    l.bytes = (l.off_dist + (size_t)l.NG * l.nA * sizeof(float) + 15) / 16 * 16;
     return l;
 }
 
@@ -117,7 +117,7 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
 
 int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
-    if (p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
+    if (p.group_lanes == 2 || p.group_lanes == 4 || p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
     const int nA = Nh + (p.robot_visible ? 1 : 0);
     return nA <= 12 ? 8 : (nA <= 40 ? 16 : 32);
 }
@@ -127,6 +127,8 @@ int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos,
 {
     if (E <= 0 || Nh <= 0 || Nh > DRE_MAX_HUMANS) return DRE_ERR_INVALID;
     switch (dre_orca_pick_group(p, Nh)) {
+    case 2: return launch_orca<2>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 4: return launch_orca<4>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     case 8: return launch_orca<8>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     case 16: return launch_orca<16>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     default: return launch_orca<32>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);

@@ -125,3 +125,94 @@ class MpcBatch:
         f(ctypes.byref(self.P), N, _p(self.paths), self.paths.shape[2], _p(self.lens), _p(path_id), _p(interp_idx),
           _p(pose), _p(self.warm_T), _p(self.warm_u), _p(self.iteration0), _p(out), _p(stats), nthreads)
         return out, stats
+
+
+# ------------------------------------------------------------------------------------------------------------
+# flat env oracle (oracle/env_ref.c)
+# ------------------------------------------------------------------------------------------------------------
+class EnvCfg(ctypes.Structure):
+    _fields_ = [("E", ctypes.c_int32), ("Nh", ctypes.c_int32), ("LB", ctypes.c_int32),
+                ("neighbor_dist", ctypes.c_float), ("time_horizon", ctypes.c_float), ("orca_radius", ctypes.c_float),
+                ("max_speed_self", ctypes.c_float), ("max_neighbors", ctypes.c_int32), ("robot_visible", ctypes.c_int32),
+                ("dt", ctypes.c_double), ("time_limit", ctypes.c_double), ("human_radius", ctypes.c_double),
+                ("robot_radius", ctypes.c_double), ("circle_radius", ctypes.c_double), ("circle_radius_humans", ctypes.c_double),
+                ("end_goal_changing", ctypes.c_int32)] + \
+               [(n, ctypes.c_double) for n in ("collision_penalty", "safety_dist", "safety_penalty", "dist_radius", "dist_factor_v",
+                                               "dist_factor_th", "act_min_vel", "act_penalty", "pt_scaling", "goal_radius",
+                                               "goal_angle", "goal_reward", "path_adv_scaling", "dev_xy", "dev_th", "dev_scale",
+                                               "corridor_penalty", "corridor_max_dev", "eop_penalty", "safety_corridor_penalty",
+                                               "safety_corridor_max_dev")] + \
+               [("lookahead", ctypes.c_int32), ("lookbehind", ctypes.c_int32), ("mpc_actions_in_input", ctypes.c_int32),
+                ("auto_path_switch", ctypes.c_int32), ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
+                ("mpc", MpcParams), ("paths", ctypes.c_void_p), ("lens", ctypes.c_void_p), ("num_paths", ctypes.c_int32),
+                ("path_stride", ctypes.c_int32)]
+
+
+_ENV_ARRAYS = ["hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime",
+               "path_idx", "loc_to_start", "step_count", "reset_epoch", "warm_T", "warm_u", "iteration0",
+               "pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid",
+               "detected_humans", "rewards", "info", "done_bits", "mpc_status"]
+
+
+class EnvArrays(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _ENV_ARRAYS]
+
+
+class EnvRef:
+    """E reference environments held in numpy arrays with the engine's state / output layout."""
+
+    def __init__(self, E, Nh, paths, lens, K=4, lookback=6, seed=0x00D24D9C, env_id_offset=0, auto_path_switch=True,
+                 end_goal_changing=True, neighbor_dist=10.0, actions_in_input=4, **over):
+        self.E, self.Nh, self.K, self.LB = E, Nh, K, lookback
+        H, LB = lookback + 1, lookback
+        self.paths = np.ascontiguousarray(paths, dtype=np.float64)
+        self.lens = np.ascontiguousarray(lens, dtype=np.int32)
+        c = EnvCfg()
+        c.E, c.Nh, c.LB = E, Nh, lookback
+        c.neighbor_dist, c.time_horizon, c.orca_radius, c.max_speed_self = neighbor_dist, 5.0, 0.3 + 0.01 + 0.175, 1.0
+        c.max_neighbors, c.robot_visible = 0, 1
+        c.dt, c.time_limit, c.human_radius, c.robot_radius, c.circle_radius, c.circle_radius_humans = 0.25, 50.0, 0.3, 0.3, 4.0, 5.0
+        c.end_goal_changing = int(end_goal_changing)
+        c.collision_penalty, c.safety_dist, c.safety_penalty = -15.0, 0.22, -15.0
+        c.dist_radius, c.dist_factor_v, c.dist_factor_th = 1.5, 0.8 * 7, 0.5 * 7
+        c.act_min_vel, c.act_penalty = 0.025, -20.0
+        c.pt_scaling, c.goal_radius, c.goal_angle, c.goal_reward = 0.5, 0.3, 0.5, 0.0
+        c.path_adv_scaling, c.dev_xy, c.dev_th, c.dev_scale = 2.0, 1.0, 0.05, 0.9
+        c.corridor_penalty, c.corridor_max_dev, c.eop_penalty = -20.0, 1.6, -10.0
+        c.safety_corridor_penalty, c.safety_corridor_max_dev = -20.0, 1.4
+        c.lookahead, c.lookbehind, c.mpc_actions_in_input, c.auto_path_switch = 20, 5, actions_in_input, int(auto_path_switch)
+        c.seed, c.env_id_offset = seed, env_id_offset
+        c.mpc = mpc_params(K=K)
+        for k, v in over.items():
+            setattr(c, k, v)
+        c.paths, c.lens = self.paths.ctypes.data, self.lens.ctypes.data
+        c.num_paths, c.path_stride = self.paths.shape[0], self.paths.shape[2]
+        self.cfg = c
+        nact = 2 * min(K, actions_in_input)
+        z = np.zeros
+        self.a = {
+            "hpos": z((E, Nh, 2)), "hgoal": z((E, Nh, 2)), "hhist": z((E, Nh, H, 2)), "hvel": z((E, Nh, 2), np.float32),
+            "hstatic": z((E, Nh), np.uint8), "hvalid": z((E, Nh), np.int32), "rpose": z((E, 4)), "rprev": z((E, 4)),
+            "rhist": z((E, H, 4)), "rpastv": z((E, LB, 2)), "rvalid": z(E, np.int32), "gtime": z(E), "path_idx": z(E, np.int32),
+            "loc_to_start": z(E, np.uint8), "step_count": z(E, np.int64), "reset_epoch": z(E, np.int32),
+            "warm_T": z((E, K, 4)), "warm_u": z((E, K, 2)), "iteration0": np.ones(E, np.int32),
+            "pt_state": z((E, 4 * 25)), "mpc_actions": z((E, nact)), "robot_node": z((E, 2 * LB)), "past_robot_vel": z((E, 2 * LB)),
+            "percent_episode": z((E, 1)), "spatial_edges": z((E, Nh, 2 * H)), "human_valid": z((E, Nh)), "detected_humans": z(E),
+            "rewards": z((E, 3)), "info": z((E, 8)), "done_bits": z(E, np.uint32), "mpc_status": z(E, MPC_STATS_DTYPE),
+        }
+        self.A = EnvArrays(*[self.a[n].ctypes.data for n in _ENV_ARRAYS])
+        L = lib()
+        L.env_ref_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.env_ref_observe.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.env_ref_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+
+    def reset(self, hpos_init=None, hgoal_init=None, nthreads=0):
+        p = np.ascontiguousarray(hpos_init, dtype=np.float64) if hpos_init is not None else None
+        g = np.ascontiguousarray(hgoal_init, dtype=np.float64) if hgoal_init is not None else None
+        lib().env_ref_reset(ctypes.byref(self.cfg), ctypes.byref(self.A), _p(p), _p(g), nthreads)
+        return self.a
+
+    def step(self, actions, nthreads=0):
+        act = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.E, 2)
+        lib().env_ref_step(ctypes.byref(self.cfg), ctypes.byref(self.A), _p(act), nthreads)
+        return self.a

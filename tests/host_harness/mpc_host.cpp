@@ -15,12 +15,12 @@ static void run(const dre_mpc_params *prm, int N, const double *paths, int strid
     for (int n = 0; n < N; ++n) {
         const int pid = path_id ? path_id[n] : 0;
         mpc_act_one<KC>(*prm, paths + (size_t)pid * 3 * stride, stride, lens[pid], interp[n], pose[3 * n], pose[3 * n + 1],
-                        pose[3 * n + 2], reinterpret_cast<double4 *>(warm_T) + n, reinterpret_cast<double2 *>(warm_u) + n,
-                        (size_t)N, it0 + n, controls + (size_t)n * 2 * K, 2 * K, status ? status + n : nullptr, S);
+                        pose[3 * n + 2], reinterpret_cast<double4 *>(warm_T) + (size_t)n * K, reinterpret_cast<double2 *>(warm_u) + (size_t)n * K,
+                        (size_t)1, it0 + n, controls + (size_t)n * 2 * K, 2 * K, status ? status + n : nullptr, S);
     }
 }
 
-// warm_T: [K][N][4], warm_u: [K][N][2] (the device layout)
+// warm_T: [N][K][4], warm_u: [N][K][2] (the device layout)
 extern "C" int host_mpc_act(const dre_mpc_params *prm, int N, const double *paths, int stride, const int32_t *lens,
                             const int32_t *path_id, const double *interp, const double *pose, double *warm_T,
                             double *warm_u, uint8_t *it0, double *controls, dre_mpc_status *status)

@@ -12,7 +12,7 @@ def _engine(group_lanes=0, **kw):
     return d.BatchedORCA(d.EngineConfig(group_lanes=group_lanes, **kw))
 
 
-@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
 @pytest.mark.parametrize("key", ORCA_KEYS)
 def test_cuda_matches_reference_golden_bit_exact(golden_orca, key, lanes):
     g = golden_orca
@@ -74,10 +74,14 @@ def test_full_size_properties():
         hvel = (torch.rand((E, Nh, 2), generator=gen, device=dev) - 0.5)
         rpos = (torch.rand((E, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 12
         orca = d.BatchedORCA(d.EngineConfig())
-        v1 = orca.predict(hpos, hvel, goal, rpos)
+        v1 = orca.predict(hpos, hvel, goal, rpos, want_stats=True)
+        st = orca.last_stats
         v2 = orca.predict(hpos, hvel, goal, rpos)
         assert torch.equal(v1, v2)
-        assert torch.isfinite(v1).all() and (v1.double().norm(dim=-1) <= 1.01).all()
+        speed = v1.double().norm(dim=-1)
+        feasible = st[..., 1] == st[..., 0]
+        # LP2-feasible results lie in the max-speed disc; LP3 (infeasible) results may leave it slightly (RVO2 semantics)
+        assert torch.isfinite(v1).all() and (speed[feasible] <= 1.0 + 1e-5).all() and (speed <= 1.5).all()
     # lone humans far from everything: new velocity == preferred velocity
     E, Nh = 4096, 4
     hpos = torch.zeros((E, Nh, 2), device=dev, dtype=torch.float64)

@@ -101,6 +101,9 @@ def load():
         L.dre_env_step_host.argtypes = [c_vp, c_vp, c_vp]
         L.dre_env_observe.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
+        L.dre_env_set_profiling.argtypes = [c_vp, c_i32]
+        L.dre_env_kernel_ms.argtypes = [c_vp, c_vp, c_vp, c_i32]
+    L.dre_measure_peak.argtypes = [c_i32, P(c_d)]
     _lib = L
     return L
 

@@ -29,6 +29,53 @@ extern "C" const char *dre_strerror(int code)
 extern "C" int dre_version(void) { return 100; }
 
 // ------------------------------------------------------------------------------------------------
+// CUDA-core peak microbenchmark (the roofline denominators SURVEY 8(d) asks the builder to measure)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_chain_kernel(T *out, int iters)
+{
+    T a0 = (T)threadIdx.x * (T)1e-6, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3, a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+    const T b = (T)0.999999, c = (T)1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+            a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+        }
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == (T)-1) out[0] = a0;
+}
+
+extern "C" int dre_measure_peak(int32_t kind, double *tflops)
+{
+    if (!tflops || (kind != 0 && kind != 1)) return DRE_ERR_INVALID;
+    int dev = 0, sms = 0;
+    DRE_CUDA_TRY(cudaGetDevice(&dev));
+    DRE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    void *buf = nullptr;
+    DRE_CUDA_TRY(cudaMalloc(&buf, 64));
+    cudaEvent_t e0, e1;
+    DRE_CUDA_TRY(cudaEventCreate(&e0));
+    DRE_CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = kind == 0 ? 4096 : 2048;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        DRE_CUDA_TRY(cudaEventRecord(e0, 0));
+        if (kind == 0) fma_chain_kernel<float><<<blocks, threads>>>((float *)buf, iters);
+        else fma_chain_kernel<double><<<blocks, threads>>>((double *)buf, iters);
+        DRE_CUDA_TRY(cudaEventRecord(e1, 0));
+        DRE_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DRE_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / ((double)best * 1e-3) * 1e-12;
+    return DRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // ORCA
 // ------------------------------------------------------------------------------------------------
 extern "C" int dre_orca_predict(const dre_orca_params *p, int32_t E, int32_t Nh, const double *hpos, const float *hvel,

@@ -16,7 +16,29 @@ struct dre_env {
     double *d_actions = nullptr;   // staging for step_host
     cudaStream_t own_stream = nullptr;
     bool was_reset = false;
+    // per-kernel timing (bench.py's roofline leg)
+    bool profiling = false;
+    static const int PROF_RING = 64;
+    cudaEvent_t ev[PROF_RING][5];
+    int ev_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_steps = 0;
 };
+
+static int prof_drain(dre_env *h)
+{
+    for (int i = 0; i < h->ev_used; ++i) {
+        DRE_CUDA_TRY(cudaEventSynchronize(h->ev[i][4]));
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            DRE_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[i][k], h->ev[i][k + 1]));
+            h->prof_ms[k] += ms;
+        }
+        h->prof_steps++;
+    }
+    h->ev_used = 0;
+    return DRE_OK;
+}
 
 namespace {
 struct Carver {
@@ -141,6 +163,7 @@ extern "C" int dre_env_destroy(dre_env *h)
     if (!h) return DRE_OK;
     cudaDeviceSynchronize();
     dre_mpc_destroy(h->mpc);
+    if (h->profiling) dre_env_set_profiling(h, 0);
     cudaFree(h->state_block); cudaFree(h->slab); cudaFree(h->d_actions);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -227,11 +250,58 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     EnvDev D = h->D;
     D.actions = actions;
+    if (!h->profiling) {
+        int rc = dre_env_launch_ha(D, 0, 1, s);
+        if (rc) return rc;
+        rc = dre_env_launch_pt(D, 0, s);
+        if (rc) return rc;
+        return env_solve_mpc(h, s);
+    }
+    if (h->ev_used == dre_env::PROF_RING) { const int rc = prof_drain(h); if (rc) return rc; }
+    cudaEvent_t *ev = h->ev[h->ev_used];
+    const int nact = n_mpc_actions(h->cfg);
+    DRE_CUDA_TRY(cudaEventRecord(ev[0], s));
     int rc = dre_env_launch_ha(D, 0, 1, s);
     if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(ev[1], s));
     rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
-    return env_solve_mpc(h, s);
+    DRE_CUDA_TRY(cudaEventRecord(ev[2], s));
+    rc = dre_mpc_launch(dre_mpc_params_of(h->mpc), dre_mpc_state_of(h->mpc), D.path_idx, D.mpc_interp, D.rpose, 4,
+                        D.out.mpc_actions, nact, nact, D.out.mpc_status, nullptr, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(ev[3], s));
+    rc = dre_env_launch_mpc_stats(D, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(ev[4], s));
+    h->ev_used++;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_set_profiling(dre_env *h, int32_t on)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (on && !h->profiling) {
+        for (int i = 0; i < dre_env::PROF_RING; ++i)
+            for (int k = 0; k < 5; ++k) DRE_CUDA_TRY(cudaEventCreate(&h->ev[i][k]));
+    } else if (!on && h->profiling) {
+        const int rc = prof_drain(h);
+        if (rc) return rc;
+        for (int i = 0; i < dre_env::PROF_RING; ++i)
+            for (int k = 0; k < 5; ++k) cudaEventDestroy(h->ev[i][k]);
+    }
+    h->profiling = on != 0;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_kernel_ms(dre_env *h, double *ms4, int64_t *steps, int32_t reset)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (h->profiling) { const int rc = prof_drain(h); if (rc) return rc; }
+    if (ms4) for (int k = 0; k < 4; ++k) ms4[k] = h->prof_ms[k];
+    if (steps) *steps = h->prof_steps;
+    if (reset) { for (int k = 0; k < 4; ++k) h->prof_ms[k] = 0.0; h->prof_steps = 0; }
+    return DRE_OK;
 }
 
 extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host)

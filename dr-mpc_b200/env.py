@@ -179,6 +179,16 @@ class BatchedHAAndPTEnv:
                                          self._stream()))
         return c, s
 
+    def set_profiling(self, on=True):
+        _lib.check(self._L.dre_env_set_profiling(self._h, int(on)))
+
+    def kernel_ms(self, reset=False):
+        """-> ({'ha_step','pt_step','mpc_solve','mpc_stats'} summed ms, profiled steps) since the last reset."""
+        ms = (ctypes.c_double * 4)()
+        n = ctypes.c_int64()
+        _lib.check(self._L.dre_env_kernel_ms(self._h, ms, ctypes.byref(n), int(reset)))
+        return dict(zip(("ha_step", "pt_step", "mpc_solve", "mpc_stats"), list(ms))), int(n.value)
+
     @property
     def MPC(self):
         return self

@@ -212,6 +212,14 @@ int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
  * double[4] {sum R, sum R_PT, sum R_HA, spare}; `reset` clears them. Feed to NCCL all-reduce. */
 int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream);
 
+/* Measurement support (bench.py): when profiling is on, step() brackets each of its kernels with CUDA events on the
+ * caller's stream; dre_env_kernel_ms() synchronises and returns the summed milliseconds per kernel since the last
+ * reset, order {ha_step, pt_step, mpc_solve, mpc_stats}, and the number of profiled steps. */
+int dre_env_set_profiling(dre_env *h, int32_t on);
+int dre_env_kernel_ms(dre_env *h, double *ms4, int64_t *steps, int32_t reset);
+/* FMA-chain microbenchmark of the CUDA-core peaks on the current device: kind 0 = fp32, 1 = fp64 -> TFLOP/s */
+int dre_measure_peak(int32_t kind, double *tflops);
+
 const char *dre_strerror(int code);
 const char *dre_last_cuda_error(void);
 int dre_version(void);

@@ -32,7 +32,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
     l.off_dist = seg((size_t)NG * nA * sizeof(float));
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
-    l.off_flags = seg((size_t)EPB * 4 * sizeof(int));
+    l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -40,16 +40,22 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
 template <int G>
 __device__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
-                               bool pos_from_smem, unsigned long long *lp3_count)
+                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
     float *sd = dist + (size_t)gi * nA;
     const float invTH = 1.0f / D.orca.time_horizon, invDt = 1.0f / D.orca.time_step;
     const int maxNb = D.orca.max_neighbors > 0 ? D.orca.max_neighbors : nA - 1;
-    for (int ag = gi; ag < EPB * Nh; ag += NG) {
+    // LP3 (infeasible) solves cost an order of magnitude more than LP2 ones, so the groups of a CTA pull agents from a
+    // shared counter instead of a static assignment
+    for (;;) {
+        int ag = 0;
+        if (g.rank() == 0) ag = atomicAdd(work_counter, 1);
+        ag = g.bcast(ag, 0);
+        if (ag >= EPB * Nh) break;
         const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
-        if (e >= D.E) break;
+        if (e >= D.E) continue;
         const size_t gidx = (size_t)e * Nh + i;
         float ox = 0.f, oy = 0.f;
         if (!D.hstatic[gidx]) {
@@ -110,11 +116,12 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
             }
             A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = D.orca.radius;
         }
-        for (int t = threadIdx.x; t < EPB * 4; t += blockDim.x) flags[t] = 0;
+        for (int t = threadIdx.x; t < EPB * 4 + 2; t += blockDim.x) flags[t] = 0;
         __syncthreads();
 
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
-        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false, D.stat_counters ? D.stat_counters + 11 : nullptr);
+        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
+                          D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4]);
         __syncthreads();
 
         // ---- integrate: robot (unicycle, agent.py:169-176) and humans (Euler, agent.py:164-168); histories ----
@@ -180,7 +187,7 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
         if (mode == 0) {
             // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
             float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
-            orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr);
+            orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1]);
             __syncthreads();
 
             // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
@@ -539,12 +546,11 @@ template <int G>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
-    const int per_env = Nh * G;
-    int EPB = per_env >= 384 ? 1 : 384 / per_env;
+    // 256 threads = 256/G lane-groups; ~5 agents per group so the dynamic schedule can even out LP2 / LP3 solves
+    const int threads = 256, NGl = threads / G;
+    int EPB = (5 * NGl) / Nh;
+    if (EPB < 1) EPB = 1;
     if (EPB > D.E) EPB = D.E;
-    int threads = (EPB * per_env + 31) / 32 * 32;
-    if (threads > 512) threads = 512;
-    if (threads < 64) threads = 64;
     const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
     auto kern = ha_step_kernel<G>;
     if (lay.bytes > 48 * 1024) {

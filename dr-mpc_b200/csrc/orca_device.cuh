@@ -25,6 +25,7 @@ struct TileGroup {
     __device__ bool any(bool p) const { return t.any(p); }
     __device__ float shfl_xor(float v, int m) const { return t.shfl_xor(v, m); }
     __device__ unsigned shfl_xor(unsigned v, int m) const { return t.shfl_xor(v, m); }
+    __device__ int bcast(int v, int src) const { return t.shfl(v, src); }
     __device__ void sync() const { t.sync(); }
 };
 #endif
@@ -37,6 +38,7 @@ struct SerialGroup {
     DRE_HD bool any(bool p) const { return p; }
     DRE_HD float shfl_xor(float v, int) const { return v; }
     DRE_HD unsigned shfl_xor(unsigned v, int) const { return v; }
+    DRE_HD int bcast(int v, int) const { return v; }
     DRE_HD void sync() const {}
 };
 

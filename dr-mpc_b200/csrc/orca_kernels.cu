@@ -21,7 +21,7 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
     l.off_lines = 0;
     l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
     l.off_dist = (l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float) + 15) / 16 * 16;
-    l.bytes = (l.off_dist + (size_t)l.NG * l.nA * sizeof(float) + 15) / 16 * 16;
+    l.bytes = (l.off_dist + (size_t)l.NG * l.nA * sizeof(float) + 15) / 16 * 16 + 16;   // + work counter
     return l;
 }
 
@@ -31,7 +31,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
                     const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
                     const double2 *__restrict__ rpos, const uint8_t *__restrict__ is_static,
                     float2 *__restrict__ vnew, dre_orca_stats *__restrict__ stats,
-                    size_t off_agents, size_t off_dist)
+                    size_t off_agents, size_t off_dist, size_t off_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nA = Nh + (p.robot_visible ? 1 : 0);
@@ -39,7 +39,9 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     OLine *lines = reinterpret_cast<OLine *>(smem_raw);
     float *agents = reinterpret_cast<float *>(smem_raw + off_agents);
     float *dist = reinterpret_cast<float *>(smem_raw + off_dist);
+    int *work_counter = reinterpret_cast<int *>(smem_raw + off_counter);
     const int env0 = blockIdx.x * EPB;
+    if (threadIdx.x == 0) *work_counter = 0;
 
     // stage the tile: agents[e_local][field][a]
     for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
@@ -68,9 +70,13 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
     const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
 
-    for (int ag = gi; ag < EPB * Nh; ag += NG) {
+    for (;;) {   // groups pull agents from a CTA-wide counter: LP3 solves are ~10x dearer than LP2 ones
+        int ag = 0;
+        if (g.rank() == 0) ag = atomicAdd(work_counter, 1);
+        ag = g.bcast(ag, 0);
+        if (ag >= EPB * Nh) break;
         const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
-        if (e >= E) break;
+        if (e >= E) continue;
         const size_t gidx = (size_t)e * Nh + i;
         float ox = 0.f, oy = 0.f;
         if (is_static != nullptr && is_static[gidx]) {
@@ -96,12 +102,10 @@ template <int G>
 static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
                        const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
 {
-    int per_env = Nh * G;
-    int EPB = per_env >= 384 ? 1 : 384 / per_env;
+    const int threads = 256, NGl = threads / G;
+    int EPB = (5 * NGl) / Nh;
+    if (EPB < 1) EPB = 1;
     if (EPB > E) EPB = E;
-    int threads = EPB * per_env;
-    threads = (threads + 31) / 32 * 32;
-    if (threads > 512) threads = 512;
     const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);
     auto kern = orca_predict_kernel<G>;
     if (l.bytes > 48 * 1024) {
@@ -110,7 +114,7 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
     }
     const int blocks = (E + EPB - 1) / EPB;
     kern<<<blocks, threads, l.bytes, s>>>(p, E, Nh, EPB, (const double2 *)hpos, (const float2 *)hvel, (const double2 *)goal,
-                                           (const double2 *)rpos, is_static, (float2 *)vnew, stats, l.off_agents, l.off_dist);
+                                           (const double2 *)rpos, is_static, (float2 *)vnew, stats, l.off_agents, l.off_dist, l.bytes - 16);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }
@@ -119,7 +123,7 @@ int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
     if (p.group_lanes == 2 || p.group_lanes == 4 || p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
     const int nA = Nh + (p.robot_visible ? 1 : 0);
-    return nA <= 12 ? 8 : (nA <= 40 ? 16 : 32);
+    return nA <= 8 ? 4 : 8;   // measured on B200: 8 lanes per agent is fastest from 10 to 50 humans (profiles/)
 }
 
 int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,

@@ -37,7 +37,7 @@ def crowd(E, Nh, spread, seed=0):
 
 for (E, Nh, spread) in ((1024, 10, 5.0), (16384, 20, 5.5), (65536, 50, 8.5), (8192, 50, 8.5), (16384, 6, 5.0)):
     hpos, hvel, goal, rpos = crowd(E, Nh, spread)
-    for G in (2, 4, 8, 16, 32):
+    for G in (4, 8, 16):
         o = d.BatchedORCA(d.EngineConfig(group_lanes=G))
         try:
             ms = timeit(lambda: o.predict(hpos, hvel, goal, rpos))

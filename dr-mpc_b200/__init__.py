@@ -5,9 +5,10 @@ from .config import EngineConfig
 from .orca import BatchedORCA
 from .mpc import BatchedMPC
 from . import paths
+from . import parallel
 try:
     from .env import BatchedHAAndPTEnv
 except ImportError:   # env module not present in minimal builds
     pass
 
-__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "paths"]
+__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "paths", "parallel"]

@@ -549,8 +549,8 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
     // 256 threads = 256/G lane-groups; ~5 agents per group so the dynamic schedule can even out LP2 / LP3 solves
     const int threads = 256, NGl = threads / G;
     int EPB = (5 * NGl) / Nh;
+    if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     if (EPB < 1) EPB = 1;
-    if (EPB > D.E) EPB = D.E;
     const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
     auto kern = ha_step_kernel<G>;
     if (lay.bytes > 48 * 1024) {

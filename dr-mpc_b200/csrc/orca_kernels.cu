@@ -104,8 +104,8 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
 {
     const int threads = 256, NGl = threads / G;
     int EPB = (5 * NGl) / Nh;
+    if (EPB > (E + 591) / 592) EPB = (E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     if (EPB < 1) EPB = 1;
-    if (EPB > E) EPB = E;
     const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);
     auto kern = orca_predict_kernel<G>;
     if (l.bytes > 48 * 1024) {

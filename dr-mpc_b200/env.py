@@ -15,8 +15,7 @@ from .mpc import MPC_STATUS_DTYPE
 DONE_BITS = {'collision': 1 << 0, 'safety_human_raise': 1 << 1, 'actuation_termination': 1 << 2, 'timeout': 1 << 3,
              'goal': 1 << 4, 'deviation_end_of_path': 1 << 5, 'corridor_hit': 1 << 6, 'safety_corridor_raise': 1 << 7,
              'done_HA': 1 << 16, 'done_PT': 1 << 17, 'done': 1 << 18, 'done_for_replay': 1 << 19}
-STAT_NAMES = ['steps', 'success', 'collision', 'safety_human_raise', 'timeout', 'deviation_end_of_path', 'corridor_hit',
-              'safety_corridor_raise', 'actuation_termination', 'mpc_retries', 'mpc_gave_up', 'orca_lp3']
+from .parallel import STAT_NAMES
 
 
 class _DevArray:

@@ -80,8 +80,11 @@ def test_full_size_properties():
         assert torch.equal(v1, v2)
         speed = v1.double().norm(dim=-1)
         feasible = st[..., 1] == st[..., 0]
-        # LP2-feasible results lie in the max-speed disc; LP3 (infeasible) results may leave it slightly (RVO2 semantics)
-        assert torch.isfinite(v1).all() and (speed[feasible] <= 1.0 + 1e-5).all() and (speed <= 1.5).all()
+        # LP2-feasible results lie in the max-speed disc. LP3 (infeasible) results can leave it: with two almost
+        # anti-parallel half-planes RVO2's fp32 discriminant in linearProgram1 cancels catastrophically (bit-exactly
+        # reproduced, see tests/test_oracle_orca.py::test_lp3_overshoot_is_reference_behaviour); it must stay rare.
+        assert torch.isfinite(v1).all() and (speed[feasible] <= 1.0 + 1e-5).all()
+        assert (speed > 1.01).double().mean() < 1e-3
     # lone humans far from everything: new velocity == preferred velocity
     E, Nh = 4096, 4
     hpos = torch.zeros((E, Nh, 2), device=dev, dtype=torch.float64)

@@ -1,0 +1,186 @@
+"""CPU: host-side logic and the C-ABI surface (no GPU compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from conftest import REPO, mpc_path_table
+
+
+def test_libdre_loads_and_exports_every_declared_symbol():
+    import dr_mpc_b200._lib as L
+    lib = L.load()
+    hdr = open(os.path.join(REPO, "include", "dre.h")).read()
+    names = sorted(set(re.findall(r"\b(dre_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libdre.so does not export {n}"
+    assert lib.dre_version() >= 100
+    assert lib.dre_strerror(-1).decode().startswith("invalid")
+
+
+def test_struct_layouts_match_header_sizes():
+    import dr_mpc_b200._lib as L
+    assert ctypes.sizeof(L.OrcaParams) == 32 and ctypes.sizeof(L.OrcaStats) == 24
+    assert ctypes.sizeof(L.MpcStatus) == 32 and ctypes.sizeof(L.MpcParams) == 72
+    # compile a tiny C program against the header to cross-check the big struct
+    src = '#include <stdio.h>\n#include "dre.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(dre_env_config), sizeof(dre_mpc_params), sizeof(dre_env_state_view), sizeof(dre_step_out));return 0;}'
+    exe = os.path.join(REPO, "tests", "host_harness", "sizes")
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-I", os.path.join(REPO, "include"), "-x", "c", "-", "-o", exe], input=src.encode(), check=True)
+    out = subprocess.check_output([exe]).decode().split()
+    os.remove(exe)
+    assert [int(x) for x in out] == [ctypes.sizeof(L.EnvConfig), ctypes.sizeof(L.MpcParams), ctypes.sizeof(L.EnvStateView), ctypes.sizeof(L.StepOut)]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "dr-mpc_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"liboracle", r"oracle[/\\.](oracle|rvo2_ref|mpc_ref|env_ref|shims)", r"#include\s+\"[^\"]*oracle"):
+                    assert not re.search(pat, txt, flags=re.M), f"{f} reaches into oracle/ ({pat})"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import dr_mpc_b200._lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.DreError, match="no CPU fallback"):
+        L.load()
+
+
+def test_paths_match_reference_paths_bit_exact(golden_mpc):
+    """dr_mpc_b200.paths regenerates the reference's four continuous-task paths (path_tracking_env.py:28-56)."""
+    import dr_mpc_b200 as d
+    ours = d.paths.continuous_task_paths()
+    for i, p in enumerate(ours):
+        ref = golden_mpc[f"path{i}"]
+        assert p.shape == ref.shape and np.abs(p - ref).max() <= 1e-13, i
+    tab, lens = d.paths.pack_paths(ours)
+    assert tab.shape == (4, 3, 125) and list(lens) == [125, 41, 125, 41]
+    # reference quirk: path 2 (CCW from theta = pi) wraps to about -3.09 at node 1
+    assert ours[2][2, 0] == np.pi and ours[2][2, 1] < -3.0
+
+
+def test_engine_config_reads_reference_config_objects():
+    import dr_mpc_b200 as d
+
+    class B:
+        pass
+
+    def bag(**kw):
+        b = B()
+        b.__dict__.update(kw)
+        return b
+    cm = bag(
+        config_general=bag(env=bag(lookback=6, time_step=0.25, time_limit=50), robot=bag(v_max=1.0, w_max=1.0)),
+        config_HA=bag(sim=bag(human_num=7, circle_radius=4, circle_radius_humans=5), orca=bag(neighbor_dist=10, time_horizon=5, safety_space=0.175),
+                      humans=bag(radius=0.3, v_max=1.0, end_goal_changing=True), robot=bag(radius=0.3, visible=True),
+                      rewards=bag(params={'actuation_termination': {'min_vel': 0.025, 'penalty': -20}, 'safety_human_raise': {'safety_dist': 0.22, 'penalty': -15},
+                                          'collision': {'penalty': -15}, 'disturbance': {'radius': 1.5, 'factor_v': 0.8 * 7, 'factor_th': 0.5 * 7}})),
+        config_PT=bag(env=bag(node_separation=0.2), MPC=bag(planning_horizon=4, actions_in_input=4), PT_model_params={'MLP_local': bag(lookahead=20, lookbehind=5)},
+                      rewards=bag(overall_scaling=0.5, params={'goal': {'goal_radius': 0.3, 'goal_angle': 0.5, 'goal_reward': 0}, 'path_advancement': {'path_advancement_scaling': 2.0},
+                                                               'deviation': {'xy': 1, 'th': 0.05, 'scale': 0.9}, 'corridor_hit': {'penalty': -20, 'max_deviation': 1.6},
+                                                               'deviation_end_of_path': {'penalty': -10}, 'safety_corridor_raise': {'penalty': -20, 'max_deviation': 1.4}})))
+    c = d.EngineConfig.from_config_master(cm, num_envs=128)
+    assert c.num_humans == 7 and c.num_envs == 128
+    assert c == d.EngineConfig(num_humans=7, num_envs=128)             # the defaults ARE the reference's values
+    e = c.env_config()
+    assert abs(e.orca.radius - 0.485) < 1e-7 and e.mpc.horizon == 4 and e.safety_corridor_max_dev == 1.4
+
+
+def test_device_mpc_header_on_host_matches_oracle(oracle, golden_mpc):
+    """The kernel's per-problem LM code (dr-mpc_b200/csrc/mpc_device.cuh), compiled for the host by
+    tests/host_harness, against the oracle with teacher-forced warm starts."""
+    hh = os.path.join(REPO, "tests", "host_harness")
+    so = os.path.join(hh, "libmpc_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include",
+                           "-o", so, os.path.join(hh, "mpc_host.cpp")])
+    import dr_mpc_b200._lib as L
+    lib = ctypes.CDLL(so)
+    _, tab, lens = mpc_path_table(golden_mpc)
+    for K, N in ((4, 600), (10, 200)):
+        rng = np.random.default_rng(K)
+        pid = rng.integers(0, 4, N).astype(np.int32)
+        idx = rng.uniform(0, lens[pid] - 1)
+        pose = np.stack([tab[pid, r, np.floor(idx).astype(int)] for r in range(3)], 1) + rng.uniform(-0.3, 0.3, (N, 3))
+        ob = oracle.MpcBatch(N, oracle.mpc_params(K=K), tab, lens)
+        prm = L.MpcParams(K, 0.25, 1.0, 1.0, 0.2, 1500, 1e-4, 1e-4, 0, 20)
+        for step in range(2):
+            wT, wu, it0 = ob.warm_T.copy(), ob.warm_u.copy(), ob.iteration0.astype(np.uint8)
+            u_o, st_o = ob.act(pid, idx, pose)
+            u_h = np.zeros((N, 2 * K)); st_h = np.zeros(N, dtype=oracle.MPC_STATS_DTYPE)
+            p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            assert lib.host_mpc_act(ctypes.byref(prm), N, p(tab), 125, p(lens), p(pid), p(idx), p(pose), p(wT), p(wu), p(it0), p(u_h), p(st_h)) == 0
+            same = (st_o["iterations"] == st_h["iterations"]) & (st_o["lm_solves"] == st_h["lm_solves"]) & (st_o["cost_evals"] == st_h["cost_evals"])
+            assert same.mean() > 0.99 and np.abs(u_o - u_h)[same].max() < 1e-6
+            assert np.abs(wT - ob.warm_T)[same].max() < 1e-5
+
+
+def test_shard_envs_partitions_exactly():
+    from dr_mpc_b200.parallel import shard_envs
+    for total, world in ((16384, 8), (65536, 8), (1000, 3), (5, 8), (16384, 1)):
+        spans = [shard_envs(total, world, r) for r in range(world)]
+        assert sum(c for _, c in spans) == total
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1)) and spans[0][0] == 0
+    with pytest.raises(ValueError):
+        shard_envs(10, 2, 2)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from oracle import oracle as O
+import dr_mpc_b200 as d
+from dr_mpc_b200.parallel import init_distributed, shard_envs, episode_stats_from_step, reduce_episode_stats
+rank, world, _ = init_distributed("gloo")
+TOTAL, NH, STEPS = 48, 8, 6
+tab, lens = d.paths.pack_paths(d.paths.continuous_task_paths())
+off, cnt = shard_envs(TOTAL, world, rank)
+env = O.EnvRef(cnt, NH, tab, lens, env_id_offset=off)     # the CPU oracle stands in for the per-GPU engine shard
+a = env.reset(nthreads=1)
+C = torch.zeros(16, dtype=torch.int64); S = torch.zeros(4, dtype=torch.float64)
+for t in range(STEPS):
+    a = env.step(a["mpc_actions"][:, :2].copy(), nthreads=1)
+    c, s = episode_stats_from_step(torch.from_numpy(a["done_bits"].astype(np.int64)), torch.from_numpy(a["rewards"]))
+    C += c; S += s
+reduce_episode_stats(C, S)
+np.savez(os.path.join(sys.argv[2], f"shard{rank}.npz"), hpos=a["hpos"], hgoal=a["hgoal"], rewards=a["rewards"], C=C.numpy(), S=S.numpy(), off=off, cnt=cnt)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding_equals_single_process(oracle, tmp_path):
+    """N>1 path on CPU (gloo, world_size 2): each rank steps its own contiguous env shard (no step-path collective),
+    statistics are all-reduced; the union must equal the single-process run bit for bit (RNG keyed by global env id)."""
+    import torch
+    import dr_mpc_b200 as d
+    from dr_mpc_b200.parallel import episode_stats_from_step
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), REPO, str(tmp_path)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    TOTAL, NH, STEPS = 48, 8, 6
+    tab, lens = d.paths.pack_paths(d.paths.continuous_task_paths())
+    ref = oracle.EnvRef(TOTAL, NH, tab, lens)
+    a = ref.reset(nthreads=2)
+    C = torch.zeros(16, dtype=torch.int64); S = torch.zeros(4, dtype=torch.float64)
+    for t in range(STEPS):
+        a = ref.step(a["mpc_actions"][:, :2].copy(), nthreads=2)
+        c, s = episode_stats_from_step(torch.from_numpy(a["done_bits"].astype(np.int64)), torch.from_numpy(a["rewards"]))
+        C += c; S += s
+    for r in range(2):
+        z = np.load(tmp_path / f"shard{r}.npz")
+        sl = slice(int(z["off"]), int(z["off"]) + int(z["cnt"]))
+        assert np.array_equal(z["hpos"], a["hpos"][sl]) and np.array_equal(z["hgoal"], a["hgoal"][sl]) and np.array_equal(z["rewards"], a["rewards"][sl])
+        assert np.array_equal(z["C"], C.numpy()) and np.allclose(z["S"], S.numpy(), rtol=1e-12)
+    assert C[0] == TOTAL * STEPS

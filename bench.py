@@ -47,7 +47,7 @@ def parse():
 def workload_config(a):
     return {"workload": f"C3 full env step: {a.envs_per_gpu} envs x {a.humans} humans per GPU, MPC horizon {a.horizon}, "
                         "2 ORCA passes + integration + rewards/obs + localisation + 1 MPC solve per env-step",
-            "envs_per_gpu": a.envs_per_gpu, "humans": a.humans, "horizon": a.horizon, "policy": "MPC action executed (alpha=0)",
+            "envs_per_gpu": a.envs_per_gpu, "humans": a.humans, "horizon": a.horizon, "policy": "MPC action + fixed per-env Gaussian perturbation (sigma 0.1 m/s, 0.2 rad/s), clipped to the action box",
             "l2": "256 MB buffer written between timed steps (L2 flush)", "parallelism": "env-sharded, no step-path collective"}
 
 
@@ -203,8 +203,18 @@ def run_ours(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     launches_per_step = 4                      # ha_step, pt_step, mpc_solve, mpc_stats
 
+    # policy: the MPC action plus a fixed per-env perturbation (N(0, 0.1) on v, N(0, 0.2) on w, clipped to the action
+    # box). Without it every robot would follow the identical trajectory and all E MPC problems would be the same one.
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    noise = torch.randn((64, E, 2), generator=gen, device=dev, dtype=torch.float64) * torch.tensor([0.1, 0.2], device=dev, dtype=torch.float64)
+    lo = torch.tensor([0.0, -1.0], device=dev, dtype=torch.float64)
+    hi = torch.tensor([1.0, 1.0], device=dev, dtype=torch.float64)
+    tick = [0]
+
     def step():
-        act.copy_(env.out["mpc_actions"][:, :2])   # policy: execute the MPC action (alpha = 0)
+        torch.add(env.out["mpc_actions"][:, :2], noise[tick[0] % 64], out=act)
+        torch.clamp(act, lo, hi, out=act)
+        tick[0] += 1
         env.step(act)
 
     for _ in range(max(a.warmup, 3)):
@@ -282,15 +292,18 @@ def run_ours(a):
                         "peaks_tflops": {"fp32": peak32.value, "fp64": peak64.value}}
 
     # ---------------- end to end through the host-buffer C-ABI call (closed loop through host memory) ----------------
-    a_host = np.ascontiguousarray(env.out["mpc_actions"][:, :2].cpu().numpy())
-    for _ in range(3):
-        views = env.step_host(a_host); a_host = np.ascontiguousarray(views["mpc_actions"][:, :2])
+    noise_h = noise[:8].cpu().numpy()
+    a_host = torch.empty((E, 2), dtype=torch.float64).pin_memory().numpy()
+    a_host[:] = env.out["mpc_actions"][:, :2].cpu().numpy()
+    for i in range(3):
+        views = env.step_host(a_host)
+        np.clip(views["mpc_actions"][:, :2] + noise_h[i % 8], [0.0, -1.0], [1.0, 1.0], out=a_host)
     n_e2e = min(a.steps, 50)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
+    for i in range(n_e2e):
         views = env.step_host(a_host)
-        a_host = np.ascontiguousarray(views["mpc_actions"][:, :2])
+        np.clip(views["mpc_actions"][:, :2] + noise_h[i % 8], [0.0, -1.0], [1.0, 1.0], out=a_host)   # host-side policy
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()

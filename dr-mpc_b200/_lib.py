@@ -58,7 +58,7 @@ class EnvStateView(ctypes.Structure):
 class StepOut(ctypes.Structure):
     _fields_ = [(n, c_vp) for n in ("pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode",
                                     "spatial_edges", "human_valid", "detected_humans", "rewards", "info", "done_bits",
-                                    "mpc_status", "slab")] + [("slab_bytes", ctypes.c_size_t)]
+                                    "mpc_status", "done_flags", "slab")] + [("slab_bytes", ctypes.c_size_t)]
 
 
 _lib = None

@@ -96,6 +96,7 @@ void carve_slab(const EnvDev &D, int n_mpc_act, void *base, dre_step_out &o, Env
     o.info = od.info = c.take<double>(E * 8);
     o.done_bits = od.done_bits = c.take<uint32_t>(E);
     o.mpc_status = od.mpc_status = c.take<dre_mpc_status>(E);
+    o.done_flags = od.done_flags = c.take<uint8_t>(E * 12);
     bytes = (c.off + 255) / 256 * 256;
     o.slab = base;
     o.slab_bytes = bytes;

@@ -413,6 +413,19 @@ __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
             D.out.rewards[(size_t)e * 3] = reward;
             D.out.rewards[(size_t)e * 3 + 2] = reward + r_ha;
             D.out.done_bits[e] = all;
+            {   // unpacked 0/1 flags so the host mirror can hand out views without launching kernels
+                const uint32_t order[12] = {DRE_DONE_PT, DRE_DONE_HA, DRE_DONE_ANY, DRE_DONE_FOR_REPLAY, DRE_DONE_GOAL, DRE_DONE_COLLISION,
+                                            DRE_DONE_SAFETY_HUMAN, DRE_DONE_TIMEOUT, DRE_DONE_END_OF_PATH, DRE_DONE_CORRIDOR_HIT,
+                                            DRE_DONE_SAFETY_CORRIDOR, DRE_DONE_ACTUATION};
+                uint32_t w0 = 0, w1 = 0, w2 = 0;
+                for (int i = 0; i < 4; ++i) {
+                    w0 |= (uint32_t)((all & order[i]) != 0) << (8 * i);
+                    w1 |= (uint32_t)((all & order[4 + i]) != 0) << (8 * i);
+                    w2 |= (uint32_t)((all & order[8 + i]) != 0) << (8 * i);
+                }
+                uint32_t *df = reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 12);
+                df[0] = w0; df[1] = w1; df[2] = w2;
+            }
             D.out.info[(size_t)e * 8 + 2] = adv; D.out.info[(size_t)e * 8 + 3] = devr;
             D.out.info[(size_t)e * 8 + 5] = cur.index; D.out.info[(size_t)e * 8 + 6] = xy_dev; D.out.info[(size_t)e * 8 + 7] = prv.index;
             cnt[0] = 1;

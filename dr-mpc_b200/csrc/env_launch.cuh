@@ -7,6 +7,7 @@ struct EnvOutDev {
         *detected_humans, *rewards, *info;
     uint32_t *done_bits;
     dre_mpc_status *mpc_status;
+    uint8_t *done_flags;
 };
 
 struct EnvDev {

@@ -253,7 +253,7 @@ template <class Grp>
 DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
                              int maxNeighbors, float invTH, float invDt, float *sdist, OLine *L, float &outx, float &outy,
-                             dre_orca_stats *st)
+                             dre_orca_stats *st, bool debug_skip_lp3 = false)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
@@ -286,7 +286,7 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     float rx, ry;
     int n_lp1 = 0, lp1_work = 0, nproj = 0;
     const int fail = orca_lp2(g, L, m, maxSpeed, prefx, prefy, false, rx, ry, &n_lp1, &lp1_work);
-    if (fail < m) nproj = orca_lp3(g, L, m, fail, maxSpeed, rx, ry, L + nA);
+    if (fail < m && !debug_skip_lp3) nproj = orca_lp3(g, L, m, fail, maxSpeed, rx, ry, L + nA);
     outx = rx; outy = ry;
     if (st) {
 #pragma unroll

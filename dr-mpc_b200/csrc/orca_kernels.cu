@@ -91,7 +91,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
             const float *A = agents + (size_t)el * 5 * nA;
             orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
                              p.max_speed_self, p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy,
-                             stats ? &stats[gidx] : nullptr);
+                             stats ? &stats[gidx] : nullptr, (p.group_lanes & 0x100) != 0);
         }
         if (g.rank() == 0) vnew[gidx] = make_float2(ox, oy);
         g.sync();
@@ -121,6 +121,8 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
 
 int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
+    const int gl = p.group_lanes & 0xff;
+    if (gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32) return gl;
     if (p.group_lanes == 2 || p.group_lanes == 4 || p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
     const int nA = Nh + (p.robot_visible ? 1 : 0);
     return nA <= 8 ? 4 : 8;   // measured on B200: 8 lanes per agent is fastest from 10 to 50 humans (profiles/)

@@ -90,7 +90,7 @@ class BatchedHAAndPTEnv:
                         ("spatial_edges", o.spatial_edges, (E, Nh, 2 * H), "f8"), ("human_valid", o.human_valid, (E, Nh), "f8"),
                         ("detected_humans", o.detected_humans, (E,), "f8"), ("rewards", o.rewards, (E, 3), "f8"),
                         ("info", o.info, (E, 8), "f8"), ("done_bits", o.done_bits, (E,), "i4"),
-                        ("mpc_status", o.mpc_status, (E, 8), "i4")]
+                        ("mpc_status", o.mpc_status, (E, 8), "i4"), ("done_flags", o.done_flags, (E, 12), "u1")]
         self.out = {name: _view(ptr, shape, kind, d) for name, ptr, shape, kind in self._layout}
         s = _lib.EnvStateView()
         _lib.check(self._L.dre_env_state(self._h, ctypes.byref(s)))
@@ -132,18 +132,19 @@ class BatchedHAAndPTEnv:
         return self._package()
 
     def _package(self):
+        import torch
         o = self.out
         bits = o["done_bits"]
         r = o["rewards"]
         reward_return = {'R_PT': r[:, 0], 'R_DO': r[:, 1], 'R': r[:, 2]}
-        done_return = {k: (bits & DONE_BITS[k]) != 0 for k in ('done_PT', 'done_HA', 'done', 'done_for_replay')}
+        fl = o["done_flags"].view(torch.bool)       # zero-copy [E,12] views: no kernels are launched to package a step
+        done_return = {k: fl[:, i] for i, k in enumerate(('done_PT', 'done_HA', 'done', 'done_for_replay'))}
         info = {'done_bits': bits, 'disturbance_v': o["info"][:, 0], 'disturbance_th': o["info"][:, 1],
                 'path_advancement': o["info"][:, 2], 'deviation': o["info"][:, 3], 'dmin': o["info"][:, 4],
                 'interp_index': o["info"][:, 5], 'xy_dev': o["info"][:, 6], 'mpc_status': o["mpc_status"]}
-        eps_done_info = {'success': (bits & DONE_BITS['goal']) != 0}
-        for k in ('collision', 'safety_human_raise', 'timeout', 'deviation_end_of_path', 'corridor_hit',
-                  'safety_corridor_raise', 'actuation_termination'):
-            eps_done_info[k] = (bits & DONE_BITS[k]) != 0
+        eps_done_info = {k: fl[:, 4 + i] for i, k in enumerate(('success', 'collision', 'safety_human_raise', 'timeout',
+                                                                 'deviation_end_of_path', 'corridor_hit',
+                                                                 'safety_corridor_raise', 'actuation_termination'))}
         return self._obs(), reward_return, done_return, info, eps_done_info
 
     def observe(self, solve_mpc=False):

@@ -181,6 +181,9 @@ typedef struct dre_step_out {
     double *info;            /* [E][8]  disturbance_v, disturbance_th, path_advancement, deviation, dmin, interp_index, xy_dev, spare */
     uint32_t *done_bits;     /* [E]     DRE_DONE_* bits        (env.py:391-414)    */
     dre_mpc_status *mpc_status; /* [E]                                              */
+    uint8_t *done_flags;     /* [E][12] 0/1: done_PT, done_HA, done, done_for_replay (env.py:414), then eps_done_info
+                                (env.py:391-404): success, collision, safety_human_raise, timeout, deviation_end_of_path,
+                                corridor_hit, safety_corridor_raise, actuation_termination */
     void *slab;              /* start of the contiguous slab                        */
     size_t slab_bytes;
 } dre_step_out;

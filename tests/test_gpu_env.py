@@ -70,6 +70,9 @@ def test_step_matches_reference_teacher_forced(golden_env, tag, Nh):
     assert np.abs(o["info"][:, 3] - g[f"{tag}_out_deviation"]).max() <= 1e-9
     assert np.array_equal(o["done_bits"] & 0xFF, g[f"{tag}_out_bits"].astype(np.int64) & 0xFF)
     assert np.array_equal((o["done_bits"] >> 16) & 1, g[f"{tag}_out_done_HA"]) and np.array_equal((o["done_bits"] >> 17) & 1, g[f"{tag}_out_done_PT"])
+    assert np.array_equal(D['done_HA'].cpu().numpy(), g[f"{tag}_out_done_HA"].astype(bool)) and np.array_equal(D['done_PT'].cpu().numpy(), g[f"{tag}_out_done_PT"].astype(bool))
+    assert np.array_equal(D['done'].cpu().numpy(), (g[f"{tag}_out_bits"] & 0xFF) != 0) and np.array_equal(eps['success'].cpu().numpy(), (g[f"{tag}_out_bits"] & 16) != 0)
+    assert np.array_equal(eps['safety_human_raise'].cpu().numpy(), (g[f"{tag}_out_bits"] & 2) != 0)
     # --- MPC controls ---
     d = np.abs(o["mpc_actions"] - g[f"{tag}_out_mpc_actions"]).max(1)
     print(f"{tag}: {T} transitions, MPC max|du|={d.max():.2e}, >1e-6: {int((d > 1e-6).sum())}")

@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=16384)
     ap.add_argument("--humans", type=int, default=20)
     ap.add_argument("--horizon", type=int, default=4)
-    ap.add_argument("--cpu-envs", type=int, default=2048, help="envs of the bounded CPU sample")
+    ap.add_argument("--cpu-envs", type=int, default=4096, help="envs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -71,7 +71,7 @@ def cpu_env_steps_per_sec(a, envs, budget_s, threads):
     t0 = time.perf_counter()
     arr = env.step(act, nthreads=threads); act = arr["mpc_actions"][:, :2].copy()
     one = time.perf_counter() - t0
-    steps = max(3, min(200, int(budget_s / max(one, 1e-6))))
+    steps = max(3, min(2000, int(budget_s / max(one, 1e-6))))
     t0 = time.perf_counter()
     for _ in range(steps):
         arr = env.step(act, nthreads=threads); act = arr["mpc_actions"][:, :2].copy()

@@ -150,6 +150,7 @@ extern "C" int dre_mpc_create(const dre_mpc_params *p, int32_t N, dre_mpc **out)
     if ((e = cudaMalloc(&h->st.warm_T, K * N * 4 * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&h->st.warm_u, K * N * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&h->st.iteration0, (size_t)N)) != cudaSuccess ||
+        (e = cudaMalloc(&h->st.queue, 64)) != cudaSuccess || 
         (e = cudaMemset(h->st.warm_T, 0, K * N * 4 * sizeof(double))) != cudaSuccess ||
         (e = cudaMemset(h->st.warm_u, 0, K * N * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaMemset(h->st.iteration0, 1, (size_t)N)) != cudaSuccess) {
@@ -164,7 +165,7 @@ extern "C" int dre_mpc_create(const dre_mpc_params *p, int32_t N, dre_mpc **out)
 extern "C" int dre_mpc_destroy(dre_mpc *h)
 {
     if (!h) return DRE_OK;
-    cudaFree(h->st.warm_T); cudaFree(h->st.warm_u); cudaFree(h->st.iteration0);
+    cudaFree(h->st.warm_T); cudaFree(h->st.warm_u); cudaFree(h->st.iteration0); cudaFree(h->st.queue);
     cudaFree(h->d_paths); cudaFree(h->d_lens);
     cudaFree(h->d_pid); cudaFree(h->d_interp); cudaFree(h->d_pose); cudaFree(h->d_ctrl); cudaFree(h->d_status);
     delete h;

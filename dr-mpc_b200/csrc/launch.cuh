@@ -25,6 +25,7 @@ struct MpcDeviceState {
     double *warm_T;      // [N][K][4]  (c,s,x,y) of the inverse-pose guesses T_1..T_K
     double *warm_u;      // [N][K][2]
     uint8_t *iteration0; // [N]
+    int *queue;          // work counter of the persistent MPC kernel
     const double *paths; // [P][3][stride]
     const int32_t *lens; // [P]
     int num_paths, path_stride;

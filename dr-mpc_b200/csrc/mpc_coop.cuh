@@ -241,11 +241,32 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
     return ok;
 }
 
-// One problem per G-lane group. Same semantics as mpc_act_one (mpc_device.cuh).
+// Arguments of one batched act() call (device pointers).
+struct CoopBatch {
+    int N;
+    const int32_t *path_id;
+    const double *interp_index, *pose;
+    int pose_stride;
+    double *controls;
+    int controls_stride, controls_count;
+    dre_mpc_status *status;
+    const uint8_t *active_mask;
+    const double *paths;
+    const int32_t *lens;
+    int num_paths, path_stride;
+    double4 *warm_T;      // [N][K]
+    double2 *warm_u;      // [N][K]
+    uint8_t *iteration0;  // [N]
+    int *queue;           // work counter (zeroed before the launch)
+};
+
+// PERSISTENT lane-group loop: a group of G lanes pulls problems from a global counter and runs one LM attempt
+// (damped solve + up to two trials) per loop iteration. LM paths differ per problem (3 to 60 attempts), and the 32/G
+// groups of a warp advance in lock-step per iteration; letting a finished group fetch the next problem immediately
+// keeps every group busy instead of idling until the slowest problem of its warp is done.
+// Semantics per problem: identical to mpc_act_one (mpc_device.cuh) = reference MPC.act (mpc.py:58-206).
 template <int G>
-__device__ void mpc_act_coop(const LaneGroup<G> &g, const dre_mpc_params &prm, const double *path, int stride, int L,
-                             double interp_idx, double px, double py, double pth, double4 *warm_T, double2 *warm_u,
-                             uint8_t *it0, double *controls, int ncontrols, dre_mpc_status *status_out)
+__device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params &prm, const CoopBatch &B)
 {
     MpcConst C;
     C.K = prm.horizon; C.dt = prm.time_step; C.vmax = prm.v_max; C.wmax = prm.w_max;
@@ -253,33 +274,58 @@ __device__ void mpc_act_coop(const LaneGroup<G> &g, const dre_mpc_params &prm, c
     const int K = C.K, k = g.lane;
     const bool act = k < K;
     const double inc = (prm.v_max * 0.99) * prm.time_step / prm.node_separation;
-    const Se2 T0 = se2_from_pose_inv(px, py, pth);
-    // ---- this lane's reference pose and initial guess ----
-    Se2 Mk, Tinit;
-    double uinit[2];
-    {
-        double target = interp_idx + inc;
-        for (int i = 0; i < k && i < K; ++i) target += inc;      // accumulate like the reference loop (mpc.py:214,224)
-        double r[3];
-        mpc_ref_pose(path, stride, L, target, r);
-        Mk = se2_from_pose_inv(r[0], r[1], r[2]);
-    }
-    const bool first_call = (*it0 != 0);
-    if (first_call || !act) { Tinit = Mk; uinit[0] = prm.v_max / 2.0; uinit[1] = 0.0; }
-    else {
-        const double4 w = warm_T[k];
-        const double2 uu = warm_u[k];
-        Tinit.c = w.x; Tinit.s = w.y; Tinit.x = w.z; Tinit.y = w.w;
-        uinit[0] = uu.x; uinit[1] = uu.y;
-    }
-    // ---- LM state machine ----
-    Se2 Tk1 = Tinit;
-    double u[2] = {uinit[0], uinit[1]};
+
+    // ---- per-problem state (registers) ----
+    int n = -1;
+    bool have = false, exhausted = false;
+    Se2 T0, Mk, Tinit, Tk1;
+    double uinit[2] = {0.0, 0.0}, u[2] = {0.0, 0.0};
     CoopRow R;
     double s = 1.0, lambda = 1e-7, curr = 0.0, prev = 0.0, gn = 0.0;
     int iter = 0, nb = 0, retries = 0, term = 0, lm_solves = 0, cost_evals = 0;
     bool need_cost0 = true, need_build = false;
-    while (term == 0) {
+    T0.c = 1.0; T0.s = 0.0; T0.x = 0.0; T0.y = 0.0;
+    Mk = T0; Tinit = T0; Tk1 = T0;
+
+    for (;;) {
+        // ---- fetch + initialise the next problem ----
+        if (!have && !exhausted) {
+            for (;;) {
+                int t = 0;
+                if (g.lane == 0) t = atomicAdd(B.queue, 1);
+                t = __shfl_sync(g.mask, t, 0, G);
+                if (t >= B.N) { exhausted = true; break; }
+                if (B.active_mask == nullptr || B.active_mask[t]) { n = t; have = true; break; }
+            }
+            if (have) {
+                int pid = B.path_id ? B.path_id[n] : 0;
+                if (pid < 0 || pid >= B.num_paths) pid = 0;
+                const double *path = B.paths + (size_t)pid * 3 * B.path_stride;
+                const int L = B.lens[pid];
+                const double *ps = B.pose + (size_t)n * B.pose_stride;
+                T0 = se2_from_pose_inv(ps[0], ps[1], ps[2]);
+                double target = B.interp_index[n] + inc;
+                for (int i = 0; i < k && i < K; ++i) target += inc;      // accumulate like the reference loop (mpc.py:214,224)
+                double r[3];
+                mpc_ref_pose(path, B.path_stride, L, target, r);
+                Mk = se2_from_pose_inv(r[0], r[1], r[2]);
+                const bool first_call = (B.iteration0[n] != 0);
+                if (first_call || !act) { Tinit = Mk; uinit[0] = prm.v_max / 2.0; uinit[1] = 0.0; }   // mpc.py:68-71
+                else {
+                    const double4 w = B.warm_T[(size_t)n * K + k];
+                    const double2 uu = B.warm_u[(size_t)n * K + k];
+                    Tinit.c = w.x; Tinit.s = w.y; Tinit.x = w.z; Tinit.y = w.w;
+                    uinit[0] = uu.x; uinit[1] = uu.y;
+                }
+                Tk1 = Tinit; u[0] = uinit[0]; u[1] = uinit[1];
+                s = 1.0; lambda = 1e-7; curr = 0.0; prev = 0.0; gn = 0.0;
+                iter = 0; nb = 0; retries = 0; term = 0; lm_solves = 0; cost_evals = 0;
+                need_cost0 = true; need_build = false;
+            }
+        }
+        if (!have) break;
+
+        // ---- LM state machine: one damped solve + up to two trials per loop iteration (lev_marq...py:43-134) ----
         if (need_cost0) {
             const Se2 Tp = g.up(Tk1);
             const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tk1, u, Mk, 1.0 / s) : 0.0;
@@ -314,14 +360,14 @@ __device__ void mpc_act_coop(const LaneGroup<G> &g, const dre_mpc_params &prm, c
             for (int a = 0; a < 5; ++a) bb += R.b[a] * R.b[a];
             gn = sqrt(g.sum_ordered(act ? bb : 0.0, K));
         }
-        // ---- one damped solve + up to two trials (lev_marq...py:43-134) ----
         double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         ++lm_solves;
         bool success = false;
         double proposed = 0.0;
         Se2 Tt = Tk1;
         double ut[2] = {u[0], u[1]};
-        if (coop_solve(g, K, R, lambda, d)) {
+        const bool solved = coop_solve(g, K, R, lambda, d);
+        if (solved) {
             // whole-step feasibility scale, walking u_0..u_{K-1}, v then w (lev_marq...py:52-91)
             double scale = 1.0;
             for (int kk = 0; kk < K; ++kk) {
@@ -372,6 +418,15 @@ __device__ void mpc_act_coop(const LaneGroup<G> &g, const dre_mpc_params &prm, c
             lambda = fmax(lambda * 0.1, 1e-7);
             curr = proposed;
         } else {
+            // Once lambda sits at its cap (lev_marq...py:126,131: min(10*lambda, 1e7)) a failed attempt repeats itself
+            // verbatim -- same system, same step, same scale, same two rejected trials -- until max_shrink_steps runs out.
+            // Fast-forward those identical attempts (the counters advance as if they had been executed).
+            if (lambda >= 1e7) {
+                const int rem = 50 - (nb + 1);
+                lm_solves += rem;
+                if (solved) cost_evals += 2 * rem;
+                nb = 49;
+            }
             lambda = fmin(lambda * 10.0, 1e7);
             ++nb;
         }
@@ -392,29 +447,34 @@ __device__ void mpc_act_coop(const LaneGroup<G> &g, const dre_mpc_params &prm, c
             else if (fabs(prev - curr) / prev <= prm.rel_change_tol) term = 6;
             else need_build = true;
         }
-    }
-    // ---- outputs + warm start (mpc.py:147,192-205) ----
-    if (act) {
-        if (2 * k < ncontrols) controls[2 * k] = u[0];
-        if (2 * k + 1 < ncontrols) controls[2 * k + 1] = u[1];
-    }
-    const Se2 Tprev_final = g.up(Tk1);
-    if (act) {
-        if (k + 1 < K) warm_T[k] = make_double4(Tk1.c, Tk1.s, Tk1.x, Tk1.y);                 // T_{k+1} -> slot k
-        else {
-            const Se2 TL = (K >= 2) ? Tprev_final : T0;                                       // duplicate T_{K-1}
-            warm_T[k] = make_double4(TL.c, TL.s, TL.x, TL.y);
-        }
-        if (k >= 1) warm_u[k - 1] = make_double2(u[0], u[1]);
-        if (k == K - 1) warm_u[K - 1] = make_double2(0.5, 0.0);
-        if (k == 0) {
-            *it0 = 0;
-            if (status_out) {
-                dre_mpc_status st;
-                st.iterations = iter; st.retries = retries; st.lm_solves = lm_solves; st.cost_evals = cost_evals;
-                st.term = term; st.pad = 0; st.final_cost = curr;
-                *status_out = st;
+
+        // ---- problem finished: outputs + warm start (mpc.py:147,192-205) ----
+        if (term != 0) {
+            const Se2 Tprev_final = g.up(Tk1);
+            if (act) {
+                double *ctl = B.controls + (size_t)n * B.controls_stride;
+                if (2 * k < B.controls_count) ctl[2 * k] = u[0];
+                if (2 * k + 1 < B.controls_count) ctl[2 * k + 1] = u[1];
+                double4 *wT = B.warm_T + (size_t)n * K;
+                double2 *wu = B.warm_u + (size_t)n * K;
+                if (k + 1 < K) wT[k] = make_double4(Tk1.c, Tk1.s, Tk1.x, Tk1.y);                 // T_{k+1} -> slot k
+                else {
+                    const Se2 TL = (K >= 2) ? Tprev_final : T0;                                   // duplicate T_{K-1}
+                    wT[k] = make_double4(TL.c, TL.s, TL.x, TL.y);
+                }
+                if (k >= 1) wu[k - 1] = make_double2(u[0], u[1]);
+                if (k == K - 1) wu[K - 1] = make_double2(0.5, 0.0);
+                if (k == 0) {
+                    B.iteration0[n] = 0;
+                    if (B.status) {
+                        dre_mpc_status st;
+                        st.iterations = iter; st.retries = retries; st.lm_solves = lm_solves; st.cost_evals = cost_evals;
+                        st.term = term; st.pad = 0; st.final_cost = curr;
+                        B.status[n] = st;
+                    }
+                }
             }
+            have = false;
         }
     }
 }

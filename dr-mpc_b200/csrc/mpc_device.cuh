@@ -492,8 +492,13 @@ DRE_UNROLL_K
                         break;
                     }
                 }
-                if (!success) lambda = fmin(lambda * 10.0, 1e7);
+                if (!success) {
+                    // at the damping cap a failed attempt repeats itself verbatim: fast-forward (see mpc_coop.cuh)
+                    if (lambda >= 1e7) { const int rem = 50 - (nb + 1); R.lm_solves += rem; R.cost_evals += 2 * rem; nb = 49; }
+                    lambda = fmin(lambda * 10.0, 1e7);
+                }
             } else {
+                if (lambda >= 1e7) { R.lm_solves += 50 - (nb + 1); nb = 49; }
                 lambda = fmin(lambda * 10.0, 1e7);
             }
         }

@@ -12,23 +12,10 @@
 
 template <int G>
 __global__ void __launch_bounds__(128)
-mpc_coop_kernel(dre_mpc_params prm, MpcDeviceState st, const int32_t *__restrict__ path_id,
-                const double *__restrict__ interp_index, const double *__restrict__ pose, int pose_stride,
-                double *__restrict__ controls, int controls_stride, int controls_count,
-                dre_mpc_status *__restrict__ status, const uint8_t *__restrict__ active_mask)
+mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
-    const int n = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
     LaneGroup<G> g;
-    if (n >= st.N) return;                                   // group-uniform exits
-    if (active_mask != nullptr && !active_mask[n]) return;
-    int pid = path_id ? path_id[n] : 0;
-    if (pid < 0 || pid >= st.num_paths) pid = 0;
-    const double *path = st.paths + (size_t)pid * 3 * st.path_stride;
-    const size_t K = (size_t)prm.horizon;
-    mpc_act_coop<G>(g, prm, path, st.path_stride, st.lens[pid], interp_index[n], pose[(size_t)n * pose_stride],
-                    pose[(size_t)n * pose_stride + 1], pose[(size_t)n * pose_stride + 2],
-                    reinterpret_cast<double4 *>(st.warm_T) + (size_t)n * K, reinterpret_cast<double2 *>(st.warm_u) + (size_t)n * K,
-                    st.iteration0 + n, controls + (size_t)n * controls_stride, controls_count, status ? status + n : nullptr);
+    mpc_coop_persistent<G>(g, prm, B);
 }
 
 template <int G>
@@ -37,9 +24,24 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
                            dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
 {
     const int threads = 128, per_block = threads / G;
-    const int blocks = (st.N + per_block - 1) / per_block;
-    mpc_coop_kernel<G><<<blocks, threads, 0, s>>>(p, st, path_id, interp_index, pose, pose_stride, controls, controls_stride,
-                                                  controls_count, status, active_mask);
+    static int resident_blocks = 0;           // persistent grid: as many CTAs as fit on the device at once
+    if (resident_blocks == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        DRE_CUDA_TRY(cudaGetDevice(&dev));
+        DRE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G>, threads, 0));
+        resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    int blocks = (st.N + per_block - 1) / per_block;
+    if (blocks > resident_blocks) blocks = resident_blocks;
+    CoopBatch B;
+    B.N = st.N; B.path_id = path_id; B.interp_index = interp_index; B.pose = pose; B.pose_stride = pose_stride;
+    B.controls = controls; B.controls_stride = controls_stride; B.controls_count = controls_count; B.status = status;
+    B.active_mask = active_mask; B.paths = st.paths; B.lens = st.lens; B.num_paths = st.num_paths; B.path_stride = st.path_stride;
+    B.warm_T = reinterpret_cast<double4 *>(st.warm_T); B.warm_u = reinterpret_cast<double2 *>(st.warm_u);
+    B.iteration0 = st.iteration0; B.queue = st.queue;
+    DRE_CUDA_TRY(cudaMemsetAsync(st.queue, 0, sizeof(int), s));
+    mpc_coop_kernel<G><<<blocks, threads, 0, s>>>(p, B);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }

@@ -32,7 +32,7 @@ class MpcParams(ctypes.Structure):
 
 class MpcStatus(ctypes.Structure):
     _fields_ = [("iterations", c_i32), ("retries", c_i32), ("lm_solves", c_i32), ("cost_evals", c_i32),
-                ("term", c_i32), ("pad", c_i32), ("final_cost", c_d)]
+                ("term", c_i32), ("zero_steps", c_i32), ("final_cost", c_d)]
 
 
 class EnvConfig(ctypes.Structure):

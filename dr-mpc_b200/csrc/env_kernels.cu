@@ -30,7 +30,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     l.off_pos = seg((size_t)EPB * Nh * sizeof(double2));          // new human positions (fp64)
     l.off_pen = seg((size_t)EPB * Nh * 3 * sizeof(double));       // pen_v, pen_th, closest_dist per human
     l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
-    l.off_dist = seg((size_t)NG * nA * sizeof(float));
+    l.off_dist = seg((size_t)NG * ((nA + 3) & ~3) * sizeof(float));
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
     l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
     l.bytes = (o + 15) / 16 * 16;
@@ -38,13 +38,13 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
 }
 
 template <int G>
-__device__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
+__device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
                                bool pos_from_smem, unsigned long long *lp3_count, int *work_counter)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
-    float *sd = dist + (size_t)gi * nA;
+    float *sd = dist + (size_t)gi * ((nA + 3) & ~3);
     const float invTH = 1.0f / D.orca.time_horizon, invDt = 1.0f / D.orca.time_step;
     const int maxNb = D.orca.max_neighbors > 0 ? D.orca.max_neighbors : nA - 1;
     // LP3 (infeasible) solves cost an order of magnitude more than LP2 ones, so the groups of a CTA pull agents from a

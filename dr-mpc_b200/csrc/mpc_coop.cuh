@@ -155,6 +155,8 @@ __device__ __forceinline__ void coop_lane_build(const MpcConst &C, const Se2 &Tp
 }
 
 // Damped block-tridiagonal Cholesky as a K-stage lane pipeline. Returns false (group-uniform) on a non-positive pivot.
+// The diagonal slots of R.L hold the INVERSE pivots 1/l_cc (computed with one rsqrt per pivot): every later use of a
+// pivot is a division, so the dependent chain of a stage is multiplications only.
 template <int G>
 __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow &R, double lambda, double d[5])
 {
@@ -166,8 +168,8 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
     R.L[0] = R.L[2] = R.L[5] = R.L[9] = R.L[14] = 1.0;
     for (int j = 0; j < K; ++j) {
         // factor rows 2..4 and the forward-substituted rhs of the previous block
-        const double l22 = g.up(R.L[5]), l32 = g.up(R.L[8]), l33 = g.up(R.L[9]);
-        const double l42 = g.up(R.L[12]), l43 = g.up(R.L[13]), l44 = g.up(R.L[14]);
+        const double i22 = g.up(R.L[5]), l32 = g.up(R.L[8]), i33 = g.up(R.L[9]);
+        const double l42 = g.up(R.L[12]), l43 = g.up(R.L[13]), i44 = g.up(R.L[14]);
         const double y2 = g.up(y[2]), y3 = g.up(y[3]), y4 = g.up(y[4]);
         if (g.lane == j) {
             double S[15], rhs[5];
@@ -177,7 +179,6 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
 #pragma unroll
             for (int a = 0; a < 5; ++a) rhs[a] = R.b[a];
             if (j > 0) {
-                const double i22 = 1.0 / l22, i33 = 1.0 / l33, i44 = 1.0 / l44;
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
                     const double b2 = R.O[3 * a] * i22;
@@ -199,8 +200,8 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
 #pragma unroll
                 for (int m = 0; m < c; ++m) dd -= R.L[c * (c + 1) / 2 + m] * R.L[c * (c + 1) / 2 + m];
                 if (!(dd > 0.0)) { ok = false; dd = 1.0; }
-                const double ld = sqrt(dd), ild = 1.0 / ld;
-                R.L[c * (c + 1) / 2 + c] = ld;
+                const double ild = rsqrt(dd);
+                R.L[c * (c + 1) / 2 + c] = ild;
 #pragma unroll
                 for (int a = c + 1; a < 5; ++a) {
                     double v = S[a * (a + 1) / 2 + c];
@@ -214,7 +215,7 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
                 double v = rhs[a];
 #pragma unroll
                 for (int m = 0; m < a; ++m) v -= R.L[a * (a + 1) / 2 + m] * y[m];
-                y[a] = v / R.L[a * (a + 1) / 2 + a];
+                y[a] = v * R.L[a * (a + 1) / 2 + a];
             }
         }
     }
@@ -231,7 +232,7 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
                 double v = rhs[a];
 #pragma unroll
                 for (int m = a + 1; m < 5; ++m) v -= R.L[m * (m + 1) / 2 + a] * d[m];
-                d[a] = v / R.L[a * (a + 1) / 2 + a];
+                d[a] = v * R.L[a * (a + 1) / 2 + a];
             }
             t0 = t1 = t2 = 0.0;
 #pragma unroll
@@ -282,7 +283,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
     double uinit[2] = {0.0, 0.0}, u[2] = {0.0, 0.0};
     CoopRow R;
     double s = 1.0, lambda = 1e-7, curr = 0.0, prev = 0.0, gn = 0.0;
-    int iter = 0, nb = 0, retries = 0, term = 0, lm_solves = 0, cost_evals = 0;
+    int iter = 0, nb = 0, retries = 0, term = 0, lm_solves = 0, cost_evals = 0, zero_steps = 0;
     bool need_cost0 = true, need_build = false;
     T0.c = 1.0; T0.s = 0.0; T0.x = 0.0; T0.y = 0.0;
     Mk = T0; Tinit = T0; Tk1 = T0;
@@ -319,7 +320,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 }
                 Tk1 = Tinit; u[0] = uinit[0]; u[1] = uinit[1];
                 s = 1.0; lambda = 1e-7; curr = 0.0; prev = 0.0; gn = 0.0;
-                iter = 0; nb = 0; retries = 0; term = 0; lm_solves = 0; cost_evals = 0;
+                iter = 0; nb = 0; retries = 0; term = 0; lm_solves = 0; cost_evals = 0; zero_steps = 0;
                 need_cost0 = true; need_build = false;
             }
         }
@@ -369,23 +370,31 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         const bool solved = coop_solve(g, K, R, lambda, d);
         if (solved) {
             // whole-step feasibility scale, walking u_0..u_{K-1}, v then w (lev_marq...py:52-91)
+            // each lane prices its own two components; the walk itself only needs the quotients
+            double allowed[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const double dp = d[c], uc = u[c];
+                const double hi = c == 0 ? C.vmax : C.wmax, lo = c == 0 ? 0.0 : -C.wmax;
+                const double maxp = dp > 0.0 ? (hi - 1e-7) - uc : (lo + 1e-7) - uc;
+                allowed[c] = (dp != 0.0 && act) ? maxp / dp : INFINITY;
+            }
             double scale = 1.0;
             for (int kk = 0; kk < K; ++kk) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const double dp = g.bcast(d[c], kk), uc = g.bcast(u[c], kk);
-                    if (dp != 0.0) {
-                        const double hi = c == 0 ? C.vmax : C.wmax, lo = c == 0 ? 0.0 : -C.wmax;
-                        const double maxp = dp > 0.0 ? (hi - 1e-7) - uc : (lo + 1e-7) - uc;
-                        const double allowed = maxp / dp;
-                        scale = fmin(scale, allowed);
-                        if (allowed < 1.0) scale = fmax(scale - 1e-7, 0.0);
-                    }
+                    const double al = g.bcast(allowed[c], kk);
+                    scale = fmin(scale, al);
+                    if (al < 1.0) scale = fmax(scale - 1e-7, 0.0);
                 }
             }
 #pragma unroll
             for (int a = 0; a < 5; ++a) d[a] *= scale;
-            for (int bt = 0; bt < 2; ++bt) {
+            // scale == 0 (a control sits on its bound and the step pushes outward): the proposed state IS the current
+            // state, both trials re-evaluate `curr` bit for bit, the predicted reduction is 0 and the ratio is defined as 0
+            // (lev_marq...py:110-113) -> both are rejected. Skip the two cost evaluations, keep the counters.
+            if (scale == 0.0) { cost_evals += 2; ++zero_steps; }
+            for (int bt = 0; bt < 2 && scale != 0.0; ++bt) {
                 if (bt > 0) {
 #pragma unroll
                     for (int a = 0; a < 5; ++a) d[a] *= 0.8;
@@ -469,7 +478,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                     if (B.status) {
                         dre_mpc_status st;
                         st.iterations = iter; st.retries = retries; st.lm_solves = lm_solves; st.cost_evals = cost_evals;
-                        st.term = term; st.pad = 0; st.final_cost = curr;
+                        st.term = term; st.zero_steps = zero_steps; st.final_cost = curr;
                         B.status[n] = st;
                     }
                 }

@@ -594,7 +594,7 @@ DRE_UNROLL_K
     if (status_out) {
         dre_mpc_status st;
         st.iterations = R.iterations; st.retries = retries; st.lm_solves = R.lm_solves; st.cost_evals = R.cost_evals;
-        st.term = term; st.pad = 0; st.final_cost = R.final_cost;
+        st.term = term; st.zero_steps = 0; st.final_cost = R.final_cost;
         *status_out = st;
     }
 }

@@ -10,15 +10,25 @@
 #include "mpc_coop.cuh"
 #include "launch.cuh"
 
-template <int G>
-__global__ void __launch_bounds__(128)
+// MINB = minimum resident CTAs per SM the register allocation is capped for (2: everything in registers;
+// 3 / 4: fewer registers, more warps to hide the fp64 dependency chains, some spills to L1)
+template <int G, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
     LaneGroup<G> g;
     mpc_coop_persistent<G>(g, prm, B);
 }
 
-template <int G>
+// DRE_MPC_MINB=2|3|4 overrides the occupancy target of the K <= 4 kernel (A/B measurements)
+static int dre_mpc_minb()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DRE_MPC_MINB"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+template <int G, int MINB>
 static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, const int32_t *path_id, const double *interp_index,
                            const double *pose, int pose_stride, double *controls, int controls_stride, int controls_count,
                            dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
@@ -29,7 +39,7 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
         int dev = 0, sms = 0, per_sm = 0;
         DRE_CUDA_TRY(cudaGetDevice(&dev));
         DRE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G>, threads, 0));
+        DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, 0));
         resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
     int blocks = (st.N + per_block - 1) / per_block;
@@ -41,7 +51,7 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
     B.warm_T = reinterpret_cast<double4 *>(st.warm_T); B.warm_u = reinterpret_cast<double2 *>(st.warm_u);
     B.iteration0 = st.iteration0; B.queue = st.queue;
     DRE_CUDA_TRY(cudaMemsetAsync(st.queue, 0, sizeof(int), s));
-    mpc_coop_kernel<G><<<blocks, threads, 0, s>>>(p, B);
+    mpc_coop_kernel<G, MINB><<<blocks, threads, 0, s>>>(p, B);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }
@@ -103,10 +113,16 @@ int dre_mpc_launch(const dre_mpc_params &p, const MpcDeviceState &st, const int3
     if (K < 1 || K > DRE_MAX_HORIZON || st.N <= 0 || st.paths == nullptr) return DRE_ERR_INVALID;
 #define DRE_MPC_ARGS p, st, path_id, interp_index, pose, pose_stride, controls, controls_stride, controls_count, status, active_mask, s
     if (!dre_mpc_force_serial()) {
-        if (K <= 4) return launch_mpc_coop<4>(DRE_MPC_ARGS);
-        if (K <= 8) return launch_mpc_coop<8>(DRE_MPC_ARGS);
-        if (K <= 16) return launch_mpc_coop<16>(DRE_MPC_ARGS);
-        if (K <= 32) return launch_mpc_coop<32>(DRE_MPC_ARGS);
+        if (K <= 4) {
+            switch (dre_mpc_minb()) {
+            case 3: return launch_mpc_coop<4, 3>(DRE_MPC_ARGS);
+            case 4: return launch_mpc_coop<4, 4>(DRE_MPC_ARGS);
+            default: return launch_mpc_coop<4, 2>(DRE_MPC_ARGS);
+            }
+        }
+        if (K <= 8) return launch_mpc_coop<8, 2>(DRE_MPC_ARGS);
+        if (K <= 16) return launch_mpc_coop<16, 2>(DRE_MPC_ARGS);
+        if (K <= 32) return launch_mpc_coop<32, 2>(DRE_MPC_ARGS);
     }
     if (K <= 4) return launch_mpc<4>(DRE_MPC_ARGS);
     if (K <= 10) return launch_mpc<10>(DRE_MPC_ARGS);

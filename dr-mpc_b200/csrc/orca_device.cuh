@@ -27,6 +27,26 @@ struct TileGroup {
     __device__ unsigned shfl_xor(unsigned v, int m) const { return t.shfl_xor(v, m); }
     __device__ int bcast(int v, int src) const { return t.shfl(v, src); }
     __device__ void sync() const { t.sync(); }
+    __device__ unsigned lane_mask() const
+    {
+        const unsigned wl = threadIdx.x & 31u;
+        return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(unsigned)(G - 1)));
+    }
+    // group-wide reductions in one REDUX instruction (sm_100a has the fp32 min/max forms; min/max are exact, so the
+    // result equals the sequential scan bit for bit)
+    __device__ int min_int(int v) const { return __reduce_min_sync(lane_mask(), v); }
+    __device__ float min_f32(float v) const
+    {
+        float r;
+        asm volatile("redux.sync.min.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(lane_mask()));
+        return r;
+    }
+    __device__ float max_f32(float v) const
+    {
+        float r;
+        asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(lane_mask()));
+        return r;
+    }
 };
 #endif
 
@@ -40,6 +60,9 @@ struct SerialGroup {
     DRE_HD unsigned shfl_xor(unsigned v, int) const { return v; }
     DRE_HD int bcast(int v, int) const { return v; }
     DRE_HD void sync() const {}
+    DRE_HD int min_int(int v) const { return v; }
+    DRE_HD float min_f32(float v) const { return v; }
+    DRE_HD float max_f32(float v) const { return v; }
 };
 
 struct OLine { float px, py, dx, dy; };   // point, direction (16 B, float4-compatible)
@@ -61,23 +84,30 @@ DRE_HD int dre_popc(unsigned b)
 #endif
 }
 
-// first line index i in [cursor, m) with det(dir_i, point_i - res) > thresh, else m
+DRE_HD unsigned dre_f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; unsigned u; } c; c.f = f; return c.u;
+#endif
+}
+
+// first line index i in [cursor, m) with det(dir_i, point_i - res) > thresh, else m.
+// Every lane tests all of its lines (independent loads, no loop-carried vote), then one group-wide min.
 template <class Grp>
 DRE_HD int orca_first_violated(const Grp &g, const OLine *L, int m, int cursor, float rx, float ry, float thresh)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
-    for (int base = (cursor / G) * G; base < m; base += G) {
-        const int i = base + lane;
-        bool v = false;
-        if (i >= cursor && i < m) {
-            const OLine l = L[i];
-            v = (l.dx * (l.py - ry) - l.dy * (l.px - rx)) > thresh;
-        }
-        const unsigned b = g.ballot(v);
-        if (b) return base + dre_ffs(b) - 1;
+    int best = m;
+#pragma unroll 1
+    for (int i = (cursor / G) * G + lane; i < m; i += G) {
+        const OLine l = L[i];
+        const bool v = (l.dx * (l.py - ry) - l.dy * (l.px - rx)) > thresh;
+        if (v && i >= cursor && i < best) best = i;
     }
-    return m;
+    return g.min_int(best);
 }
 
 // RVO2 linearProgram1 on pivot line i; lanes share the scan over lines j < i
@@ -94,6 +124,7 @@ DRE_HD bool orca_lp1(const Grp &g, const OLine *L, int i, float radius, float ox
     float tL = -dotProduct - sq;
     float tR = -dotProduct + sq;
     bool fail = false;
+#pragma unroll 1
     for (int j = lane; j < i; j += G) {
         const OLine lj = L[j];
         const float den = li.dx * lj.dy - li.dy * lj.dx;
@@ -106,11 +137,8 @@ DRE_HD bool orca_lp1(const Grp &g, const OLine *L, int i, float radius, float ox
             else tL = fmaxf(tL, t);
         }
     }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-        tR = fminf(tR, g.shfl_xor(tR, o));
-        tL = fmaxf(tL, g.shfl_xor(tL, o));
-    }
+    tR = g.min_f32(tR);
+    tL = g.max_f32(tL);
     fail = g.any(fail);
     if (fail || tL > tR) return false;
     if (dirOpt) {
@@ -123,77 +151,6 @@ DRE_HD bool orca_lp1(const Grp &g, const OLine *L, int i, float radius, float ox
         else { rx = li.px + t * li.dx; ry = li.py + t * li.dy; }
     }
     return true;
-}
-
-// RVO2 linearProgram2; returns the failing line index or m. n_lp1 / lp1_work are optional counters.
-template <class Grp>
-DRE_HD int orca_lp2(const Grp &g, const OLine *L, int m, float radius, float ox, float oy, bool dirOpt,
-                    float &rx, float &ry, int *n_lp1, int *lp1_work)
-{
-    if (dirOpt) { rx = ox * radius; ry = oy * radius; }
-    else if (ox * ox + oy * oy > radius * radius) {
-        const float inv = 1.0f / sqrtf(ox * ox + oy * oy);
-        rx = (ox * inv) * radius; ry = (oy * inv) * radius;
-    } else { rx = ox; ry = oy; }
-    int cursor = 0;
-    for (;;) {
-        const int i = orca_first_violated(g, L, m, cursor, rx, ry, 0.0f);
-        if (i >= m) return m;
-        const float tx = rx, ty = ry;
-        if (n_lp1) { *n_lp1 += 1; *lp1_work += i; }
-        if (!orca_lp1(g, L, i, radius, ox, oy, dirOpt, rx, ry)) { rx = tx; ry = ty; return i; }
-        cursor = i + 1;
-    }
-}
-
-// RVO2 linearProgram3 (no obstacle lines). P is scratch for the projected lines (capacity m).
-template <class Grp>
-DRE_HD int orca_lp3(const Grp &g, const OLine *L, int m, int beginLine, float radius, float &rx, float &ry, OLine *P)
-{
-    constexpr int G = Grp::size;
-    const int lane = g.rank();
-    float distance = 0.0f;
-    int cursor = beginLine, nproj = 0;
-    for (;;) {
-        const int i = orca_first_violated(g, L, m, cursor, rx, ry, distance);
-        if (i >= m) break;
-        const OLine li = L[i];
-        int cnt = 0;
-        for (int base = 0; base < i; base += G) {
-            const int j = base + lane;
-            bool keep = false;
-            OLine ln;
-            ln.px = ln.py = ln.dx = ln.dy = 0.0f;
-            if (j < i) {
-                const OLine lj = L[j];
-                const float determinant = li.dx * lj.dy - li.dy * lj.dx;
-                keep = true;
-                if (fabsf(determinant) <= DRE_RVO_EPSILON) {
-                    if (li.dx * lj.dx + li.dy * lj.dy > 0.0f) keep = false;
-                    else { ln.px = 0.5f * (li.px + lj.px); ln.py = 0.5f * (li.py + lj.py); }
-                } else {
-                    const float t = (lj.dx * (li.py - lj.py) - lj.dy * (li.px - lj.px)) / determinant;
-                    ln.px = li.px + t * li.dx; ln.py = li.py + t * li.dy;
-                }
-                if (keep) {
-                    const float ex = lj.dx - li.dx, ey = lj.dy - li.dy;
-                    const float inv = 1.0f / sqrtf(ex * ex + ey * ey);
-                    ln.dx = ex * inv; ln.dy = ey * inv;
-                }
-            }
-            const unsigned b = g.ballot(keep);
-            if (keep) P[cnt + dre_popc(b & ((1u << lane) - 1u))] = ln;
-            cnt += dre_popc(b);
-        }
-        g.sync();
-        const float tx = rx, ty = ry;
-        ++nproj;
-        if (orca_lp2(g, P, cnt, radius, -li.dy, li.dx, true, rx, ry, (int *)nullptr, (int *)nullptr) < cnt) { rx = tx; ry = ty; }
-        distance = li.dx * (li.py - ry) - li.dy * (li.px - rx);
-        g.sync();   // P is rewritten by the next outer iteration
-        cursor = i + 1;
-    }
-    return nproj;
 }
 
 // One ORCA half-plane (RVO2 Agent::computeNewVelocity, agent-agent branch)
@@ -248,7 +205,13 @@ DRE_HD OLine orca_make_line(float px, float py, float vx, float vy, float rs, fl
 
 // Full solve for agent `self` of a tile of nA agents held in (shared) arrays ax..ar. The other agents are the
 // tile's agents in index order skipping `self` (crowd_sim.py:274-280: other humans in list order, robot last).
-//   sdist : scratch float[nA] private to the group      L : scratch OLine[2*nA] private to the group
+//   sdist : scratch float[round_up(nA,4)], 16 B aligned, private to the group
+//   L     : scratch OLine[2*nA] private to the group (ORCA lines, then LP3's projected lines)
+//
+// RVO2's linearProgram2 / linearProgram3 are driven from ONE loop with a single LP2 body: stage 0 runs LP2 on the ORCA
+// lines with the preferred velocity; if it fails at line `fail`, every later violated line i re-enters the same body
+// with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
+// solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
 template <class Grp>
 DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
@@ -259,12 +222,19 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     const int lane = g.rank();
     const float px = ax[self], py = ay[self], vx = avx[self], vy = avy[self], rs = ar[self];
     const float rangeSq = neighborDist * neighborDist;
-    for (int j = lane; j < nA; j += G) {
-        const float dx = px - ax[j], dy = py - ay[j];
-        const float d = dx * dx + dy * dy;
-        sdist[j] = (j != self && d < rangeSq) ? d : INFINITY;
+    const int nA4 = (nA + 3) & ~3;
+    for (int j = lane; j < nA4; j += G) {
+        float d = INFINITY;
+        if (j < nA) {
+            const float dx = px - ax[j], dy = py - ay[j];
+            const float dd = dx * dx + dy * dy;
+            if (j != self && dd < rangeSq) d = dd;
+        }
+        sdist[j] = d;
     }
     g.sync();
+    // rank of neighbour j = #{k : (d_k, k) < (d_j, j)} (RVO2 insertNeighbor: ascending distSq, ties by visit order).
+    // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
     int cnt = 0;
     unsigned mask = 0;
     for (int base = 0; base < nA; base += G) {
@@ -272,21 +242,103 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
         const bool in = (j < nA) && (sdist[j] < INFINITY);
         cnt += dre_popc(g.ballot(in));
         if (in) {
-            const float dj = sdist[j];
-            int r = 0;
-            for (int k = 0; k < nA; ++k) {
-                const float dk = sdist[k];
-                r += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+            const unsigned uj = dre_f2u(sdist[j]);
+            int r = 0, eq = 0;
+#pragma unroll 2
+            for (int k = 0; k < nA4; k += 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(sdist + k);
+                const unsigned u0 = dre_f2u(q.x), u1 = dre_f2u(q.y), u2 = dre_f2u(q.z), u3 = dre_f2u(q.w);
+                r += (u0 < uj) + (u1 < uj) + (u2 < uj) + (u3 < uj);
+                eq += (u0 == uj) + (u1 == uj) + (u2 == uj) + (u3 == uj);
+            }
+            if (eq > 1) {   // exact ties (rare): earlier index first
+#pragma unroll 1
+                for (int k = 0; k < j; ++k) r += (dre_f2u(sdist[k]) == uj) ? 1 : 0;
             }
             if (r < maxNeighbors) L[r] = orca_make_line(px, py, vx, vy, rs, ax[j], ay[j], avx[j], avy[j], ar[j], invTH, invDt, mask);
         }
     }
     const int m = cnt < maxNeighbors ? cnt : maxNeighbors;
     g.sync();
-    float rx, ry;
-    int n_lp1 = 0, lp1_work = 0, nproj = 0;
-    const int fail = orca_lp2(g, L, m, maxSpeed, prefx, prefy, false, rx, ry, &n_lp1, &lp1_work);
-    if (fail < m && !debug_skip_lp3) nproj = orca_lp3(g, L, m, fail, maxSpeed, rx, ry, L + nA);
+
+    OLine *P = L + nA;                       // LP3's projected lines
+    float rx = 0.0f, ry = 0.0f;
+    int n_lp1 = 0, lp1_work = 0, nproj = 0, fail = m;
+    // arguments of the current LP2 run
+    const OLine *cl = L;
+    int cm = m;
+    float cox = prefx, coy = prefy;
+    bool dirOpt = false;
+    // LP3 state
+    bool stage0 = true;
+    int i3 = 0;
+    float distance = 0.0f, tx = 0.0f, ty = 0.0f;
+    OLine li3;
+    li3.px = li3.py = li3.dx = li3.dy = 0.0f;
+    for (;;) {
+        // ---- linearProgram2 on (cl, cm) ----
+        if (dirOpt) { rx = cox * maxSpeed; ry = coy * maxSpeed; }
+        else if (cox * cox + coy * coy > maxSpeed * maxSpeed) {
+            const float inv = 1.0f / sqrtf(cox * cox + coy * coy);
+            rx = (cox * inv) * maxSpeed; ry = (coy * inv) * maxSpeed;
+        } else { rx = cox; ry = coy; }
+        int failed_at = cm;
+        for (int cursor = 0;;) {
+            const int i = orca_first_violated(g, cl, cm, cursor, rx, ry, 0.0f);
+            if (i >= cm) break;
+            const float sx = rx, sy = ry;
+            if (stage0) { n_lp1 += 1; lp1_work += i; }
+            if (!orca_lp1(g, cl, i, maxSpeed, cox, coy, dirOpt, rx, ry)) { rx = sx; ry = sy; failed_at = i; break; }
+            cursor = i + 1;
+        }
+        // ---- linearProgram3 driver ----
+        if (stage0) {
+            stage0 = false;
+            fail = failed_at;
+            if (fail >= m || debug_skip_lp3) break;
+            i3 = fail;
+        } else {
+            if (failed_at < cm) { rx = tx; ry = ty; }
+            distance = li3.dx * (li3.py - ry) - li3.dy * (li3.px - rx);
+            g.sync();   // P is rewritten below
+            i3 = i3 + 1;
+        }
+        const int i = orca_first_violated(g, L, m, i3, rx, ry, distance);
+        if (i >= m) break;
+        i3 = i;
+        li3 = L[i];
+        int pc = 0;
+        for (int base = 0; base < i; base += G) {
+            const int j = base + lane;
+            bool keep = false;
+            OLine ln;
+            ln.px = ln.py = ln.dx = ln.dy = 0.0f;
+            if (j < i) {
+                const OLine lj = L[j];
+                const float determinant = li3.dx * lj.dy - li3.dy * lj.dx;
+                keep = true;
+                if (fabsf(determinant) <= DRE_RVO_EPSILON) {
+                    if (li3.dx * lj.dx + li3.dy * lj.dy > 0.0f) keep = false;
+                    else { ln.px = 0.5f * (li3.px + lj.px); ln.py = 0.5f * (li3.py + lj.py); }
+                } else {
+                    const float t = (lj.dx * (li3.py - lj.py) - lj.dy * (li3.px - lj.px)) / determinant;
+                    ln.px = li3.px + t * li3.dx; ln.py = li3.py + t * li3.dy;
+                }
+                if (keep) {
+                    const float ex = lj.dx - li3.dx, ey = lj.dy - li3.dy;
+                    const float inv = 1.0f / sqrtf(ex * ex + ey * ey);
+                    ln.dx = ex * inv; ln.dy = ey * inv;
+                }
+            }
+            const unsigned b = g.ballot(keep);
+            if (keep) P[pc + dre_popc(b & ((1u << lane) - 1u))] = ln;
+            pc += dre_popc(b);
+        }
+        g.sync();
+        tx = rx; ty = ry;
+        ++nproj;
+        cl = P; cm = pc; cox = -li3.dy; coy = li3.dx; dirOpt = true;
+    }
     outx = rx; outy = ry;
     if (st) {
 #pragma unroll

@@ -21,7 +21,7 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
     l.off_lines = 0;
     l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
     l.off_dist = (l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float) + 15) / 16 * 16;
-    l.bytes = (l.off_dist + (size_t)l.NG * l.nA * sizeof(float) + 15) / 16 * 16 + 16;   // + work counter
+    l.bytes = (l.off_dist + (size_t)l.NG * ((l.nA + 3) & ~3) * sizeof(float) + 15) / 16 * 16 + 16;   // + work counter
     return l;
 }
 
@@ -66,7 +66,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     TileGroup<G> g(cg::tiled_partition<G>(blk));
     const int gi = threadIdx.x / G;
     OLine *L = lines + (size_t)gi * 2 * nA;
-    float *sd = dist + (size_t)gi * nA;
+    float *sd = dist + (size_t)gi * ((nA + 3) & ~3);
     const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
     const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
 

@@ -9,7 +9,7 @@ from .orca import _is_torch, _dptr, _hptr
 from .paths import pack_paths
 
 MPC_STATUS_DTYPE = np.dtype([("iterations", "i4"), ("retries", "i4"), ("lm_solves", "i4"), ("cost_evals", "i4"),
-                             ("term", "i4"), ("pad", "i4"), ("final_cost", "f8")])
+                             ("term", "i4"), ("zero_steps", "i4"), ("final_cost", "f8")])
 
 
 class BatchedMPC:

@@ -92,7 +92,7 @@ typedef struct dre_mpc_status {
     int32_t lm_solves;   /* damped linear solves, all attempts                  */
     int32_t cost_evals;  /* trial cost evaluations, all attempts                */
     int32_t term;        /* 1 zero-gradient, 3 max iterations, 4 zero cost, 5 abs change, 6 rel change, -1 gave up */
-    int32_t pad;
+    int32_t zero_steps;  /* damped solves whose box-feasibility scale was exactly 0 (the step is void, both trials are rejected) */
     double final_cost;
 } dre_mpc_status;
 

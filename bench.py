@@ -201,7 +201,7 @@ def run_ours(a):
     S = env.reset()
     act = S['PT']['MPC_actions'][:, :2].clone()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    launches_per_step = 4                      # ha_step, pt_step, mpc_solve, mpc_stats
+    launches_per_step = 4                      # pt_step, mpc_solve, mpc_stats, ha_step
 
     # policy: the MPC action plus a fixed per-env perturbation (N(0, 0.1) on v, N(0, 0.2) on w, clipped to the action
     # box). Without it every robot would follow the identical trajectory and all E MPC problems would be the same one.
@@ -309,8 +309,9 @@ def run_ours(a):
     barrier()
     e2e = {"value": world * E * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 8, "d2h_bytes_per_step": env.slab_bytes,
            "steps": n_e2e, "ms_per_step": e2e_s / n_e2e * 1e3,
-           "what": "dre_env_step_host: pinned host actions -> H2D -> 4 kernels -> D2H of the whole output slab (observations, rewards, "
-                   "done bits, MPC status) -> host; the next action is read from the host slab"}
+           "what": "dre_env_step_host: pinned host actions -> H2D -> robot/path half + MPC solve -> crowd half in env chunks on two "
+                   "streams, each chunk's outputs copied D2H while the next computes -> the whole output slab (observations, rewards, "
+                   "done bits, MPC status) in pinned host memory; the next action is read from the host slab"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

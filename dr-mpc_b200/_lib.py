@@ -99,6 +99,7 @@ def load():
         L.dre_env_reset.argtypes = [c_vp, c_vp, c_vp, c_vp]
         L.dre_env_step.argtypes = [c_vp, c_vp, c_vp]
         L.dre_env_step_host.argtypes = [c_vp, c_vp, c_vp]
+        L.dre_env_set_host_chunks.argtypes = [c_vp, c_i32]
         L.dre_env_observe.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
         L.dre_env_set_profiling.argtypes = [c_vp, c_i32]

@@ -150,7 +150,8 @@ extern "C" int dre_mpc_create(const dre_mpc_params *p, int32_t N, dre_mpc **out)
     if ((e = cudaMalloc(&h->st.warm_T, K * N * 4 * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&h->st.warm_u, K * N * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&h->st.iteration0, (size_t)N)) != cudaSuccess ||
-        (e = cudaMalloc(&h->st.queue, 64)) != cudaSuccess || 
+        (e = cudaMalloc(&h->st.queue, 128)) != cudaSuccess || (e = cudaMemset(h->st.queue, 0, 128)) != cudaSuccess ||
+
         (e = cudaMemset(h->st.warm_T, 0, K * N * 4 * sizeof(double))) != cudaSuccess ||
         (e = cudaMemset(h->st.warm_u, 0, K * N * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaMemset(h->st.iteration0, 1, (size_t)N)) != cudaSuccess) {

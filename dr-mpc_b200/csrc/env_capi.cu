@@ -1,6 +1,9 @@
 // env_capi.cu -- extern "C" entry points of the batched environment (include/dre.h: dre_env_*).
 // Replaces HAAndPTEnv.reset/step (reference environment/HA_and_PT/human_avoidance_and_path_tracking_env.py:243-416).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 #include "env_launch.cuh"
@@ -15,6 +18,16 @@ struct dre_env {
     dre_step_out out;
     double *d_actions = nullptr;   // staging for step_host
     cudaStream_t own_stream = nullptr;
+    // step_host pipeline: one crowd-half launch; the last CTA of every env chunk raises a flag in mapped host memory,
+    // the host thread polls the flags and queues that chunk's D2H copy on the copy stream
+    static const int MAX_CHUNKS = 32;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_pt = nullptr, ev_done = nullptr;
+    int *h_flags = nullptr;        // mapped pinned host memory [MAX_CHUNKS]
+    int *d_flags = nullptr;        // its device alias
+    int *d_chunk_count = nullptr;  // device [MAX_CHUNKS]
+    int step_seq = 0;
+    int host_chunks = 8;
     bool was_reset = false;
     // per-kernel timing (bench.py's roofline leg)
     bool profiling = false;
@@ -29,10 +42,11 @@ static int prof_drain(dre_env *h)
 {
     for (int i = 0; i < h->ev_used; ++i) {
         DRE_CUDA_TRY(cudaEventSynchronize(h->ev[i][4]));
+        static const int slot[4] = {1, 2, 3, 0};   // launch order pt, mpc, stats, ha -> {ha, pt, mpc, stats}
         for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
             DRE_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[i][k], h->ev[i][k + 1]));
-            h->prof_ms[k] += ms;
+            h->prof_ms[slot[k]] += ms;
         }
         h->prof_steps++;
     }
@@ -146,11 +160,20 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     if ((e = cudaMalloc(&h->state_block, sbytes)) != cudaSuccess || (e = cudaMemset(h->state_block, 0, sbytes)) != cudaSuccess ||
         (e = cudaMalloc(&h->slab, obytes)) != cudaSuccess || (e = cudaMemset(h->slab, 0, obytes)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_actions, (size_t)D.E * 2 * sizeof(double))) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_pt, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&h->h_flags, dre_env::MAX_CHUNKS * sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer((void **)&h->d_flags, h->h_flags, 0)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_chunk_count, dre_env::MAX_CHUNKS * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(h->d_chunk_count, 0, dre_env::MAX_CHUNKS * sizeof(int))) != cudaSuccess) {
         dre_set_cuda_error(e, __FILE__, __LINE__);
         dre_env_destroy(h);
         return DRE_ERR_CUDA;
     }
+    memset(h->h_flags, 0, dre_env::MAX_CHUNKS * sizeof(int));
     carve_state(D, h->state_block, sbytes);
     carve_slab(D, n_mpc_actions(*cfg), h->slab, h->out, D.out, obytes);
     h->slab_bytes = obytes;
@@ -167,6 +190,12 @@ extern "C" int dre_env_destroy(dre_env *h)
     if (h->profiling) dre_env_set_profiling(h, 0);
     cudaFree(h->state_block); cudaFree(h->slab); cudaFree(h->d_actions);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_front) cudaEventDestroy(h->ev_front);
+    if (h->ev_pt) cudaEventDestroy(h->ev_pt);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    cudaFree(h->d_chunk_count);
     delete h;
     return DRE_OK;
 }
@@ -251,28 +280,31 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     EnvDev D = h->D;
     D.actions = actions;
+    // robot/path half + MPC solve first, crowd half (which merges rewards / dones) last: see env_kernels.cu
     if (!h->profiling) {
-        int rc = dre_env_launch_ha(D, 0, 1, s);
+        int rc = dre_env_launch_pt(D, 0, s);
         if (rc) return rc;
-        rc = dre_env_launch_pt(D, 0, s);
+        rc = env_solve_mpc(h, s);
         if (rc) return rc;
-        return env_solve_mpc(h, s);
+        return dre_env_launch_ha(D, 0, 1, s);
     }
     if (h->ev_used == dre_env::PROF_RING) { const int rc = prof_drain(h); if (rc) return rc; }
     cudaEvent_t *ev = h->ev[h->ev_used];
     const int nact = n_mpc_actions(h->cfg);
+    // event order = launch order: pt_step, mpc_solve, mpc_stats, ha_step (prof_drain maps them back to the
+    // documented {ha_step, pt_step, mpc_solve, mpc_stats} order)
     DRE_CUDA_TRY(cudaEventRecord(ev[0], s));
-    int rc = dre_env_launch_ha(D, 0, 1, s);
+    int rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(ev[1], s));
-    rc = dre_env_launch_pt(D, 0, s);
-    if (rc) return rc;
-    DRE_CUDA_TRY(cudaEventRecord(ev[2], s));
     rc = dre_mpc_launch(dre_mpc_params_of(h->mpc), dre_mpc_state_of(h->mpc), D.path_idx, D.mpc_interp, D.rpose, 4,
                         D.out.mpc_actions, nact, nact, D.out.mpc_status, nullptr, s);
     if (rc) return rc;
-    DRE_CUDA_TRY(cudaEventRecord(ev[3], s));
+    DRE_CUDA_TRY(cudaEventRecord(ev[2], s));
     rc = dre_env_launch_mpc_stats(D, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(ev[3], s));
+    rc = dre_env_launch_ha(D, 0, 1, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(ev[4], s));
     h->ev_used++;
@@ -305,15 +337,100 @@ extern "C" int dre_env_kernel_ms(dre_env *h, double *ms4, int64_t *steps, int32_
     return DRE_OK;
 }
 
+// step() on host buffers, pipelined: H2D actions -> robot/path half (its PT state travels during the MPC solve) -> MPC
+// -> ONE crowd-half launch whose CTAs finish roughly in env order; the last CTA of each env chunk raises a flag in
+// mapped host memory, this thread polls the flags and queues the chunk's observation copy, so of the whole D2H only the
+// last chunk's share and the small per-env fields are exposed.
 extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host)
 {
     if (!h || !actions_host || !slab_host) return DRE_ERR_INVALID;
-    cudaStream_t s = h->own_stream;
-    DRE_CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)h->D.E * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
-    const int rc = dre_env_step(h, h->d_actions, s);
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    cudaStream_t s = h->own_stream, c = h->copy_stream;
+    const int E = h->D.E, Nh = h->D.Nh, H = h->D.LB + 1;
+    static const bool trace = getenv("DRE_HOST_TRACE") != nullptr;   // measurement aid: host-side timeline of one call in 64
+    const bool tr = trace && (h->step_seq & 63) == 63;
+    auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_start = tr ? now_us() : 0.0;
+    double t_flag[dre_env::MAX_CHUNKS] = {}, t_front = 0.0, t_enq = 0.0;
+    DRE_CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)E * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    EnvDev D = h->D;
+    D.actions = h->d_actions;
+    char *dev = (char *)h->slab, *host = (char *)slab_host;
+    auto d2h = [&](const void *field, size_t per_env, int e0, int e1) -> cudaError_t {
+        const size_t off = (const char *)field - dev + (size_t)e0 * per_env;
+        return cudaMemcpyAsync(host + off, dev + off, (size_t)(e1 - e0) * per_env, cudaMemcpyDeviceToHost, c);
+    };
+    int rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
-    DRE_CUDA_TRY(cudaMemcpyAsync(slab_host, h->slab, h->slab_bytes, cudaMemcpyDeviceToHost, s));
-    DRE_CUDA_TRY(cudaStreamSynchronize(s));
+    // the PT state (the second largest output) is final after pt_step: it travels during the MPC solve
+    DRE_CUDA_TRY(cudaEventRecord(h->ev_pt, s));
+    DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_pt, 0));
+    DRE_CUDA_TRY(d2h(h->out.pt_state, (size_t)4 * (h->D.lookahead + h->D.lookbehind) * sizeof(double), 0, E));
+    rc = env_solve_mpc(h, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));
+    DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_front, 0));
+    DRE_CUDA_TRY(d2h(h->out.mpc_actions, (size_t)n_mpc_actions(h->cfg) * sizeof(double), 0, E));
+    // chunking: whole CTAs per chunk
+    const int epb = dre_env_ha_envs_per_cta(D);
+    int chunks = h->host_chunks < dre_env::MAX_CHUNKS ? h->host_chunks : dre_env::MAX_CHUNKS;
+    if (chunks < 1) chunks = 1;
+    int per = ((E + chunks - 1) / chunks + epb - 1) / epb * epb;
+    chunks = (E + per - 1) / per;
+    h->step_seq = h->step_seq == 0x7fffffff ? 1 : h->step_seq + 1;
+    D.chunk_flags = h->d_flags; D.chunk_count = h->d_chunk_count; D.chunk_envs = per; D.step_seq = h->step_seq;
+    rc = dre_env_launch_ha(D, 0, 1, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));
+    if (tr) { t_enq = now_us(); cudaEventSynchronize(h->ev_front); t_front = now_us(); }
+    volatile int *flags = h->h_flags;
+    for (int i = 0; i < chunks; ++i) {
+        const int e0 = i * per, e1 = e0 + per < E ? e0 + per : E;
+        for (unsigned spin = 0; flags[i] != h->step_seq; ++spin) {
+            if ((spin & 0x3ff) == 0x3ff) {   // the launch may have failed or finished without us seeing the flag yet
+                const cudaError_t q = cudaEventQuery(h->ev_done);
+                if (q == cudaSuccess) { if (flags[i] != h->step_seq) { h->h_flags[i] = h->step_seq; } break; }
+                if (q != cudaErrorNotReady) { dre_set_cuda_error(q, __FILE__, __LINE__); return DRE_ERR_CUDA; }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (tr) t_flag[i] = now_us();
+        // the pair history of the crowd is 3/4 of the crowd half's bytes: one copy per chunk
+        DRE_CUDA_TRY(d2h(h->out.spatial_edges, (size_t)Nh * 2 * H * sizeof(double), e0, e1));
+    }
+    // every CTA has written its observation: the small observation arrays go as two contiguous runs of the slab
+    // (robot_node .. percent_episode, human_valid .. detected_humans) while the last CTAs finish their look-ahead pass
+    {
+        const size_t a0 = (const char *)h->out.robot_node - dev, a1 = (const char *)h->out.spatial_edges - dev;
+        const size_t b0 = (const char *)h->out.human_valid - dev, b1 = (const char *)h->out.rewards - dev;
+        DRE_CUDA_TRY(cudaMemcpyAsync(host + a0, dev + a0, a1 - a0, cudaMemcpyDeviceToHost, c));
+        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
+    }
+    // rewards, info, done bits, MPC status, done flags (one run, ~130 B per env) once the launch is complete
+    DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_done, 0));
+    {
+        const size_t b0 = (const char *)h->out.rewards - dev, b1 = h->slab_bytes;
+        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
+    }
+    if (tr) {
+        cudaEventSynchronize(h->ev_done);
+        const double t_done = now_us();
+        cudaStreamSynchronize(c);
+        const double t_end = now_us();
+        fprintf(stderr, "[host trace] enqueued %.0f us, front (pt+mpc) done %.0f, chunk flags at", t_enq - t_start, t_front - t_start);
+        for (int i = 0; i < chunks; ++i) fprintf(stderr, " %.0f", t_flag[i] - t_start);
+        fprintf(stderr, ", crowd half done %.0f, copies done %.0f us\n", t_done - t_start, t_end - t_start);
+    }
+    DRE_CUDA_TRY(cudaStreamSynchronize(c));
+    return DRE_OK;
+}
+
+extern "C" int dre_env_set_host_chunks(dre_env *h, int32_t chunks)
+{
+    if (!h || chunks < 1 || chunks > dre_env::MAX_CHUNKS) return DRE_ERR_INVALID;
+    h->host_chunks = chunks;
     return DRE_OK;
 }
 

@@ -1,14 +1,21 @@
 // env_kernels.cu -- the batched env step around the ORCA pass and the MPC solve.
 // Compile with -fmad=false (bit-faithful fp32 ORCA, once-rounded fp64 env arithmetic).
 //
+// One env step = pt_step_kernel -> MPC solve -> ha_step_kernel. The robot's motion depends only on the action, so the
+// robot/path half of the step (and the MPC solve, which needs nothing but the new robot pose) runs FIRST: its outputs
+// can already travel to the host while the crowd half, which produces 3/4 of the output bytes, is still computing.
+//
+//   pt_step_kernel : robot unicycle step (agent.py:169-176) + PTEnv.step (path_tracking_env.py:80-101): 5 intermediate
+//                    poses, 2 localisations, PT rewards (reward_comp.py:20-116), optional path switch
+//                    (HA_and_PT env.py:130-141), PT state (path_tracking_core.py:94-145).
 //   ha_step_kernel : HAEnv.step / warm_start (reference human_avoidance_env.py:128-186, 79-125) for EPB envs per CTA:
-//                    ORCA pass 1 -> robot unicycle + human Euler integration -> history roll -> ORCA pass 2
+//                    ORCA pass 1 (robot at its previous pose) -> human Euler integration -> history roll -> ORCA pass 2
 //                    (disturbance look-ahead, :245) -> collision / safety / disturbance / actuation rewards (:189-291)
+//                    -> merge with the PT rewards / dones (HA_and_PT env.py:311-416), episode statistics
 //                    -> observation (:24-77) -> goal resampling (:181-184, crowd_sim.py:114-144 with Philox).
-//                    The env's agents live in a shared-memory fp32 SoA tile for both ORCA passes.
-//   pt_step_kernel : PTEnv.step (path_tracking_env.py:80-101): 5 intermediate poses, 2 localisations, PT rewards
-//                    (reward_comp.py:20-116), optional path switch (HA_and_PT env.py:130-141), PT state
-//                    (path_tracking_core.py:94-145), merge of rewards / dones (HA_and_PT env.py:311-416), episode stats.
+//                    The env's agents live in a shared-memory fp32 SoA tile for both ORCA passes. For the host path the
+//                    last CTA of every chunk of envs raises a flag in mapped host memory, so the D2H copy of a chunk's
+//                    observations starts while later CTAs of the same launch are still computing.
 //   env_reset_kernel : reset_continuous_task (HA_and_PT env.py:263-280) + HAEnv.reset (:297-338) + spawning
 //                    (crowd_sim.py:232-262 with Philox).
 #include "orca_device.cuh"
@@ -19,7 +26,7 @@
 // shared-memory layout of ha_step_kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct HaLayout {
-    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, bytes;
+    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, bytes;
 };
 static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
 {
@@ -33,6 +40,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     l.off_dist = seg((size_t)NG * ((nA + 3) & ~3) * sizeof(float));
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
     l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
+    l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -92,6 +100,8 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
     float *dist = reinterpret_cast<float *>(smem_raw + lay.off_dist);
     float2 *vnew = reinterpret_cast<float2 *>(smem_raw + lay.off_vnew);
     int *flags = reinterpret_cast<int *>(smem_raw + lay.off_flags);
+    unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(smem_raw + lay.off_stats);   // [9]
+    double *s_sum = reinterpret_cast<double *>(s_cnt + 9);                                            // [3]
     const int env0 = blockIdx.x * EPB;
     const double dt = D.dt;
 
@@ -111,12 +121,16 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
                     const float2 v = D.hvel[(size_t)e * Nh + a];
                     x = (float)q.x; y = (float)q.y; vx = v.x; vy = v.y;
                 } else {
-                    x = (float)D.rpose[(size_t)e * 4]; y = (float)D.rpose[(size_t)e * 4 + 1];
+                    // pt_step_kernel has already moved the robot: the humans act on its pose BEFORE the move
+                    // (human_avoidance_env.py:129 precedes :132)
+                    const double *rq = (mode == 0 ? D.rprev : D.rpose) + (size_t)e * 4;
+                    x = (float)rq[0]; y = (float)rq[1];
                 }
             }
             A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = D.orca.radius;
         }
         for (int t = threadIdx.x; t < EPB * 4 + 2; t += blockDim.x) flags[t] = 0;
+        if (threadIdx.x < 12) s_cnt[threadIdx.x] = 0ull;   // 9 counters + 3 double sums (0.0 == all-zero bits)
         __syncthreads();
 
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
@@ -155,16 +169,10 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
                 double av = 0.0, aw = 0.0;
                 if (mode == 0) {
                     av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1];
-                    double nx, ny, nth;
-                    D.rprev[(size_t)e * 4] = rp[0]; D.rprev[(size_t)e * 4 + 1] = rp[1]; D.rprev[(size_t)e * 4 + 2] = rp[2];
-                    unicycle_step(rp[0], rp[1], rp[2], av, aw, dt, nx, ny, nth);
-                    rp[0] = nx; rp[1] = ny; rp[2] = nth;
-                    if (D.orca.robot_visible) {
+                    if (D.orca.robot_visible) {   // pass 2 sees the robot at its new pose (already in rpose)
                         float *A = agents + (size_t)el * 5 * nA;
-                        A[Nh] = (float)nx; A[nA + Nh] = (float)ny;
+                        A[Nh] = (float)rp[0]; A[nA + Nh] = (float)rp[1];
                     }
-                    D.gtime[e] += dt;
-                    D.step_count[e] += 1;
                 }
                 // robot history (human_avoidance_env.py:133-141 / :114-122)
                 double *rh = D.rhist + (size_t)e * H * 4;
@@ -184,70 +192,10 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
         }
         __syncthreads();
 
-        if (mode == 0) {
-            // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
-            float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
-            orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1]);
-            __syncthreads();
-
-            // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
-            for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
-                const int el = t / Nh, i = t - el * Nh, e = env0 + el;
-                if (e >= D.E) continue;
-                const double2 hp = posd[el * Nh + i];
-                const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
-                const double dx = hp.x - rx, dy = hp.y - ry;
-                const double closest = sqrt(dx * dx + dy * dy) - D.human_radius - D.robot_radius;
-                double pv_ = 0.0, pth_ = 0.0;
-                if (!D.hstatic[(size_t)e * Nh + i] && !(closest > D.dist_radius || closest <= 0.0)) {
-                    const float *A = agents + (size_t)el * 5 * nA;
-                    const double cvx = (double)A[2 * nA + i], cvy = (double)A[3 * nA + i];
-                    const double fvx = (double)vnext[el * Nh + i].x, fvy = (double)vnext[el * Nh + i].y;
-                    const double curr_v = sqrt(cvx * cvx + cvy * cvy), fut_v = sqrt(fvx * fvx + fvy * fvy);
-                    const double curr_th = atan2(cvy, cvx), fut_th = atan2(fvy, fvx);
-                    const double dvm = fut_v - curr_v;
-                    const double pen_v_i = D.dist_factor_v * (dvm < 0.0 ? dvm : 0.0);
-                    const double th_diff = wrap_pi(fut_th - curr_th);
-                    const double pen_th_i = -D.dist_factor_th * fabs(th_diff);
-                    const double scaling = 1.0 - closest / D.dist_radius;
-                    pv_ = pen_v_i * scaling; pth_ = pen_th_i * scaling;
-                }
-                pen[(el * Nh + i) * 3] = pv_; pen[(el * Nh + i) * 3 + 1] = pth_; pen[(el * Nh + i) * 3 + 2] = closest;
-            }
-            __syncthreads();
-
-            // ---- per-env reward / done (one thread per env sums in human order, like the reference loop) ----
-            for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
-                const int e = env0 + el;
-                if (e >= D.E) continue;
-                double dmin = INFINITY, pen_v = 0.0, pen_th = 0.0;
-                bool collision = false;
-                for (int i = 0; i < Nh; ++i) {
-                    const double c = pen[(el * Nh + i) * 3 + 2];
-                    if (c <= 0.0) collision = true;
-                    else if (c < dmin) dmin = c;
-                    pen_v += pen[(el * Nh + i) * 3]; pen_th += pen[(el * Nh + i) * 3 + 1];
-                }
-                if (collision) dmin = 0.0;
-                double reward = 0.0;
-                uint32_t bits = 0;
-                if (collision) { reward += D.collision_penalty; bits |= DRE_DONE_COLLISION | DRE_DONE_HA; }
-                if (dmin < D.safety_dist) { reward += D.safety_penalty; bits |= DRE_DONE_SAFETY_HUMAN | DRE_DONE_HA; }
-                reward += (pen_v + pen_th);
-                double total_v = 0.0;
-                const double *pv = D.rpastv + (size_t)e * D.LB * 2;
-                for (int s = 0; s < D.LB; ++s) total_v += fabs(pv[s * 2]);
-                if (total_v < D.act_min_vel) { reward += D.act_penalty; bits |= DRE_DONE_ACTUATION | DRE_DONE_HA; }
-                D.out.rewards[(size_t)e * 3 + 1] = reward;
-                D.out.info[(size_t)e * 8 + 0] = pen_v; D.out.info[(size_t)e * 8 + 1] = pen_th; D.out.info[(size_t)e * 8 + 4] = dmin;
-                D.out.done_bits[e] = bits;
-            }
-        }
     }
 
     // ---- observation (human_avoidance_env.py:24-77), frame = 'robot' ----
     if (write_obs) {
-        if (mode != 2) __syncthreads();
         const int W = 2 * H;
         for (int t = threadIdx.x; t < EPB * Nh * H; t += blockDim.x) {
             const int el = t / (Nh * H), r = t - el * Nh * H, i = r / H, s = r - i * H, e = env0 + el;
@@ -284,6 +232,116 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
             if (e >= D.E) continue;
             D.out.percent_episode[e] = D.gtime[e] / D.time_limit * 10.0 - 5.0;
             D.out.detected_humans[e] = (double)Nh;
+        }
+    }
+
+    // ---- the observation of this CTA's envs is final: chunk flag for the pipelined host path (threadFenceReduction
+    // pattern: the last CTA of a chunk sees every other CTA's fenced writes through the counter, then publishes
+    // system-wide), raised BEFORE the look-ahead pass so the copy of a chunk overlaps the second half of its own CTAs ----
+    if (D.chunk_flags != nullptr && mode == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int ctas_per_chunk = D.chunk_envs / EPB;            // chunk_envs is a multiple of EPB
+            const int c = blockIdx.x / ctas_per_chunk;
+            const int first = c * ctas_per_chunk;
+            const int total = (int)gridDim.x - first < ctas_per_chunk ? (int)gridDim.x - first : ctas_per_chunk;
+            if (atomicAdd(D.chunk_count + c, 1) + 1 == total) {
+                D.chunk_count[c] = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(D.chunk_flags + c) = D.step_seq;
+            }
+        }
+    }
+
+    if (mode == 0) {
+        // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
+        float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
+        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1]);
+        __syncthreads();
+
+        // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
+        for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+            const int el = t / Nh, i = t - el * Nh, e = env0 + el;
+            if (e >= D.E) continue;
+            const double2 hp = posd[el * Nh + i];
+            const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
+            const double dx = hp.x - rx, dy = hp.y - ry;
+            const double closest = sqrt(dx * dx + dy * dy) - D.human_radius - D.robot_radius;
+            double pv_ = 0.0, pth_ = 0.0;
+            if (!D.hstatic[(size_t)e * Nh + i] && !(closest > D.dist_radius || closest <= 0.0)) {
+                const float *A = agents + (size_t)el * 5 * nA;
+                const double cvx = (double)A[2 * nA + i], cvy = (double)A[3 * nA + i];
+                const double fvx = (double)vnext[el * Nh + i].x, fvy = (double)vnext[el * Nh + i].y;
+                const double curr_v = sqrt(cvx * cvx + cvy * cvy), fut_v = sqrt(fvx * fvx + fvy * fvy);
+                const double curr_th = atan2(cvy, cvx), fut_th = atan2(fvy, fvx);
+                const double dvm = fut_v - curr_v;
+                const double pen_v_i = D.dist_factor_v * (dvm < 0.0 ? dvm : 0.0);
+                const double th_diff = wrap_pi(fut_th - curr_th);
+                const double pen_th_i = -D.dist_factor_th * fabs(th_diff);
+                const double scaling = 1.0 - closest / D.dist_radius;
+                pv_ = pen_v_i * scaling; pth_ = pen_th_i * scaling;
+            }
+            pen[(el * Nh + i) * 3] = pv_; pen[(el * Nh + i) * 3 + 1] = pth_; pen[(el * Nh + i) * 3 + 2] = closest;
+        }
+        __syncthreads();
+
+        // ---- per-env reward / done (one thread per env sums in human order, like the reference loop) ----
+        for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
+            const int e = env0 + el;
+            if (e >= D.E) continue;
+            double dmin = INFINITY, pen_v = 0.0, pen_th = 0.0;
+            bool collision = false;
+            for (int i = 0; i < Nh; ++i) {
+                const double c = pen[(el * Nh + i) * 3 + 2];
+                if (c <= 0.0) collision = true;
+                else if (c < dmin) dmin = c;
+                pen_v += pen[(el * Nh + i) * 3]; pen_th += pen[(el * Nh + i) * 3 + 1];
+            }
+            if (collision) dmin = 0.0;
+            double reward = 0.0;
+            uint32_t bits = 0;
+            if (collision) { reward += D.collision_penalty; bits |= DRE_DONE_COLLISION | DRE_DONE_HA; }
+            if (dmin < D.safety_dist) { reward += D.safety_penalty; bits |= DRE_DONE_SAFETY_HUMAN | DRE_DONE_HA; }
+            reward += (pen_v + pen_th);
+            double total_v = 0.0;
+            const double *pv = D.rpastv + (size_t)e * D.LB * 2;
+            for (int s = 0; s < D.LB; ++s) total_v += fabs(pv[s * 2]);
+            if (total_v < D.act_min_vel) { reward += D.act_penalty; bits |= DRE_DONE_ACTUATION | DRE_DONE_HA; }
+            D.out.info[(size_t)e * 8 + 0] = pen_v; D.out.info[(size_t)e * 8 + 1] = pen_th; D.out.info[(size_t)e * 8 + 4] = dmin;
+            // ---- merge with the PT part written by pt_step_kernel (HA_and_PT env.py:322-331, 391-414) ----
+            const double r_pt = D.out.rewards[(size_t)e * 3];
+            uint32_t all = D.out.done_bits[e] | bits;
+            if (all & (DRE_DONE_HA | DRE_DONE_PT)) all |= DRE_DONE_ANY | DRE_DONE_FOR_REPLAY;
+            D.out.rewards[(size_t)e * 3 + 1] = reward;
+            D.out.rewards[(size_t)e * 3 + 2] = r_pt + reward;
+            D.out.done_bits[e] = all;
+            {   // unpacked 0/1 flags so the host mirror can hand out views without launching kernels
+                const uint32_t order[12] = {DRE_DONE_PT, DRE_DONE_HA, DRE_DONE_ANY, DRE_DONE_FOR_REPLAY, DRE_DONE_GOAL, DRE_DONE_COLLISION,
+                                            DRE_DONE_SAFETY_HUMAN, DRE_DONE_TIMEOUT, DRE_DONE_END_OF_PATH, DRE_DONE_CORRIDOR_HIT,
+                                            DRE_DONE_SAFETY_CORRIDOR, DRE_DONE_ACTUATION};
+                uint32_t w0 = 0, w1 = 0, w2 = 0;
+                for (int q = 0; q < 4; ++q) {
+                    w0 |= (uint32_t)((all & order[q]) != 0) << (8 * q);
+                    w1 |= (uint32_t)((all & order[4 + q]) != 0) << (8 * q);
+                    w2 |= (uint32_t)((all & order[8 + q]) != 0) << (8 * q);
+                }
+                uint32_t *df = reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 12);
+                df[0] = w0; df[1] = w1; df[2] = w2;
+            }
+            if (D.stat_counters) {
+                const uint32_t sb[8] = {DRE_DONE_GOAL, DRE_DONE_COLLISION, DRE_DONE_SAFETY_HUMAN, DRE_DONE_TIMEOUT, DRE_DONE_END_OF_PATH,
+                                        DRE_DONE_CORRIDOR_HIT, DRE_DONE_SAFETY_CORRIDOR, DRE_DONE_ACTUATION};
+                atomicAdd(&s_cnt[0], 1ull);
+                for (int q = 0; q < 8; ++q)
+                    if (all & sb[q]) atomicAdd(&s_cnt[1 + q], 1ull);
+                atomicAdd(&s_sum[0], r_pt + reward); atomicAdd(&s_sum[1], r_pt); atomicAdd(&s_sum[2], reward);
+            }
+        }
+        __syncthreads();
+        if (D.stat_counters) {   // one global atomic per counter per CTA
+            if (threadIdx.x < 9 && s_cnt[threadIdx.x]) atomicAdd(D.stat_counters + threadIdx.x, s_cnt[threadIdx.x]);
+            if (threadIdx.x >= 9 && threadIdx.x < 12) atomicAdd(D.stat_sums + (threadIdx.x - 9), s_sum[threadIdx.x - 9]);
         }
     }
 
@@ -347,18 +405,22 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
 __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long cnt[10];
-    double sums[3] = {0.0, 0.0, 0.0};
-    for (int i = 0; i < 10; ++i) cnt[i] = 0;
     if (e < D.E) {
         int pid = D.path_idx[e];
         PathView P = path_view(D.paths, D.path_stride, pid, D.lens);
-        const double cx = D.rpose[(size_t)e * 4], cy = D.rpose[(size_t)e * 4 + 1], cth = D.rpose[(size_t)e * 4 + 2];
+        double *rp = D.rpose + (size_t)e * 4;
+        double cx = rp[0], cy = rp[1], cth = rp[2];
         bool lts = D.loc_to_start[e] != 0;
         Localization cur;
         if (mode == 0) {
-            const double px = D.rprev[(size_t)e * 4], py = D.rprev[(size_t)e * 4 + 1], pth = D.rprev[(size_t)e * 4 + 2];
+            // ---- robot.step(action): exact-arc unicycle (agent.py:169-176 -> unicycle.py:89-126) ----
+            const double px = cx, py = cy, pth = cth;
             const double av = D.actions[(size_t)e * 2], aw = D.actions[(size_t)e * 2 + 1];
+            unicycle_step(px, py, pth, av, aw, D.dt, cx, cy, cth);
+            D.rprev[(size_t)e * 4] = px; D.rprev[(size_t)e * 4 + 1] = py; D.rprev[(size_t)e * 4 + 2] = pth;
+            rp[0] = cx; rp[1] = cy; rp[2] = cth;
+            D.gtime[e] += D.dt;
+            D.step_count[e] += 1;
             const Localization prv = localize_on_path(P, px, py, lts);
             cur = localize_on_path(P, cx, cy, lts);
             if (cur.index >= (double)(P.L / 3) && cur.index < (double)(2 * P.L / 3)) lts = false;
@@ -406,34 +468,11 @@ __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
             else reward += sc * 0.0;
             if (D.safety_corridor_max_dev < xy_dev) { reward += sc * D.safety_corridor_penalty; bits |= DRE_DONE_SAFETY_CORRIDOR | DRE_DONE_PT; }
             else reward += sc * 0.0;
-            // ---- merge with the HA part (HA_and_PT env.py:322-331, 391-414) ----
-            const double r_ha = D.out.rewards[(size_t)e * 3 + 1];
-            uint32_t all = D.out.done_bits[e] | bits;
-            if (all & (DRE_DONE_HA | DRE_DONE_PT)) all |= DRE_DONE_ANY | DRE_DONE_FOR_REPLAY;
+            // the HA half (ha_step_kernel, launched after the MPC solve) merges rewards / dones (HA_and_PT env.py:322-331)
             D.out.rewards[(size_t)e * 3] = reward;
-            D.out.rewards[(size_t)e * 3 + 2] = reward + r_ha;
-            D.out.done_bits[e] = all;
-            {   // unpacked 0/1 flags so the host mirror can hand out views without launching kernels
-                const uint32_t order[12] = {DRE_DONE_PT, DRE_DONE_HA, DRE_DONE_ANY, DRE_DONE_FOR_REPLAY, DRE_DONE_GOAL, DRE_DONE_COLLISION,
-                                            DRE_DONE_SAFETY_HUMAN, DRE_DONE_TIMEOUT, DRE_DONE_END_OF_PATH, DRE_DONE_CORRIDOR_HIT,
-                                            DRE_DONE_SAFETY_CORRIDOR, DRE_DONE_ACTUATION};
-                uint32_t w0 = 0, w1 = 0, w2 = 0;
-                for (int i = 0; i < 4; ++i) {
-                    w0 |= (uint32_t)((all & order[i]) != 0) << (8 * i);
-                    w1 |= (uint32_t)((all & order[4 + i]) != 0) << (8 * i);
-                    w2 |= (uint32_t)((all & order[8 + i]) != 0) << (8 * i);
-                }
-                uint32_t *df = reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 12);
-                df[0] = w0; df[1] = w1; df[2] = w2;
-            }
+            D.out.done_bits[e] = bits;
             D.out.info[(size_t)e * 8 + 2] = adv; D.out.info[(size_t)e * 8 + 3] = devr;
             D.out.info[(size_t)e * 8 + 5] = cur.index; D.out.info[(size_t)e * 8 + 6] = xy_dev; D.out.info[(size_t)e * 8 + 7] = prv.index;
-            cnt[0] = 1;
-            cnt[1] = (all & DRE_DONE_GOAL) ? 1 : 0; cnt[2] = (all & DRE_DONE_COLLISION) ? 1 : 0;
-            cnt[3] = (all & DRE_DONE_SAFETY_HUMAN) ? 1 : 0; cnt[4] = (all & DRE_DONE_TIMEOUT) ? 1 : 0;
-            cnt[5] = (all & DRE_DONE_END_OF_PATH) ? 1 : 0; cnt[6] = (all & DRE_DONE_CORRIDOR_HIT) ? 1 : 0;
-            cnt[7] = (all & DRE_DONE_SAFETY_CORRIDOR) ? 1 : 0; cnt[8] = (all & DRE_DONE_ACTUATION) ? 1 : 0;
-            sums[0] = reward + r_ha; sums[1] = reward; sums[2] = r_ha;
             // ---- path switch on goal / end of path (what soft_reset does, HA_and_PT env.py:130-141) ----
             if (D.auto_path_switch && (bits & (DRE_DONE_GOAL | DRE_DONE_END_OF_PATH))) {
                 pid = (pid + 1) % D.num_paths;
@@ -449,27 +488,6 @@ __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
         }
         pt_state_gen(P, cx, cy, cth, cur.index, D.lookahead, D.lookbehind, D.out.pt_state + (size_t)e * (4 * (D.lookahead + D.lookbehind)), 1);
         D.mpc_interp[e] = cur.index;
-    }
-    if (mode == 0 && D.stat_counters) {
-        // block reduction of the episode statistics, then one atomic per counter per CTA
-        __shared__ unsigned long long s_cnt[9];
-        __shared__ double s_sum[3];
-        if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0;
-        if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
-        __syncthreads();
-        for (int i = 0; i < 9; ++i) {
-            unsigned long long v = cnt[i];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[i], v);
-        }
-        for (int i = 0; i < 3; ++i) {
-            double v = sums[i];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[i], v);
-        }
-        __syncthreads();
-        if (threadIdx.x < 9 && s_cnt[threadIdx.x]) atomicAdd(D.stat_counters + threadIdx.x, s_cnt[threadIdx.x]);
-        if (threadIdx.x < 3) atomicAdd(D.stat_sums + threadIdx.x, s_sum[threadIdx.x]);
     }
 }
 
@@ -555,15 +573,21 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
+int dre_env_ha_envs_per_cta(const EnvDev &D)
+{
+    const int G = dre_orca_pick_group(D.orca, D.Nh);
+    int EPB = (5 * (256 / G)) / D.Nh;
+    if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
+    return EPB < 1 ? 1 : EPB;
+}
+
 template <int G>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
     // 256 threads = 256/G lane-groups; ~5 agents per group so the dynamic schedule can even out LP2 / LP3 solves
-    const int threads = 256, NGl = threads / G;
-    int EPB = (5 * NGl) / Nh;
-    if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
-    if (EPB < 1) EPB = 1;
+    const int threads = 256;
+    const int EPB = dre_env_ha_envs_per_cta(D);
     const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
     auto kern = ha_step_kernel<G>;
     if (lay.bytes > 48 * 1024) {

@@ -12,6 +12,10 @@ struct EnvOutDev {
 
 struct EnvDev {
     int E, Nh, LB;
+    // pipelined host path: the last CTA of every chunk of `chunk_envs` envs stores `step_seq` to chunk_flags[chunk]
+    // (mapped host memory); chunk_count = per-chunk CTA counters in device memory. nullptr = no signalling.
+    int *chunk_flags, *chunk_count;
+    int chunk_envs, step_seq;
     dre_orca_params orca;
     double dt, time_limit, human_radius, robot_radius, circle_radius, circle_radius_humans;
     int end_goal_changing;
@@ -52,6 +56,7 @@ struct EnvDev {
 };
 
 int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s);
+int dre_env_ha_envs_per_cta(const EnvDev &D);
 int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s);
 int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s);
 int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s);

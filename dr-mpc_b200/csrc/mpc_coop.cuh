@@ -259,6 +259,9 @@ struct CoopBatch {
     double2 *warm_u;      // [N][K]
     uint8_t *iteration0;  // [N]
     int *queue;           // work counter (zeroed before the launch)
+    unsigned long long *trace;   // TRACE builds only: [0..5] cycles in fetch/cost0/build/solve/trials/bookkeeping,
+                                 // [6] loop iterations, [7] sum of the warp's live groups over iterations, [8] max iterations of a group,
+                                 // [9] groups, [10] cycles of the longest-running group (all summed over group leaders)
 };
 
 // PERSISTENT lane-group loop: a group of G lanes pulls problems from a global counter and runs one LM attempt
@@ -266,9 +269,13 @@ struct CoopBatch {
 // groups of a warp advance in lock-step per iteration; letting a finished group fetch the next problem immediately
 // keeps every group busy instead of idling until the slowest problem of its warp is done.
 // Semantics per problem: identical to mpc_act_one (mpc_device.cuh) = reference MPC.act (mpc.py:58-206).
-template <int G>
+template <int G, bool TRACE = false>
 __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params &prm, const CoopBatch &B)
 {
+    unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_t = 0, tr_start = 0;
+    if (TRACE) { tr_t = clock64(); tr_start = tr_t; }
+#define DRE_TR(i) do { if (TRACE) { const long long _n = clock64(); tr[i] += (unsigned long long)(_n - tr_t); tr_t = _n; } } while (0)
     MpcConst C;
     C.K = prm.horizon; C.dt = prm.time_step; C.vmax = prm.v_max; C.wmax = prm.w_max;
     C.inv_vmax = 1.0 / prm.v_max; C.inv_2wmax = 1.0 / (2.0 * prm.w_max); C.pose_jac_exact = prm.pose_jac_exact;
@@ -325,6 +332,8 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             }
         }
         if (!have) break;
+        if (TRACE) { tr[6] += 1; tr[7] += __popc(__activemask()) / G; }
+        DRE_TR(0);
 
         // ---- LM state machine: one damped solve + up to two trials per loop iteration (lev_marq...py:43-134) ----
         if (need_cost0) {
@@ -333,6 +342,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             curr = g.sum_ordered(c, K);
             need_cost0 = false; need_build = true;
         }
+        DRE_TR(1);
         if (need_build) {
             ++iter; prev = curr; nb = 0; need_build = false;
             const Se2 Tp = g.up(Tk1);
@@ -361,6 +371,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             for (int a = 0; a < 5; ++a) bb += R.b[a] * R.b[a];
             gn = sqrt(g.sum_ordered(act ? bb : 0.0, K));
         }
+        DRE_TR(2);
         double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         ++lm_solves;
         bool success = false;
@@ -368,6 +379,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         Se2 Tt = Tk1;
         double ut[2] = {u[0], u[1]};
         const bool solved = coop_solve(g, K, R, lambda, d);
+        DRE_TR(3);
         if (solved) {
             // whole-step feasibility scale, walking u_0..u_{K-1}, v then w (lev_marq...py:52-91)
             // each lane prices its own two components; the walk itself only needs the quotients
@@ -422,6 +434,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 if (ratio > 0.25) { success = true; break; }
             }
         }
+        DRE_TR(4);
         if (success) {
             Tk1 = Tt; u[0] = ut[0]; u[1] = ut[1];
             lambda = fmax(lambda * 0.1, 1e-7);
@@ -485,6 +498,14 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             }
             have = false;
         }
+        DRE_TR(5);
     }
+    if (TRACE && B.trace != nullptr && g.lane == 0) {
+        for (int i = 0; i < 8; ++i) atomicAdd(B.trace + i, tr[i]);
+        atomicMax(B.trace + 8, tr[6]);
+        atomicAdd(B.trace + 9, 1ull);
+        atomicMax(B.trace + 10, (unsigned long long)(clock64() - tr_start));
+    }
+#undef DRE_TR
 }
 #endif  // __CUDACC__

@@ -7,17 +7,26 @@
 // Data layout: warm-start poses/controls are problem-major ([N][K] double4 / double2), so the lanes of a warp
 // (G-lane groups of consecutive problems) read/write one contiguous run; per-problem inputs and outputs likewise.
 #include <cstdlib>
+#include <cstdio>
 #include "mpc_coop.cuh"
 #include "launch.cuh"
 
 // MINB = minimum resident CTAs per SM the register allocation is capped for (2: everything in registers;
 // 3 / 4: fewer registers, more warps to hide the fp64 dependency chains, some spills to L1)
-template <int G, int MINB>
+template <int G, int MINB, bool TRACE = false>
 __global__ void __launch_bounds__(128, MINB)
 mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
     LaneGroup<G> g;
-    mpc_coop_persistent<G>(g, prm, B);
+    mpc_coop_persistent<G, TRACE>(g, prm, B);
+}
+
+// DRE_MPC_TRACE=1: run the instrumented K <= 4 kernel and print where a lane-group's cycles go (stderr; synchronises)
+static bool dre_mpc_trace()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DRE_MPC_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 
 // DRE_MPC_MINB=2|3|4 overrides the occupancy target of the K <= 4 kernel (A/B measurements)
@@ -51,6 +60,23 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
     B.warm_T = reinterpret_cast<double4 *>(st.warm_T); B.warm_u = reinterpret_cast<double2 *>(st.warm_u);
     B.iteration0 = st.iteration0; B.queue = st.queue;
     DRE_CUDA_TRY(cudaMemsetAsync(st.queue, 0, sizeof(int), s));
+    B.trace = nullptr;
+    if (G == 4 && MINB == 2 && dre_mpc_trace()) {
+        static unsigned long long *d_tr = nullptr;
+        if (!d_tr) DRE_CUDA_TRY(cudaMalloc(&d_tr, 16 * sizeof(unsigned long long)));
+        DRE_CUDA_TRY(cudaMemsetAsync(d_tr, 0, 16 * sizeof(unsigned long long), s));
+        B.trace = d_tr;
+        mpc_coop_kernel<4, 2, true><<<blocks, threads, 0, s>>>(p, B);
+        DRE_CUDA_TRY(cudaGetLastError());
+        unsigned long long h[16];
+        DRE_CUDA_TRY(cudaMemcpyAsync(h, d_tr, sizeof h, cudaMemcpyDeviceToHost, s));
+        DRE_CUDA_TRY(cudaStreamSynchronize(s));
+        const double it = (double)(h[6] ? h[6] : 1), gr = (double)(h[9] ? h[9] : 1);
+        fprintf(stderr, "[mpc trace] groups %llu iters/group %.1f (max %llu) live groups/warp %.2f | cycles per iteration: fetch %.0f cost0 %.0f "
+                        "build %.0f solve %.0f trials %.0f book %.0f | longest group %.0f us at 1.965 GHz\n",
+                h[9], it / gr, h[8], (double)h[7] / it, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it, h[10] / 1965.0);
+        return DRE_OK;
+    }
     mpc_coop_kernel<G, MINB><<<blocks, threads, 0, s>>>(p, B);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;

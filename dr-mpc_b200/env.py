@@ -170,6 +170,10 @@ class BatchedHAAndPTEnv:
                                              ctypes.c_void_p(self._host_slab.data_ptr())))
         return self._host_views
 
+    def set_host_chunks(self, chunks):
+        """Number of env chunks step_host pipelines the crowd half and its D2H copies in (1 = no pipelining)."""
+        _lib.check(self._L.dre_env_set_host_chunks(self._h, int(chunks)))
+
     def stats(self, reset=False):
         """Episode statistics accumulated on device -> (int64[16], float64[4]) CUDA tensors (feed to all_reduce)."""
         import torch

@@ -207,6 +207,8 @@ int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init,
 int dre_env_step(dre_env *h, const double *actions, void *stream);
 /* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab) */
 int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
+/* number of env chunks whose observation copies dre_env_step_host overlaps with the crowd half (1..32, default 8) */
+int dre_env_set_host_chunks(dre_env *h, int32_t chunks);
 /* regenerate observations only (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148) */
 int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
 /* episode statistics accumulated on device since the last call: int64[16]

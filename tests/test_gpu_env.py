@@ -154,3 +154,26 @@ def test_free_running_full_size_invariants():
         assert (((bits & 0xFF) != 0) == ((bits & (1 << 18)) != 0)).all()
         runs.append((env.state["hpos"].clone(), env.out["rewards"].clone(), c.copy()))
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_step_host_pipeline_equals_device_step(chunks):
+    """The host-buffer entry point (chunk-pipelined crowd half + overlapped D2H) returns exactly the device step's
+    slab, for ragged chunkings (E not a multiple of the chunk count or of the CTA's env tile)."""
+    import torch
+    import dr_mpc_b200 as d
+    E, Nh = 1000 + 37, 10
+    a_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E)
+    b_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E)
+    b_env.set_host_chunks(chunks)
+    Sa = a_env.reset(); b_env.reset()
+    act = Sa['PT']['MPC_actions'][:, :2].clone()
+    for t in range(6):
+        a_env.step(act)
+        views = b_env.step_host(act.cpu().numpy())
+        torch.cuda.synchronize()
+        for name, dev_t in a_env.out.items():
+            assert np.array_equal(dev_t.cpu().numpy().view(np.uint8), np.asarray(views[name]).view(np.uint8)), (t, name)
+        for name in ("hpos", "hvel", "hgoal", "rpose", "hhist"):
+            assert torch.equal(a_env.state[name], b_env.state[name]), (t, name)
+        act = a_env.out["mpc_actions"][:, :2].clone()

@@ -2,11 +2,19 @@
 //
 // A group of G lanes (G = 4, 8, 16 or 32 >= K) owns one problem; lane k owns horizon step k: pose T_{k+1}, control
 // u_k, reference M_k and block row k of the block-tridiagonal normal equations (diagonal block D_k packed 5x5,
-// coupling block O_k 5x3, rhs b_k), all in REGISTERS -- nothing lives in local memory, which is what bounds the
-// one-thread-per-problem formulation (its 3.5 KB/thread working set falls out of L1). Residuals, Jacobians and
-// trial costs are embarrassingly parallel over lanes (the neighbour pose comes by shuffle); the block Cholesky
-// runs as K pipeline stages in which lane j consumes lane j-1's factor rows (9 doubles by shuffle); sums over
-// the horizon are taken in step order so they round like the sequential reference.
+// coupling block O_k 5x3, rhs b_k). Residuals, Jacobians and trial costs are embarrassingly parallel over lanes (the
+// neighbour pose comes by shuffle); the block Cholesky runs as K pipeline stages in which lane j consumes lane j-1's
+// factor rows (9 doubles by shuffle); sums over the horizon are taken in step order so they round like the
+// sequential reference.
+//
+// The kernel is bound by the LATENCY of fp64 dependency chains (measured: ~6.7 cycles per warp instruction with 2 warps
+// per scheduler), so everything here is about (a) more resident warps and (b) fewer instructions on the chain:
+//   * the linearisation (D, O, b: 35 doubles per lane, read-only between rebuilds) and the retry guess live in a
+//     conflict-free shared-memory column per thread instead of registers -> 168 registers, 3 CTAs (12 warps) per SM;
+//   * every pose carries its heading, updated additively by the LM step, so the two log maps per cost / build take their
+//     angle from a subtraction + wrap instead of atan2;
+//   * sin/cos of the small angles (dt*w and the LM step) use a branch-free Taylor kernel;
+//   * the factor stores inverse pivots (one rsqrt per pivot, no divisions on the chain).
 //
 // Control flow is a per-group state machine with the phases in a fixed order (initial cost -> build -> damped solve ->
 // trial 1 -> trial 2 -> bookkeeping), so the groups of a warp, which follow different LM paths, re-converge at every
@@ -15,6 +23,8 @@
 #include "mpc_device.cuh"
 
 #if defined(__CUDACC__)
+
+#define DRE_MPC_CTA 128   // threads per CTA of the cooperative kernel (shared-memory columns are strided by this)
 
 template <int G>
 struct LaneGroup {
@@ -47,27 +57,87 @@ struct LaneGroup {
             return v;
         }
     }
-    __device__ Se2 up(const Se2 &T) const
-    {
-        Se2 r;
-        r.c = up(T.c); r.s = up(T.s); r.x = up(T.x); r.y = up(T.y);
-        return r;
-    }
 };
 
+// pose with its heading: th == atan2(s, c) modulo 2 pi, tracked additively
+struct Se2h { Se2 T; double th; };
+
+template <int G>
+__device__ __forceinline__ Se2h lane_up(const LaneGroup<G> &g, const Se2h &a)
+{
+    Se2h r;
+    r.T.c = g.up(a.T.c); r.T.s = g.up(a.T.s); r.T.x = g.up(a.T.x); r.T.y = g.up(a.T.y); r.th = g.up(a.th);
+    return r;
+}
+
+// angle of a rotation known modulo 2 pi -> [-pi, pi] like atan2
+__device__ __forceinline__ double wrap_angle(double a)
+{
+    return a - (2.0 * DRE_PI) * rint(a * (1.0 / (2.0 * DRE_PI)));
+}
+
+// sin and cos for |x| <= 0.5 by Taylor series (truncation < 5e-17 relative); larger arguments fall back
+__device__ __forceinline__ void sincos_small(double x, double *sn, double *cs)
+{
+    if (fabs(x) > 0.5) { sincos(x, sn, cs); return; }
+    const double z = x * x;
+    double ps = -1.0 / 1307674368000.0;                 // -1/15!
+    ps = fma(ps, z, 1.0 / 6227020800.0);                // +1/13!
+    ps = fma(ps, z, -1.0 / 39916800.0);                 // -1/11!
+    ps = fma(ps, z, 1.0 / 362880.0);                    // +1/9!
+    ps = fma(ps, z, -1.0 / 5040.0);                     // -1/7!
+    ps = fma(ps, z, 1.0 / 120.0);                       // +1/5!
+    ps = fma(ps, z, -1.0 / 6.0);                        // -1/3!
+    *sn = fma(x * z, ps, x);
+    double pc = 1.0 / 20922789888000.0;                 // +1/16!
+    pc = fma(pc, z, -1.0 / 87178291200.0);              // -1/14!
+    pc = fma(pc, z, 1.0 / 479001600.0);                 // +1/12!
+    pc = fma(pc, z, -1.0 / 3628800.0);                  // -1/10!
+    pc = fma(pc, z, 1.0 / 40320.0);                     // +1/8!
+    pc = fma(pc, z, -1.0 / 720.0);                      // -1/6!
+    pc = fma(pc, z, 1.0 / 24.0);                        // +1/4!
+    *cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+
+// log map of T whose rotation angle p (wrapped) is already known
+__device__ __forceinline__ void se2_log_known(const Se2 &T, double p, double e[3], double &ct)
+{
+    ct = half_cot(p, T.s, T.c);
+    const double h = 0.5 * p;
+    e[0] = ct * T.x + h * T.y;
+    e[1] = ct * T.y - h * T.x;
+    e[2] = p;
+}
+
+// exp(rx, ry, p) * T with the heading carried along (the LM update T <- exp(delta^) T)
+__device__ __forceinline__ Se2h se2h_step(double rx, double ry, double p, const Se2h &T)
+{
+    double sn, cs;
+    sincos_small(p, &sn, &cs);
+    const PhiCoef q = phi_coef(p, sn, cs);
+    Se2 E;
+    E.c = cs; E.s = sn;
+    E.x = q.A * rx - q.B * ry;
+    E.y = q.B * rx + q.A * ry;
+    Se2h r;
+    r.T = se2_mul(E, T.T);
+    r.th = T.th + p;
+    return r;
+}
+
 // per-lane cost of step k: pose + kinematic + 4 barriers (mpc.py:99-142)
-__device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2 &Tprev, const Se2 &Tk1, const double u[2],
-                                                 const Se2 &Mk, double inv_s)
+__device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2h &Tprev, const Se2h &Tk1, const double u[2],
+                                                 const Se2h &Mk, double inv_s)
 {
     double e[3], ct;
-    se2_log(se2_mul_inv(Mk, Tk1), e, ct);
+    se2_log_known(se2_mul_inv(Mk.T, Tk1.T), wrap_angle(Mk.th - Tk1.th), e, ct);
     double cost = 0.5 * inv_s * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
     const double p = C.dt * u[1];
     double sn, cs;
-    sincos(p, &sn, &cs);
+    sincos_small(p, &sn, &cs);
     const PhiCoef q = phi_coef(p, sn, cs);
-    const Se2 E = se2_mul(se2_mul_inv(Tk1, Tprev), se2_exp_x(C.dt * u[0], p, sn, cs, q));
-    se2_log(E, e, ct);
+    const Se2 E = se2_mul(se2_mul_inv(Tk1.T, Tprev.T), se2_exp_x(C.dt * u[0], p, sn, cs, q));
+    se2_log_known(E, wrap_angle(Tk1.th - Tprev.th + p), e, ct);
     cost += 0.5 * 1000.0 * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
     const double b0 = barrier_val((C.vmax - u[0]) * C.inv_vmax), b1 = barrier_val(u[0] * C.inv_vmax);
     const double b2 = barrier_val((C.wmax - u[1]) * C.inv_2wmax), b3 = barrier_val((u[1] + C.wmax) * C.inv_2wmax);
@@ -75,45 +145,53 @@ __device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2 &T
     return cost;
 }
 
-struct CoopRow {
-    double D[15];   // packed lower 5x5 diagonal block of z_k = (u_k, delta_{k+1})
-    double O[15];   // 5x3 coupling with delta_k (previous lane)
-    double b[5];
-    double L[15];   // Cholesky factor of the Schur complement
+// this thread's shared-memory column: slot i lives at col[i * DRE_MPC_CTA] (consecutive threads -> consecutive banks)
+struct CoopCol {
+    double *col;
+    __device__ double &operator[](int i) const { return col[i * DRE_MPC_CTA]; }
+};
+enum { CS_D = 0, CS_O = 15, CS_B = 30, CS_TI = 35, CS_UI = 40, CS_SLOTS = 42 };   // D 15, O 15, b 5, Tinit (c,s,x,y,th), uinit 2
+
+struct CoopFactor {
+    double L[15];   // Cholesky factor of the Schur complement, diagonal slots hold the INVERSE pivots
     double B[15];   // O L_{prev}^{-T}
 };
 
-// Build block row k. `first` = lane 0 (T_k is the locked current pose: no coupling / no contribution to a previous block).
-// pc6 / pcb: this step's kinematic contribution to the PREVIOUS block's delta-delta part (sent down by the caller).
-__device__ __forceinline__ void coop_lane_build(const MpcConst &C, const Se2 &Tprev, const Se2 &Tk1, const double u[2],
-                                                const Se2 &Mk, double s, bool first, CoopRow &R, double pc6[6], double pcb[3])
+// Build block row k into the shared-memory column (lane 0's T_k is the locked current pose: no coupling and no
+// contribution to a previous block). Returns this lane's |b_k|^2.
+template <int G>
+__device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const MpcConst &C, const Se2h &Tprev, const Se2h &Tk1,
+                                                  const double u[2], const Se2h &Mk, double s, bool act, const CoopCol &M)
 {
+    const int k = g.lane;
+    const bool first = k == 0;
+    double D[15], O[15], b[5], pc6[6], pcb[3];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) { R.D[i] = 0.0; R.O[i] = 0.0; }
+    for (int i = 0; i < 15; ++i) { D[i] = 0.0; O[i] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) R.b[i] = 0.0;
+    for (int i = 0; i < 5; ++i) b[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) pc6[i] = 0.0;
     pcb[0] = pcb[1] = pcb[2] = 0.0;
     {   // pose term
         double e[3], ct;
-        const Se2 E = se2_mul_inv(Mk, Tk1);
-        se2_log(E, e, ct);
+        const Se2 E = se2_mul_inv(Mk.T, Tk1.T);
+        se2_log_known(E, wrap_angle(Mk.th - Tk1.th), e, ct);
         Aff Gm = se2_Jlinv(e, E.s, E.c, ct);
         if (C.pose_jac_exact) Gm = aff_mul(Gm, se2_Ad(E));
         const double r0[3] = {-Gm.m[0], -Gm.m[1], -Gm.m[2]}, r1[3] = {-Gm.m[3], -Gm.m[4], -Gm.m[5]}, r2[3] = {0.0, 0.0, -1.0};
-        acc_block<3>(R.D, R.b, 2, r0, r1, r2, e, 3.0 / s);
+        acc_block<3>(D, b, 2, r0, r1, r2, e, 3.0 / s);
     }
     {   // kinematic term
         const double p = C.dt * u[1];
         double sn, cs;
-        sincos(p, &sn, &cs);
+        sincos_small(p, &sn, &cs);
         const PhiCoef q = phi_coef(p, sn, cs);
         const double rx = C.dt * u[0];
-        const Se2 Lh = se2_mul_inv(Tk1, Tprev);
+        const Se2 Lh = se2_mul_inv(Tk1.T, Tprev.T);
         const Se2 E = se2_mul(Lh, se2_exp_x(rx, p, sn, cs, q));
         double e[3], ct;
-        se2_log(E, e, ct);
+        se2_log_known(E, wrap_angle(Tk1.th - Tprev.th + p), e, ct);
         const Aff Gm = se2_Jlinv(e, E.s, E.c, ct);
         Aff Jl;
         Jl.m[0] = q.A; Jl.m[1] = q.B;  Jl.m[2] = q.alpha * rx;
@@ -122,7 +200,7 @@ __device__ __forceinline__ void coop_lane_build(const MpcConst &C, const Se2 &Tp
         const double r0[5] = {C.dt * Ju.m[0], C.dt * Ju.m[2], Gm.m[0], Gm.m[1], Gm.m[2]};
         const double r1[5] = {C.dt * Ju.m[3], C.dt * Ju.m[5], Gm.m[3], Gm.m[4], Gm.m[5]};
         const double r2[5] = {0.0, C.dt, 0.0, 0.0, 1.0};
-        acc_block<5>(R.D, R.b, 0, r0, r1, r2, e, 1000.0);
+        acc_block<5>(D, b, 0, r0, r1, r2, e, 1000.0);
         if (!first) {
             const Aff GL = aff_mul(Gm, se2_Ad(Lh));
             const double q0[3] = {-GL.m[0], -GL.m[1], -GL.m[2]}, q1[3] = {-GL.m[3], -GL.m[4], -GL.m[5]}, q2[3] = {0.0, 0.0, -1.0};
@@ -135,7 +213,7 @@ __device__ __forceinline__ void coop_lane_build(const MpcConst &C, const Se2 &Tp
 #pragma unroll
             for (int a = 0; a < 5; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) R.O[3 * a + c] = 1000.0 * (r0[a] * q0[c] + r1[a] * q1[c] + r2[a] * q2[c]);
+                for (int c = 0; c < 3; ++c) O[3 * a + c] = 1000.0 * (r0[a] * q0[c] + r1[a] * q1[c] + r2[a] * q2[c]);
         }
     }
     {   // barriers
@@ -147,18 +225,42 @@ __device__ __forceinline__ void coop_lane_build(const MpcConst &C, const Se2 &Tp
         const double e2 = barrier_val(x2) * k500, e3 = barrier_val(x3) * k500;
         const double j0 = -k500 * barrier_grad(x0) * C.inv_vmax, j1 = k500 * barrier_grad(x1) * C.inv_vmax;
         const double j2 = -k500 * barrier_grad(x2) * C.inv_2wmax, j3 = k500 * barrier_grad(x3) * C.inv_2wmax;
-        R.b[0] -= 0.1 * (j0 * e0 + j1 * e1);
-        R.b[1] -= 0.1 * (j2 * e2 + j3 * e3);
-        R.D[0] += 0.1 * (j0 * j0 + j1 * j1);
-        R.D[2] += 0.1 * (j2 * j2 + j3 * j3);
+        b[0] -= 0.1 * (j0 * e0 + j1 * e1);
+        b[1] -= 0.1 * (j2 * e2 + j3 * e3);
+        D[0] += 0.1 * (j0 * j0 + j1 * j1);
+        D[2] += 0.1 * (j2 * j2 + j3 * j3);
     }
+    // this step's kinematic term also lands on the previous block's delta-delta part: receive from lane k+1
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double rb = g.down(pcb[a]);
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+            const double rv = g.down(pc6[a * (a + 1) / 2 + c]);
+            if (k + 1 < C.K) D[(2 + a) * (3 + a) / 2 + 2 + c] += rv;
+        }
+        if (k + 1 < C.K) b[2 + a] += rb;
+    }
+    if (!act) {   // padding lanes: identity block, zero rhs
+#pragma unroll
+        for (int i = 0; i < 15; ++i) { D[i] = 0.0; O[i] = 0.0; }
+        D[0] = D[2] = D[5] = D[9] = D[14] = 1.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) b[i] = 0.0;
+    }
+    double bb = 0.0;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) { M[CS_D + i] = D[i]; M[CS_O + i] = O[i]; }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { M[CS_B + a] = b[a]; bb += b[a] * b[a]; }
+    return bb;
 }
 
 // Damped block-tridiagonal Cholesky as a K-stage lane pipeline. Returns false (group-uniform) on a non-positive pivot.
 // The diagonal slots of R.L hold the INVERSE pivots 1/l_cc (computed with one rsqrt per pivot): every later use of a
 // pivot is a division, so the dependent chain of a stage is multiplications only.
 template <int G>
-__device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow &R, double lambda, double d[5])
+__device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, const CoopCol &M, CoopFactor &R, double lambda, double d[5])
 {
     const double damp = 1.0 + lambda;
     double y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -174,16 +276,16 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, CoopRow
         if (g.lane == j) {
             double S[15], rhs[5];
 #pragma unroll
-            for (int i = 0; i < 15; ++i) S[i] = R.D[i];
+            for (int i = 0; i < 15; ++i) S[i] = M[CS_D + i];
             S[0] *= damp; S[2] *= damp; S[5] *= damp; S[9] *= damp; S[14] *= damp;
 #pragma unroll
-            for (int a = 0; a < 5; ++a) rhs[a] = R.b[a];
+            for (int a = 0; a < 5; ++a) rhs[a] = M[CS_B + a];
             if (j > 0) {
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
-                    const double b2 = R.O[3 * a] * i22;
-                    const double b3 = (R.O[3 * a + 1] - b2 * l32) * i33;
-                    const double b4 = (R.O[3 * a + 2] - b2 * l42 - b3 * l43) * i44;
+                    const double b2 = M[CS_O + 3 * a] * i22;
+                    const double b3 = (M[CS_O + 3 * a + 1] - b2 * l32) * i33;
+                    const double b4 = (M[CS_O + 3 * a + 2] - b2 * l42 - b3 * l43) * i44;
                     R.B[3 * a] = b2; R.B[3 * a + 1] = b3; R.B[3 * a + 2] = b4;
                 }
 #pragma unroll
@@ -265,12 +367,13 @@ struct CoopBatch {
 };
 
 // PERSISTENT lane-group loop: a group of G lanes pulls problems from a global counter and runs one LM attempt
-// (damped solve + up to two trials) per loop iteration. LM paths differ per problem (3 to 60 attempts), and the 32/G
+// (damped solve + up to two trials) per loop iteration. LM paths differ per problem (3 to >100 attempts), and the 32/G
 // groups of a warp advance in lock-step per iteration; letting a finished group fetch the next problem immediately
 // keeps every group busy instead of idling until the slowest problem of its warp is done.
 // Semantics per problem: identical to mpc_act_one (mpc_device.cuh) = reference MPC.act (mpc.py:58-206).
+// smem: CS_SLOTS * DRE_MPC_CTA doubles.
 template <int G, bool TRACE = false>
-__device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params &prm, const CoopBatch &B)
+__device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params &prm, const CoopBatch &B, double *smem)
 {
     unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tr_t = 0, tr_start = 0;
@@ -282,18 +385,20 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
     const int K = C.K, k = g.lane;
     const bool act = k < K;
     const double inc = (prm.v_max * 0.99) * prm.time_step / prm.node_separation;
+    CoopCol M;
+    M.col = smem + threadIdx.x;
 
     // ---- per-problem state (registers) ----
     int n = -1;
     bool have = false, exhausted = false;
-    Se2 T0, Mk, Tinit, Tk1;
-    double uinit[2] = {0.0, 0.0}, u[2] = {0.0, 0.0};
-    CoopRow R;
+    Se2h T0, Mk, Tk1;
+    double u[2] = {0.0, 0.0};
+    CoopFactor R;
     double s = 1.0, lambda = 1e-7, curr = 0.0, prev = 0.0, gn = 0.0;
     int iter = 0, nb = 0, retries = 0, term = 0, lm_solves = 0, cost_evals = 0, zero_steps = 0;
     bool need_cost0 = true, need_build = false;
-    T0.c = 1.0; T0.s = 0.0; T0.x = 0.0; T0.y = 0.0;
-    Mk = T0; Tinit = T0; Tk1 = T0;
+    T0.T.c = 1.0; T0.T.s = 0.0; T0.T.x = 0.0; T0.T.y = 0.0; T0.th = 0.0;
+    Mk = T0; Tk1 = T0;
 
     for (;;) {
         // ---- fetch + initialise the next problem ----
@@ -311,21 +416,26 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 const double *path = B.paths + (size_t)pid * 3 * B.path_stride;
                 const int L = B.lens[pid];
                 const double *ps = B.pose + (size_t)n * B.pose_stride;
-                T0 = se2_from_pose_inv(ps[0], ps[1], ps[2]);
+                T0.T = se2_from_pose_inv(ps[0], ps[1], ps[2]);
+                T0.th = -ps[2];
                 double target = B.interp_index[n] + inc;
                 for (int i = 0; i < k && i < K; ++i) target += inc;      // accumulate like the reference loop (mpc.py:214,224)
                 double r[3];
                 mpc_ref_pose(path, B.path_stride, L, target, r);
-                Mk = se2_from_pose_inv(r[0], r[1], r[2]);
+                Mk.T = se2_from_pose_inv(r[0], r[1], r[2]);
+                Mk.th = -r[2];
                 const bool first_call = (B.iteration0[n] != 0);
-                if (first_call || !act) { Tinit = Mk; uinit[0] = prm.v_max / 2.0; uinit[1] = 0.0; }   // mpc.py:68-71
+                if (first_call || !act) { Tk1 = Mk; u[0] = prm.v_max / 2.0; u[1] = 0.0; }   // mpc.py:68-71
                 else {
                     const double4 w = B.warm_T[(size_t)n * K + k];
                     const double2 uu = B.warm_u[(size_t)n * K + k];
-                    Tinit.c = w.x; Tinit.s = w.y; Tinit.x = w.z; Tinit.y = w.w;
-                    uinit[0] = uu.x; uinit[1] = uu.y;
+                    Tk1.T.c = w.x; Tk1.T.s = w.y; Tk1.T.x = w.z; Tk1.T.y = w.w;
+                    Tk1.th = atan2(w.y, w.x);
+                    u[0] = uu.x; u[1] = uu.y;
                 }
-                Tk1 = Tinit; u[0] = uinit[0]; u[1] = uinit[1];
+                // the initial guess is needed again only by the pose_error_scaling retry (mpc.py:188-190)
+                M[CS_TI] = Tk1.T.c; M[CS_TI + 1] = Tk1.T.s; M[CS_TI + 2] = Tk1.T.x; M[CS_TI + 3] = Tk1.T.y; M[CS_TI + 4] = Tk1.th;
+                M[CS_UI] = u[0]; M[CS_UI + 1] = u[1];
                 s = 1.0; lambda = 1e-7; curr = 0.0; prev = 0.0; gn = 0.0;
                 iter = 0; nb = 0; retries = 0; term = 0; lm_solves = 0; cost_evals = 0; zero_steps = 0;
                 need_cost0 = true; need_build = false;
@@ -337,7 +447,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
 
         // ---- LM state machine: one damped solve + up to two trials per loop iteration (lev_marq...py:43-134) ----
         if (need_cost0) {
-            const Se2 Tp = g.up(Tk1);
+            const Se2h Tp = lane_up(g, Tk1);
             const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tk1, u, Mk, 1.0 / s) : 0.0;
             curr = g.sum_ordered(c, K);
             need_cost0 = false; need_build = true;
@@ -345,30 +455,8 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         DRE_TR(1);
         if (need_build) {
             ++iter; prev = curr; nb = 0; need_build = false;
-            const Se2 Tp = g.up(Tk1);
-            double pc6[6], pcb[3];
-            coop_lane_build(C, k == 0 ? T0 : Tp, Tk1, u, Mk, s, k == 0, R, pc6, pcb);
-            // this step's kinematic term also lands on the previous block's delta-delta part: receive from lane k+1
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double rb = g.down(pcb[a]);
-#pragma unroll
-                for (int c = 0; c <= a; ++c) {
-                    const double rv = g.down(pc6[a * (a + 1) / 2 + c]);
-                    if (k + 1 < K) R.D[(2 + a) * (3 + a) / 2 + 2 + c] += rv;
-                }
-                if (k + 1 < K) R.b[2 + a] += rb;
-            }
-            if (!act) {   // padding lanes: identity block, zero rhs
-#pragma unroll
-                for (int i = 0; i < 15; ++i) { R.D[i] = 0.0; R.O[i] = 0.0; }
-                R.D[0] = R.D[2] = R.D[5] = R.D[9] = R.D[14] = 1.0;
-#pragma unroll
-                for (int i = 0; i < 5; ++i) R.b[i] = 0.0;
-            }
-            double bb = 0.0;
-#pragma unroll
-            for (int a = 0; a < 5; ++a) bb += R.b[a] * R.b[a];
+            const Se2h Tp = lane_up(g, Tk1);
+            const double bb = coop_lane_build(g, C, k == 0 ? T0 : Tp, Tk1, u, Mk, s, act, M);
             gn = sqrt(g.sum_ordered(act ? bb : 0.0, K));
         }
         DRE_TR(2);
@@ -376,9 +464,9 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         ++lm_solves;
         bool success = false;
         double proposed = 0.0;
-        Se2 Tt = Tk1;
+        Se2h Tt = Tk1;
         double ut[2] = {u[0], u[1]};
-        const bool solved = coop_solve(g, K, R, lambda, d);
+        const bool solved = coop_solve(g, K, M, R, lambda, d);
         DRE_TR(3);
         if (solved) {
             // whole-step feasibility scale, walking u_0..u_{K-1}, v then w (lev_marq...py:52-91)
@@ -412,8 +500,8 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                     for (int a = 0; a < 5; ++a) d[a] *= 0.8;
                 }
                 ut[0] = u[0] + d[0]; ut[1] = u[1] + d[1];
-                Tt = se2_mul(se2_exp(d[2], d[3], d[4]), Tk1);
-                const Se2 Tp = g.up(Tt);
+                Tt = se2h_step(d[2], d[3], d[4], Tk1);
+                const Se2h Tp = lane_up(g, Tt);
                 const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tt, ut, Mk, 1.0 / s) : 0.0;
                 proposed = g.sum_ordered(c, K);
                 ++cost_evals;
@@ -422,11 +510,11 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 double gg = 0.0, qq = 0.0;
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
-                    gg += R.b[a] * d[a];
+                    gg += M[CS_B + a] * d[a];
                     double r = 0.0;
 #pragma unroll
-                    for (int c2 = 0; c2 < 5; ++c2) r += R.D[a >= c2 ? a * (a + 1) / 2 + c2 : c2 * (c2 + 1) / 2 + a] * d[c2];
-                    if (k > 0) r += 2.0 * (R.O[3 * a] * p2 + R.O[3 * a + 1] * p3 + R.O[3 * a + 2] * p4);
+                    for (int c2 = 0; c2 < 5; ++c2) r += M[CS_D + (a >= c2 ? a * (a + 1) / 2 + c2 : c2 * (c2 + 1) / 2 + a)] * d[c2];
+                    if (k > 0) r += 2.0 * (M[CS_O + 3 * a] * p2 + M[CS_O + 3 * a + 1] * p3 + M[CS_O + 3 * a + 2] * p4);
                     qq += d[a] * r;
                 }
                 const double pred = g.sum_ordered(act ? gg : 0.0, K) - 0.5 * g.sum_ordered(act ? qq : 0.0, K);
@@ -459,7 +547,8 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 if (retries >= prm.max_retries) term = -1;
                 else {   // mpc.py:188-190: pose_error_scaling *= 5 and start over from the stored initial guess
                     s *= 5.0; ++retries;
-                    Tk1 = Tinit; u[0] = uinit[0]; u[1] = uinit[1];
+                    Tk1.T.c = M[CS_TI]; Tk1.T.s = M[CS_TI + 1]; Tk1.T.x = M[CS_TI + 2]; Tk1.T.y = M[CS_TI + 3]; Tk1.th = M[CS_TI + 4];
+                    u[0] = M[CS_UI]; u[1] = M[CS_UI + 1];
                     lambda = 1e-7; iter = 0; need_cost0 = true;
                 }
             }
@@ -472,16 +561,16 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
 
         // ---- problem finished: outputs + warm start (mpc.py:147,192-205) ----
         if (term != 0) {
-            const Se2 Tprev_final = g.up(Tk1);
+            const Se2h Tprev_final = lane_up(g, Tk1);
             if (act) {
                 double *ctl = B.controls + (size_t)n * B.controls_stride;
                 if (2 * k < B.controls_count) ctl[2 * k] = u[0];
                 if (2 * k + 1 < B.controls_count) ctl[2 * k + 1] = u[1];
                 double4 *wT = B.warm_T + (size_t)n * K;
                 double2 *wu = B.warm_u + (size_t)n * K;
-                if (k + 1 < K) wT[k] = make_double4(Tk1.c, Tk1.s, Tk1.x, Tk1.y);                 // T_{k+1} -> slot k
+                if (k + 1 < K) wT[k] = make_double4(Tk1.T.c, Tk1.T.s, Tk1.T.x, Tk1.T.y);           // T_{k+1} -> slot k
                 else {
-                    const Se2 TL = (K >= 2) ? Tprev_final : T0;                                   // duplicate T_{K-1}
+                    const Se2 TL = (K >= 2) ? Tprev_final.T : T0.T;                                 // duplicate T_{K-1}
                     wT[k] = make_double4(TL.c, TL.s, TL.x, TL.y);
                 }
                 if (k >= 1) wu[k - 1] = make_double2(u[0], u[1]);

@@ -11,14 +11,15 @@
 #include "mpc_coop.cuh"
 #include "launch.cuh"
 
-// MINB = minimum resident CTAs per SM the register allocation is capped for (2: everything in registers;
-// 3 / 4: fewer registers, more warps to hide the fp64 dependency chains, some spills to L1)
+// MINB = minimum resident CTAs per SM the register allocation is capped for. The linearisation lives in shared memory
+// (mpc_coop.cuh), which lets 3 CTAs = 12 warps per SM hide the fp64 dependency chains without spills.
 template <int G, int MINB, bool TRACE = false>
 __global__ void __launch_bounds__(128, MINB)
 mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
+    extern __shared__ __align__(16) double coop_smem[];   // CS_SLOTS columns of DRE_MPC_CTA doubles
     LaneGroup<G> g;
-    mpc_coop_persistent<G, TRACE>(g, prm, B);
+    mpc_coop_persistent<G, TRACE>(g, prm, B, coop_smem);
 }
 
 // DRE_MPC_TRACE=1: run the instrumented K <= 4 kernel and print where a lane-group's cycles go (stderr; synchronises)
@@ -42,13 +43,14 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
                            const double *pose, int pose_stride, double *controls, int controls_stride, int controls_count,
                            dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
 {
-    const int threads = 128, per_block = threads / G;
+    const int threads = DRE_MPC_CTA, per_block = threads / G;
+    const size_t smem = (size_t)CS_SLOTS * DRE_MPC_CTA * sizeof(double);
     static int resident_blocks = 0;           // persistent grid: as many CTAs as fit on the device at once
     if (resident_blocks == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         DRE_CUDA_TRY(cudaGetDevice(&dev));
         DRE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, 0));
+        DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, smem));
         resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
     int blocks = (st.N + per_block - 1) / per_block;
@@ -61,12 +63,12 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
     B.iteration0 = st.iteration0; B.queue = st.queue;
     DRE_CUDA_TRY(cudaMemsetAsync(st.queue, 0, sizeof(int), s));
     B.trace = nullptr;
-    if (G == 4 && MINB == 2 && dre_mpc_trace()) {
+    if (G == 4 && MINB == 3 && dre_mpc_trace()) {
         static unsigned long long *d_tr = nullptr;
         if (!d_tr) DRE_CUDA_TRY(cudaMalloc(&d_tr, 16 * sizeof(unsigned long long)));
         DRE_CUDA_TRY(cudaMemsetAsync(d_tr, 0, 16 * sizeof(unsigned long long), s));
         B.trace = d_tr;
-        mpc_coop_kernel<4, 2, true><<<blocks, threads, 0, s>>>(p, B);
+        mpc_coop_kernel<4, 3, true><<<blocks, threads, smem, s>>>(p, B);
         DRE_CUDA_TRY(cudaGetLastError());
         unsigned long long h[16];
         DRE_CUDA_TRY(cudaMemcpyAsync(h, d_tr, sizeof h, cudaMemcpyDeviceToHost, s));
@@ -77,7 +79,7 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
                 h[9], it / gr, h[8], (double)h[7] / it, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it, h[10] / 1965.0);
         return DRE_OK;
     }
-    mpc_coop_kernel<G, MINB><<<blocks, threads, 0, s>>>(p, B);
+    mpc_coop_kernel<G, MINB><<<blocks, threads, smem, s>>>(p, B);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }
@@ -141,14 +143,14 @@ int dre_mpc_launch(const dre_mpc_params &p, const MpcDeviceState &st, const int3
     if (!dre_mpc_force_serial()) {
         if (K <= 4) {
             switch (dre_mpc_minb()) {
-            case 3: return launch_mpc_coop<4, 3>(DRE_MPC_ARGS);
+            case 2: return launch_mpc_coop<4, 2>(DRE_MPC_ARGS);
             case 4: return launch_mpc_coop<4, 4>(DRE_MPC_ARGS);
-            default: return launch_mpc_coop<4, 2>(DRE_MPC_ARGS);
+            default: return launch_mpc_coop<4, 3>(DRE_MPC_ARGS);
             }
         }
-        if (K <= 8) return launch_mpc_coop<8, 2>(DRE_MPC_ARGS);
-        if (K <= 16) return launch_mpc_coop<16, 2>(DRE_MPC_ARGS);
-        if (K <= 32) return launch_mpc_coop<32, 2>(DRE_MPC_ARGS);
+        if (K <= 8) return launch_mpc_coop<8, 3>(DRE_MPC_ARGS);
+        if (K <= 16) return launch_mpc_coop<16, 3>(DRE_MPC_ARGS);
+        if (K <= 32) return launch_mpc_coop<32, 3>(DRE_MPC_ARGS);
     }
     if (K <= 4) return launch_mpc<4>(DRE_MPC_ARGS);
     if (K <= 10) return launch_mpc<10>(DRE_MPC_ARGS);

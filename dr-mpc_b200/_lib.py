@@ -47,16 +47,16 @@ class EnvConfig(ctypes.Structure):
                 ("corridor_penalty", c_d), ("corridor_max_dev", c_d), ("end_of_path_penalty", c_d),
                 ("safety_corridor_penalty", c_d), ("safety_corridor_max_dev", c_d),
                 ("lookahead", c_i32), ("lookbehind", c_i32), ("mpc_actions_in_input", c_i32), ("auto_path_switch", c_i32),
-                ("seed", c_u64), ("env_id_offset", c_i64)]
+                ("soft_reset_on_device", c_i32), ("seed", c_u64), ("env_id_offset", c_i64)]
 
 
 class EnvStateView(ctypes.Structure):
     _fields_ = [(n, c_vp) for n in ("hpos", "hvel", "hgoal", "hstatic", "hhist", "hvalid", "rpose", "rprev", "rhist",
-                                    "rpastv", "rvalid", "gtime", "path_idx", "loc_to_start", "step_count")]
+                                    "rpastv", "rvalid", "gtime", "path_idx", "loc_to_start", "step_count", "sr_state")]
 
 
 class StepOut(ctypes.Structure):
-    _fields_ = [(n, c_vp) for n in ("pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode",
+    _fields_ = [(n, c_vp) for n in ("pt_state", "actions_used", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode",
                                     "spatial_edges", "human_valid", "detected_humans", "rewards", "info", "done_bits",
                                     "mpc_status", "done_flags", "slab")] + [("slab_bytes", ctypes.c_size_t)]
 

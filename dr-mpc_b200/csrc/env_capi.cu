@@ -89,6 +89,7 @@ void carve_state(EnvDev &D, void *base, size_t &bytes)
     D.step_count = c.take<int64_t>(E);
     D.reset_epoch = c.take<int32_t>(E);
     D.mpc_interp = c.take<double>(E);
+    D.sr_state = c.take<int32_t>(E * 4);
     D.stat_counters = c.take<unsigned long long>(16);
     D.stat_sums = c.take<double>(4);
     bytes = (c.off + 255) / 256 * 256;
@@ -99,6 +100,7 @@ void carve_slab(const EnvDev &D, int n_mpc_act, void *base, dre_step_out &o, Env
     Carver c(base);
     const size_t E = D.E, Nh = D.Nh, H = D.LB + 1, LB = D.LB;
     o.pt_state = od.pt_state = c.take<double>(E * 4 * (D.lookahead + D.lookbehind));
+    o.actions_used = od.actions_used = c.take<double>(E * 2);
     o.mpc_actions = od.mpc_actions = c.take<double>(E * n_mpc_act);
     o.robot_node = od.robot_node = c.take<double>(E * 2 * LB);
     o.past_robot_vel = od.past_robot_vel = c.take<double>(E * 2 * LB);
@@ -110,7 +112,7 @@ void carve_slab(const EnvDev &D, int n_mpc_act, void *base, dre_step_out &o, Env
     o.info = od.info = c.take<double>(E * 8);
     o.done_bits = od.done_bits = c.take<uint32_t>(E);
     o.mpc_status = od.mpc_status = c.take<dre_mpc_status>(E);
-    o.done_flags = od.done_flags = c.take<uint8_t>(E * 12);
+    o.done_flags = od.done_flags = c.take<uint8_t>(E * 16);
     bytes = (c.off + 255) / 256 * 256;
     o.slab = base;
     o.slab_bytes = bytes;
@@ -129,6 +131,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     if (cfg->num_envs <= 0 || cfg->num_humans <= 0 || cfg->num_humans > DRE_MAX_HUMANS || cfg->lookback < 1 || cfg->lookback > 32)
         return DRE_ERR_INVALID;
     if (cfg->lookahead + cfg->lookbehind <= 0 || !(cfg->time_step > 0)) return DRE_ERR_INVALID;
+    if (cfg->soft_reset_on_device && !cfg->auto_path_switch) return DRE_ERR_INVALID;
     dre_env *h = new (std::nothrow) dre_env();
     if (!h) return DRE_ERR_NOMEM;
     h->cfg = *cfg;
@@ -148,6 +151,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     D.corridor_max_dev = cfg->corridor_max_dev; D.eop_penalty = cfg->end_of_path_penalty;
     D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
     D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
+    D.soft_reset = cfg->soft_reset_on_device;
     D.seed = cfg->seed; D.env_id_offset = cfg->env_id_offset;
 
     int rc = dre_mpc_create(&cfg->mpc, cfg->num_envs, &h->mpc);
@@ -217,7 +221,7 @@ extern "C" int dre_env_state(dre_env *h, dre_env_state_view *v)
     v->hpos = (double *)D.hpos; v->hvel = (float *)D.hvel; v->hgoal = (double *)D.hgoal; v->hstatic = D.hstatic;
     v->hhist = (double *)D.hhist; v->hvalid = D.hvalid; v->rpose = D.rpose; v->rprev = D.rprev; v->rhist = D.rhist;
     v->rpastv = D.rpastv; v->rvalid = D.rvalid; v->gtime = D.gtime; v->path_idx = D.path_idx; v->loc_to_start = D.loc_to_start;
-    v->step_count = D.step_count;
+    v->step_count = D.step_count; v->sr_state = D.sr_state;
     return DRE_OK;
 }
 
@@ -365,7 +369,10 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     // the PT state (the second largest output) is final after pt_step: it travels during the MPC solve
     DRE_CUDA_TRY(cudaEventRecord(h->ev_pt, s));
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_pt, 0));
-    DRE_CUDA_TRY(d2h(h->out.pt_state, (size_t)4 * (h->D.lookahead + h->D.lookbehind) * sizeof(double), 0, E));
+    {   // pt_state and actions_used are adjacent at the head of the slab
+        const size_t head = (const char *)h->out.mpc_actions - dev;
+        DRE_CUDA_TRY(cudaMemcpyAsync(host, dev, head, cudaMemcpyDeviceToHost, c));
+    }
     rc = env_solve_mpc(h, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));

@@ -112,6 +112,91 @@ DRE_HD void pt_state_gen(const PathView &P, double px, double py, double pth, do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// HAAndPTEnv.soft_reset (reference HA_and_PT env.py:120-240) as a per-env state machine. The reference loops
+// `while done: pick a scripted action; self.step(action, soft_reset=True)` for ONE env; a batch steps in lock-step,
+// so the loop is unrolled over step() calls: before every step the machine looks at the previous step's done bits
+// and either hands control back to the caller's action (return 0) or supplies the scripted action (return 1).
+// ---------------------------------------------------------------------------------------------------------------
+enum { DRE_SR_NORMAL = 0, DRE_SR_MAIN = 1, DRE_SR_EXTRA = 2 };
+struct SrState {
+    int mode;     // NORMAL: not in soft_reset(); MAIN: inside the `while done` loop; EXTRA: inside the 7-step back-up loop (:227-233)
+    int oot;      // out_of_trigger_because_of_backup (:126)
+    int extra;    // back-up steps left in the EXTRA loop
+    int consec;   // consecutive_no_v (:122)
+    int steps;    // steps_in_soft_reset (:123)
+    int nb;       // num_backup_steps (:127)
+};
+DRE_HD SrState sr_unpack(const int32_t *p)
+{
+    SrState S;
+    S.mode = p[0] & 0xff; S.oot = (p[0] >> 8) & 0xff; S.extra = (p[0] >> 16) & 0xff;
+    S.consec = p[1]; S.steps = p[2]; S.nb = p[3];
+    return S;
+}
+DRE_HD void sr_pack(const SrState &S, int32_t *p)
+{
+    p[0] = S.mode | (S.oot << 8) | (S.extra << 16); p[1] = S.consec; p[2] = S.steps; p[3] = S.nb;
+}
+
+// prev_bits: DRE_DONE_* word of the previous step of this env (0 right after reset). (x, y, th): current robot pose.
+// P / lts: current path and localize_to_start flag. Returns 1 and sets (av, aw) when the step must run a scripted
+// action; `stuck` reports the reference's "Stuck in soft reset" exit (> 250 steps, :235-238).
+DRE_HD int soft_reset_decide(SrState &S, uint32_t prev_bits, const PathView &P, double x, double y, double th, bool lts,
+                             double &av, double &aw, bool &stuck)
+{
+    stuck = false;
+    const bool prev_done = (prev_bits & DRE_DONE_ANY) != 0;
+    const uint32_t reasons = prev_bits & 0xFFu;
+    if (S.mode == DRE_SR_MAIN) {
+        // end of a `while` iteration: the extra back-up loop starts if the main step was a back-up that cleared the triggers
+        if (!prev_done && S.oot) { S.mode = DRE_SR_EXTRA; S.extra = 7; }
+        else {
+            if (S.steps > 250) { stuck = true; S.mode = DRE_SR_NORMAL; return 0; }
+            if (!prev_done) { S.mode = DRE_SR_NORMAL; return 0; }          // `while done` ends: S' goes back to the caller
+        }
+    }
+    if (S.mode == DRE_SR_EXTRA) {
+        if (!prev_done && S.extra > 0) { S.extra -= 1; av = -0.3; aw = 0.0; return 1; }   // :229-233
+        if (S.steps > 250) { stuck = true; S.mode = DRE_SR_NORMAL; return 0; }
+        if (!prev_done) { S.mode = DRE_SR_NORMAL; return 0; }
+        S.mode = DRE_SR_MAIN;                                                // a trigger fired during the back-up: loop on
+    }
+    if (S.mode == DRE_SR_NORMAL) {
+        if (!prev_done) return 0;
+        S.consec = 0; S.steps = 0; S.nb = 0; S.oot = 0; S.extra = 0;        // soft_reset() entered (:121-127)
+    }
+    // ---- top of a `while done` iteration (:128-216) ----
+    // goal / end of path: the path was already switched inside the step that raised it (auto_path_switch, :130-141)
+    if ((reasons & (DRE_DONE_GOAL | DRE_DONE_END_OF_PATH)) != 0u || reasons == DRE_DONE_ACTUATION) {   // :184-185
+        S.mode = DRE_SR_NORMAL;
+        return 0;
+    }
+    S.mode = DRE_SR_MAIN;
+    if ((prev_bits & DRE_DONE_HA) != 0u && S.consec > 10 && S.nb < 5) {     // :187-190
+        av = -0.3; aw = 0.0;
+        S.nb += 1; S.oot = 1;
+    } else {
+        S.nb = 0; S.oot = 0;
+        // query_closest_path_node_plus_one (path_tracking_env.py:221-225), turn towards it (:194-206)
+        const Localization loc = localize_on_path(P, x, y, lts);
+        const int idx = (int)(loc.index + 1.0) % P.L;
+        const double desired = atan2(P.y[idx] - y, P.x[idx] - x);
+        const double th_diff = np_mod(desired - th + DRE_PI, 2.0 * DRE_PI) - DRE_PI;
+        const double w = th_diff < 0.0 ? -0.1 : 0.1;
+        if ((reasons & (DRE_DONE_CORRIDOR_HIT | DRE_DONE_SAFETY_CORRIDOR)) != 0u && (reasons & DRE_DONE_SAFETY_HUMAN) == 0u) {
+            if (fabs(th_diff) > 0.3) { av = 0.0; aw = w * 7.0; }
+            else { av = 0.5; aw = w; }
+            S.consec = 0;
+        } else {
+            av = 0.0; aw = 0.0;
+            S.consec += 1;
+        }
+    }
+    S.steps += 1;
+    return 1;
+}
+
 // uniform doubles for (env, step, stream id, draw): two per Philox call
 DRE_HD void env_uniform2(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t stream, uint32_t draw, double &u0, double &u1)
 {

@@ -168,7 +168,7 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
                 double *rp = D.rpose + (size_t)e * 4;
                 double av = 0.0, aw = 0.0;
                 if (mode == 0) {
-                    av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1];
+                    av = D.out.actions_used[(size_t)e * 2]; aw = D.out.actions_used[(size_t)e * 2 + 1];   // set by pt_step_kernel
                     if (D.orca.robot_visible) {   // pass 2 sees the robot at its new pose (already in rpose)
                         float *A = agents + (size_t)el * 5 * nA;
                         A[Nh] = (float)rp[0]; A[nA + Nh] = (float)rp[1];
@@ -326,8 +326,8 @@ ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
                     w1 |= (uint32_t)((all & order[4 + q]) != 0) << (8 * q);
                     w2 |= (uint32_t)((all & order[8 + q]) != 0) << (8 * q);
                 }
-                uint32_t *df = reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 12);
-                df[0] = w0; df[1] = w1; df[2] = w2;
+                uint32_t *df = reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 16);
+                df[0] = w0; df[1] = w1; df[2] = w2;   // df[3] (soft-reset flags) belongs to pt_step_kernel
             }
             if (D.stat_counters) {
                 const uint32_t sb[8] = {DRE_DONE_GOAL, DRE_DONE_COLLISION, DRE_DONE_SAFETY_HUMAN, DRE_DONE_TIMEOUT, DRE_DONE_END_OF_PATH,
@@ -413,9 +413,20 @@ __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
         bool lts = D.loc_to_start[e] != 0;
         Localization cur;
         if (mode == 0) {
+            // ---- which action runs: the caller's, or the scripted one of an env recovering from a termination ----
+            double av = D.actions[(size_t)e * 2], aw = D.actions[(size_t)e * 2 + 1];
+            uint32_t sr_flags = 0;
+            if (D.soft_reset) {
+                SrState S = sr_unpack(D.sr_state + (size_t)e * 4);
+                bool stuck;
+                if (soft_reset_decide(S, D.out.done_bits[e], P, cx, cy, cth, lts, av, aw, stuck)) sr_flags |= 1u;
+                if (stuck) sr_flags |= 1u << 8;
+                sr_pack(S, D.sr_state + (size_t)e * 4);
+            }
+            D.out.actions_used[(size_t)e * 2] = av; D.out.actions_used[(size_t)e * 2 + 1] = aw;
+            reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 16)[3] = sr_flags;
             // ---- robot.step(action): exact-arc unicycle (agent.py:169-176 -> unicycle.py:89-126) ----
             const double px = cx, py = cy, pth = cth;
-            const double av = D.actions[(size_t)e * 2], aw = D.actions[(size_t)e * 2 + 1];
             unicycle_step(px, py, pth, av, aw, D.dt, cx, cy, cth);
             D.rprev[(size_t)e * 4] = px; D.rprev[(size_t)e * 4 + 1] = py; D.rprev[(size_t)e * 4 + 2] = pth;
             rp[0] = cx; rp[1] = cy; rp[2] = cth;
@@ -529,6 +540,8 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
     D.path_idx[e] = 0;
     D.loc_to_start[e] = 1;
     D.mpc_iteration0[e] = 1;
+    for (int i = 0; i < 4; ++i) { D.sr_state[(size_t)e * 4 + i] = 0; reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 16)[i] = 0u; }
+    D.out.done_bits[e] = 0u;
     const uint64_t gid = (uint64_t)(D.env_id_offset + e);
     const uint64_t stp = ((uint64_t)D.reset_epoch[e] << 20) + (1ull << 18);
     for (int i = 0; i < Nh; ++i) {

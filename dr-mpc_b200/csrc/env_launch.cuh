@@ -3,7 +3,7 @@
 #include "launch.cuh"
 
 struct EnvOutDev {
-    double *pt_state, *mpc_actions, *robot_node, *past_robot_vel, *percent_episode, *spatial_edges, *human_valid,
+    double *pt_state, *actions_used, *mpc_actions, *robot_node, *past_robot_vel, *percent_episode, *spatial_edges, *human_valid,
         *detected_humans, *rewards, *info;
     uint32_t *done_bits;
     dre_mpc_status *mpc_status;
@@ -22,7 +22,7 @@ struct EnvDev {
     double collision_penalty, safety_dist, safety_penalty, dist_radius, dist_factor_v, dist_factor_th, act_min_vel, act_penalty;
     double pt_overall_scaling, goal_radius, goal_angle, goal_reward, path_adv_scaling, dev_xy, dev_th, dev_scale;
     double corridor_penalty, corridor_max_dev, eop_penalty, safety_corridor_penalty, safety_corridor_max_dev;
-    int lookahead, lookbehind, auto_path_switch;
+    int lookahead, lookbehind, auto_path_switch, soft_reset;
     uint64_t seed;
     int64_t env_id_offset;
     // ---- state (structure of arrays, env-major) ----
@@ -44,6 +44,7 @@ struct EnvDev {
     int32_t *reset_epoch;   // [E]
     double *mpc_interp;     // [E]
     uint8_t *mpc_iteration0; // [E] (aliases the MPC object's flags)
+    int32_t *sr_state;      // [E][4] soft-reset state machine
     // ---- paths ----
     const double *paths;
     const int32_t *lens;

@@ -84,13 +84,14 @@ class BatchedHAAndPTEnv:
         self.slab_bytes = int(o.slab_bytes)
         nact = 2 * min(self.K, self.cfg.actions_in_input)
         npt = 4 * (self.cfg.lookahead + self.cfg.lookbehind)
-        self._layout = [("pt_state", o.pt_state, (E, npt), "f8"), ("mpc_actions", o.mpc_actions, (E, nact), "f8"),
+        self._layout = [("pt_state", o.pt_state, (E, npt), "f8"), ("actions_used", o.actions_used, (E, 2), "f8"),
+                        ("mpc_actions", o.mpc_actions, (E, nact), "f8"),
                         ("robot_node", o.robot_node, (E, 2 * LB), "f8"), ("past_robot_vel", o.past_robot_vel, (E, 2 * LB), "f8"),
                         ("percent_episode", o.percent_episode, (E, 1), "f8"),
                         ("spatial_edges", o.spatial_edges, (E, Nh, 2 * H), "f8"), ("human_valid", o.human_valid, (E, Nh), "f8"),
                         ("detected_humans", o.detected_humans, (E,), "f8"), ("rewards", o.rewards, (E, 3), "f8"),
                         ("info", o.info, (E, 8), "f8"), ("done_bits", o.done_bits, (E,), "i4"),
-                        ("mpc_status", o.mpc_status, (E, 8), "i4"), ("done_flags", o.done_flags, (E, 12), "u1")]
+                        ("mpc_status", o.mpc_status, (E, 8), "i4"), ("done_flags", o.done_flags, (E, 16), "u1")]
         self.out = {name: _view(ptr, shape, kind, d) for name, ptr, shape, kind in self._layout}
         s = _lib.EnvStateView()
         _lib.check(self._L.dre_env_state(self._h, ctypes.byref(s)))
@@ -102,7 +103,7 @@ class BatchedHAAndPTEnv:
             "rhist": _view(s.rhist, (E, H, 4), "f8", d), "rpastv": _view(s.rpastv, (E, LB, 2), "f8", d),
             "rvalid": _view(s.rvalid, (E,), "i4", d), "gtime": _view(s.gtime, (E,), "f8", d),
             "path_idx": _view(s.path_idx, (E,), "i4", d), "loc_to_start": _view(s.loc_to_start, (E,), "u1", d),
-            "step_count": _view(s.step_count, (E,), "i8", d),
+            "step_count": _view(s.step_count, (E,), "i8", d), "sr_state": _view(s.sr_state, (E, 4), "i4", d),
         }
 
     def _stream(self):
@@ -137,11 +138,14 @@ class BatchedHAAndPTEnv:
         bits = o["done_bits"]
         r = o["rewards"]
         reward_return = {'R_PT': r[:, 0], 'R_DO': r[:, 1], 'R': r[:, 2]}
-        fl = o["done_flags"].view(torch.bool)       # zero-copy [E,12] views: no kernels are launched to package a step
+        fl = o["done_flags"].view(torch.bool)       # zero-copy [E,16] views: no kernels are launched to package a step
         done_return = {k: fl[:, i] for i, k in enumerate(('done_PT', 'done_HA', 'done', 'done_for_replay'))}
         info = {'done_bits': bits, 'disturbance_v': o["info"][:, 0], 'disturbance_th': o["info"][:, 1],
                 'path_advancement': o["info"][:, 2], 'deviation': o["info"][:, 3], 'dmin': o["info"][:, 4],
-                'interp_index': o["info"][:, 5], 'xy_dev': o["info"][:, 6], 'mpc_status': o["mpc_status"]}
+                'interp_index': o["info"][:, 5], 'xy_dev': o["info"][:, 6], 'mpc_status': o["mpc_status"],
+                # on-device soft reset (EngineConfig.soft_reset_on_device): transitions flagged here ran the scripted
+                # recovery action of HAAndPTEnv.soft_reset (env.py:120-240) and do not belong in the replay buffer
+                'soft_reset': fl[:, 12], 'soft_reset_stuck': fl[:, 13], 'actions_used': o["actions_used"]}
         eps_done_info = {k: fl[:, 4 + i] for i, k in enumerate(('success', 'collision', 'safety_human_raise', 'timeout',
                                                                  'deviation_end_of_path', 'corridor_hit',
                                                                  'safety_corridor_raise', 'actuation_termination'))}

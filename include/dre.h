@@ -141,6 +141,11 @@ typedef struct dre_env_config {
     int32_t mpc_actions_in_input;                /* config_PT.MPC.actions_in_input (4)                   */
     int32_t auto_path_switch;                    /* 1: advance to the next path on goal / end-of-path inside step()
                                                     (what soft_reset does at HA_and_PT env.py:130-141)   */
+    int32_t soft_reset_on_device;                /* 1: HAAndPTEnv.soft_reset (env.py:120-240) runs as a per-env state machine
+                                                    inside step(): while an env recovers from a termination its action is
+                                                    the scripted one (wait / back up / turn to the path) instead of the
+                                                    caller's, and the transition is flagged (done_flags[12]) so the caller
+                                                    keeps it out of the replay buffer. Needs auto_path_switch = 1.   */
     uint64_t seed;                               /* Philox key for device-side spawning / goal resampling */
     int64_t env_id_offset;                       /* global id of env 0 of this shard (multi-GPU)         */
 } dre_env_config;
@@ -163,6 +168,8 @@ typedef struct dre_env_state_view {
     int32_t *path_idx; /* [E]                   */
     uint8_t *loc_to_start; /* [E]               */
     int64_t *step_count;   /* [E]               */
+    int32_t *sr_state;     /* [E][4] soft-reset machine: {mode | out_of_trigger<<8 | extra_backup_left<<16,
+                              consecutive_no_v, steps_in_soft_reset, num_backup_steps} (env.py:121-127)   */
 } dre_env_state_view;
 
 /* One step's outputs: device pointers into ONE contiguous slab (so that a single D2H copy moves it).
@@ -170,6 +177,7 @@ typedef struct dre_env_state_view {
  * path_tracking_env.py:190-204) with the leading batch dim E instead of 1. */
 typedef struct dre_step_out {
     double *pt_state;        /* [E][100]            S['PT']['PT_state']            */
+    double *actions_used;    /* [E][2]  the (v, w) the step executed: the caller's, or the scripted soft-reset action */
     double *mpc_actions;     /* [E][2*min(K,A)]     S['PT']['MPC_actions']         */
     double *robot_node;      /* [E][2*LB]           S['HA']['robot_node']          */
     double *past_robot_vel;  /* [E][2*LB]           S['HA']['past_robot_velocities'] */
@@ -181,9 +189,10 @@ typedef struct dre_step_out {
     double *info;            /* [E][8]  disturbance_v, disturbance_th, path_advancement, deviation, dmin, interp_index, xy_dev, spare */
     uint32_t *done_bits;     /* [E]     DRE_DONE_* bits        (env.py:391-414)    */
     dre_mpc_status *mpc_status; /* [E]                                              */
-    uint8_t *done_flags;     /* [E][12] 0/1: done_PT, done_HA, done, done_for_replay (env.py:414), then eps_done_info
+    uint8_t *done_flags;     /* [E][16] 0/1: done_PT, done_HA, done, done_for_replay (env.py:414), then eps_done_info
                                 (env.py:391-404): success, collision, safety_human_raise, timeout, deviation_end_of_path,
-                                corridor_hit, safety_corridor_raise, actuation_termination */
+                                corridor_hit, safety_corridor_raise, actuation_termination; [12] this step ran a scripted
+                                soft-reset action, [13] soft reset gave up (> 250 steps, env.py:235-238), [14..15] spare */
     void *slab;              /* start of the contiguous slab                        */
     size_t slab_bytes;
 } dre_step_out;

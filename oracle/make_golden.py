@@ -134,7 +134,7 @@ def _snapshot(env, K):
     Nh = len(ha.humans)
     s = {
         "hpos": np.array([[h.px, h.py] for h in ha.humans]), "hvel": np.array([[h.vx, h.vy] for h in ha.humans], dtype=np.float32),
-        "hgoal": np.array([[h.gx, h.gy] for h in ha.humans]),
+        "hgoal": np.array([[h.gx, h.gy] for h in ha.humans]), "hstatic": np.array([bool(h.isObstacle) for h in ha.humans], dtype=np.uint8),
         "hhist": ha.human_history_global.copy(), "hvalid": ha.human_valid_history[:Nh].astype(np.int32),
         "rpose": np.array([env.robot.px, env.robot.py, env.robot.theta, 0.0]),
         "rprev": np.concatenate([env.prev_robot_pose, [0.0]]),
@@ -221,12 +221,86 @@ def golden_env():
     print("env_rollouts.npz", os.path.getsize(os.path.join(OUT, "env_rollouts.npz")), "bytes")
 
 
+# ------------------------------------------------------------------------------------------------------------
+# 4. HAAndPTEnv.soft_reset (HA_and_PT env.py:120-240): EVERY env.step call of a run, including the scripted ones the
+#    reference issues from inside soft_reset(), with the action it chose. env.step is wrapped on the instance (the
+#    reference code is untouched) so the calls made by soft_reset() are seen too.
+# ------------------------------------------------------------------------------------------------------------
+def golden_soft_reset():
+    from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
+    from environment.human_avoidance.utils.action import ActionRot
+    out = {}
+    for tag, Nh, seed, policy_steps in (("h6", 6, 3, 420), ("h10", 10, 4, 160), ("h6s", 6, 5, 60)):
+        cm = _config(Nh)
+        env = HAAndPTEnv(cm, seed_addition=seed)
+        env.case_counter['train'] = seed
+        K = cm.config_PT.MPC.planning_horizon
+        S = env.reset()
+        rng = np.random.default_rng(seed)
+        if tag == "h6s":
+            # a static human (crowd_sim.py:270-272) parked on the path: the robot runs into its safety range, waits more
+            # than 10 steps, backs up (env.py:187-190) and takes the 7 extra back-up steps (:227-233)
+            h0 = env.HA_env.humans[0]
+            node = env.PT_env.paths[0][:, 22]
+            h0.isObstacle = True
+            h0.px, h0.py, h0.vx, h0.vy, h0.gx, h0.gy = float(node[0]), float(node[1]), 0.0, 0.0, float(node[0]), float(node[1])
+        rec = []
+        inner = env.step
+
+        def recording_step(action, update=True, soft_reset=False, model_info=None):
+            pre = _snapshot(env, K)
+            r = inner(action, update=update, soft_reset=soft_reset, model_info=model_info)
+            S2, R, D, info, eps = r
+            bits = sum(b for name, b in _BITS.items() if name in info['done'])
+            rec.append({"pre": pre, "post": _snapshot(env, K), "action": np.array([action.v, action.w], dtype=np.float64),
+                        "soft": np.uint8(bool(soft_reset)), "bits": np.int64(bits), "done": np.uint8(D['done']),
+                        "done_HA": np.uint8(D['done_HA']), "rewards": np.array([R['R_PT'], R['R_DO'], R['R']])})
+            return r
+
+        env.step = recording_step
+        done_return, info = {'done': False}, None
+        n = 0
+        while n < policy_steps:
+            if done_return['done']:
+                S = env.soft_reset(done_return, info, S)
+                if S is None:
+                    break
+            a = np.array(S['PT']['MPC_actions'][0, :2], dtype=np.float64)
+            phase = (n // 20) % 6
+            if phase == 1:
+                a = a + rng.normal(0, 0.3, 2)
+            elif phase == 3 and tag != "h6s":
+                a = np.array([1.0, -0.35]) if (n // 120) % 2 == 0 else np.array([1.0, 0.5])   # leave the corridor
+            elif phase == 5 and tag == "h6":
+                a = np.array([0.0, 0.0]) if (n // 5) % 2 else a * 0.3                          # stall: actuation termination
+            a[0] = float(np.clip(a[0], 0, 1)); a[1] = float(np.clip(a[1], -1, 1))
+            S, R, D, info, eps = env.step(ActionRot(a[0], a[1]))
+            done_return = D
+            n += 1
+        for k in rec[0]["pre"]:
+            out[f"{tag}_pre_{k}"] = np.stack([np.asarray(r["pre"][k]) for r in rec])
+            out[f"{tag}_post_{k}"] = np.stack([np.asarray(r["post"][k]) for r in rec])
+        for k in ("action", "soft", "bits", "done", "done_HA", "rewards"):
+            out[f"{tag}_{k}"] = np.stack([np.asarray(r[k]) for r in rec])
+        soft = out[f"{tag}_soft"].astype(bool)
+        acts = out[f"{tag}_action"][soft]
+        kinds = {"wait": int(((acts[:, 0] == 0) & (acts[:, 1] == 0)).sum()), "backup": int((acts[:, 0] == -0.3).sum()),
+                 "turn": int(((acts[:, 0] == 0) & (acts[:, 1] != 0)).sum()), "creep": int((acts[:, 0] == 0.5).sum())}
+        allbits = out[f"{tag}_bits"]
+        print(tag, "calls", len(rec), "scripted", int(soft.sum()), kinds,
+              "done events", {k: int(((allbits & b) != 0).sum()) for k, b in _BITS.items()})
+    np.savez_compressed(os.path.join(OUT, "soft_reset.npz"), **out)
+    print("soft_reset.npz", os.path.getsize(os.path.join(OUT, "soft_reset.npz")), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["orca", "mpc", "env"]
+    which = sys.argv[1:] or ["orca", "mpc", "env", "soft_reset"]
     if "orca" in which:
         golden_orca()
     if "mpc" in which:
         golden_mpc()
     if "env" in which:
         golden_env()
+    if "soft_reset" in which:
+        golden_soft_reset()

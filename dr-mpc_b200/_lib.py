@@ -102,6 +102,7 @@ def load():
         L.dre_env_set_host_chunks.argtypes = [c_vp, c_i32]
         L.dre_env_observe.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
+        L.dre_env_cvmm_filter.argtypes = [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]
         L.dre_env_set_profiling.argtypes = [c_vp, c_i32]
         L.dre_env_kernel_ms.argtypes = [c_vp, c_vp, c_vp, c_i32]
     L.dre_measure_peak.argtypes = [c_i32, P(c_d)]

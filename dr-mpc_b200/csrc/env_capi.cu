@@ -441,6 +441,15 @@ extern "C" int dre_env_set_host_chunks(dre_env *h, int32_t chunks)
     return DRE_OK;
 }
 
+extern "C" int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lookahead_steps, const double *backup_actions,
+                                   int32_t num_backup, double *safe_actions, int32_t *info4, uint8_t *candidate_safe, void *stream)
+{
+    if (!h || !actions || !backup_actions || !safe_actions) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    return dre_env_launch_cvmm(h->D, actions, lookahead_steps, backup_actions, num_backup, safe_actions, info4, candidate_safe,
+                               (cudaStream_t)stream);
+}
+
 extern "C" int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream)
 {
     if (!h) return DRE_ERR_INVALID;

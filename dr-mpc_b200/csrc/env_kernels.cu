@@ -584,6 +584,99 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CVMM safety filter: HAAndPTEnv.cvmm_diverse_safety_pipeline / cvmm_safety_check (HA_and_PT env.py:422-513).
+// One warp per env, lane c = candidate action c (0 = the policy's action, 1..A = the back-up set): constant-velocity
+// roll-out of the humans against the exact-arc roll-out of the robot, plus the corridor test on the first two steps.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ bool cvmm_safety_check(const EnvDev &D, int e, const PathView &P, bool lts, double v, double w, int num_steps, double &fde)
+{
+    double x = D.rpose[(size_t)e * 4], y = D.rpose[(size_t)e * 4 + 1], th = D.rpose[(size_t)e * 4 + 2];
+    const double lim = D.robot_radius + D.human_radius + 0.22 + 1e-3;   // continuous task (:492-494)
+    double dist_to_path = 0.0;
+    fde = 1e10;
+    for (int i = 0; i < num_steps; ++i) {
+        double nx, ny, nth;
+        unicycle_step(x, y, th, v, w, D.dt, nx, ny, nth);
+        x = nx; y = ny; th = nth;
+        const double tt = D.dt * (double)(i + 1);
+        for (int j = 0; j < D.Nh; ++j) {
+            const double2 hp = D.hpos[(size_t)e * D.Nh + j];
+            const float2 hv = D.hvel[(size_t)e * D.Nh + j];
+            const double hx = hp.x + (double)hv.x * tt, hy = hp.y + (double)hv.y * tt;
+            const double dx = hx - x, dy = hy - y;
+            if (sqrt(dx * dx + dy * dy) < lim) return false;
+        }
+        if (i < 2) {   // query_off_path (path_tracking_env.py:207-214)
+            const Localization loc = localize_on_path(P, x, y, lts);
+            const double ddx = x - loc.ix, ddy = y - loc.iy;
+            dist_to_path = sqrt(ddx * ddx + ddy * ddy);
+            if (D.safety_corridor_max_dev < dist_to_path) return false;
+        }
+    }
+    fde = dist_to_path;
+    return true;
+}
+
+// info[e] = {original_safe, num_safe among the back-up actions (0 if the original was safe), chosen back-up index
+// (-1 = the original action), 1 if the choice was the random fall-back (no safe action)}
+__global__ void __launch_bounds__(128) cvmm_filter_kernel(EnvDev D, const double *__restrict__ actions, int num_steps,
+                                                          const double *__restrict__ backup, int A, double *__restrict__ safe_out,
+                                                          int32_t *__restrict__ info, uint8_t *__restrict__ cand_safe)
+{
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, c = threadIdx.x & 31;
+    if (e >= D.E) return;
+    const PathView P = path_view(D.paths, D.path_stride, D.path_idx[e], D.lens);
+    const bool lts = D.loc_to_start[e] != 0;
+    const double tv = actions[(size_t)e * 2], tw = actions[(size_t)e * 2 + 1];
+    double v = tv, w = tw;
+    if (c >= 1 && c <= A) { v = backup[(size_t)(c - 1) * 2]; w = backup[(size_t)(c - 1) * 2 + 1]; }
+    bool safe = false;
+    double fde = 1e10;
+    if (c <= A) safe = cvmm_safety_check(D, e, P, lts, v, w, num_steps, fde);
+    if (cand_safe != nullptr && c <= A) cand_safe[(size_t)e * (A + 1) + c] = safe ? 1 : 0;
+    const unsigned all = __ballot_sync(0xffffffffu, safe);
+    const bool orig_safe = (all & 1u) != 0u;
+    const unsigned bm = all & ~1u;                     // safe back-up actions
+    double ov = tv, ow = tw;
+    int chosen = -1, nsafe = 0, random = 0;
+    if (!orig_safe) {
+        nsafe = __popc(bm);
+        if (nsafe == 0) {   // random back-up action (:459-464; np.random there, Philox here)
+            double u0, u1;
+            env_uniform2(D.seed, (uint64_t)(D.env_id_offset + e), (uint64_t)D.step_count[e] + ((uint64_t)D.reset_epoch[e] << 20), 0xC7u, 0u, u0, u1);
+            chosen = (int)(u0 * (double)A);
+            if (chosen >= A) chosen = A - 1;
+            random = 1;
+        } else {
+            // highest speed among the safe ones, then the angular velocity closest to the policy's (first occurrence) (:467-477)
+            double vmax = (bm >> c) & 1u ? v : -INFINITY;
+            for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            const bool at_max = ((bm >> c) & 1u) && v == vmax;
+            double diff = at_max ? fabs(w - tw) : INFINITY;
+            double dmin = diff;
+            for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+            const unsigned pick = __ballot_sync(0xffffffffu, at_max && diff == dmin);
+            chosen = __ffs((int)pick) - 2;             // lane c holds back-up action c - 1
+        }
+        ov = backup[(size_t)chosen * 2]; ow = backup[(size_t)chosen * 2 + 1];
+    }
+    if (c == 0) {
+        safe_out[(size_t)e * 2] = ov; safe_out[(size_t)e * 2 + 1] = ow;
+        if (info != nullptr) { info[(size_t)e * 4] = orig_safe ? 1 : 0; info[(size_t)e * 4 + 1] = nsafe; info[(size_t)e * 4 + 2] = chosen; info[(size_t)e * 4 + 3] = random; }
+    }
+}
+
+int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, const double *backup, int A, double *safe_out,
+                        int32_t *info, uint8_t *cand_safe, cudaStream_t s)
+{
+    if (A < 1 || A > 31 || num_steps < 1) return DRE_ERR_INVALID;
+    const int threads = 128, envs_per_block = threads / 32;
+    cvmm_filter_kernel<<<(D.E + envs_per_block - 1) / envs_per_block, threads, 0, s>>>(D, actions, num_steps, backup, A, safe_out, info, cand_safe);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 int dre_env_ha_envs_per_cta(const EnvDev &D)

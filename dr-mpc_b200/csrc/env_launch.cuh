@@ -60,6 +60,8 @@ int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s);
 int dre_env_ha_envs_per_cta(const EnvDev &D);
 int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s);
 int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s);
+int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, const double *backup, int A, double *safe_out,
+                        int32_t *info, uint8_t *cand_safe, cudaStream_t s);
 int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s);
 
 // capi.cu accessors

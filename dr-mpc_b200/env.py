@@ -174,6 +174,28 @@ class BatchedHAAndPTEnv:
                                              ctypes.c_void_p(self._host_slab.data_ptr())))
         return self._host_views
 
+    CVMM_ACTION_SET = ((0.05, -0.8), (0.15, -0.8), (0.6, -0.8), (0.05, -0.2), (0.15, -0.2), (0.6, -0.2), (0.15, 0.0), (0.6, 0.0),
+                       (0.05, 0.2), (0.15, 0.2), (0.6, 0.2), (0.05, 0.8), (0.15, 0.8), (0.6, 0.8))   # config_general.py:88-91
+
+    def cvmm_diverse_safety_pipeline(self, action_execute, num_steps=8, backup_actions=None, want_candidates=False):
+        """HAAndPTEnv.cvmm_diverse_safety_pipeline (env.py:422-473) for every env: `action_execute` [E,2] float64 CUDA
+        tensor -> (safe_actions [E,2], info). info['original_safe'] / ['num_safe'] / ['chosen'] (-1 = original kept) /
+        ['random'] (no safe action: random back-up, env.py:459-464) are int32 [E] tensors; the env is not modified."""
+        import torch
+        a = action_execute.to(device=self.device, dtype=torch.float64).contiguous()
+        bk = torch.as_tensor(np.asarray(self.CVMM_ACTION_SET if backup_actions is None else backup_actions, dtype=np.float64),
+                             device=self.device).contiguous()
+        out = torch.empty_like(a)
+        info = torch.empty((self.E, 4), dtype=torch.int32, device=self.device)
+        cand = torch.empty((self.E, bk.shape[0] + 1), dtype=torch.uint8, device=self.device) if want_candidates else None
+        _lib.check(self._L.dre_env_cvmm_filter(self._h, ctypes.c_void_p(a.data_ptr()), int(num_steps), ctypes.c_void_p(bk.data_ptr()),
+                                               int(bk.shape[0]), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(info.data_ptr()),
+                                               ctypes.c_void_p(cand.data_ptr()) if cand is not None else None, self._stream()))
+        d = {'original_safe': info[:, 0], 'num_safe': info[:, 1], 'chosen': info[:, 2], 'random': info[:, 3]}
+        if cand is not None:
+            d['candidate_safe'] = cand
+        return out, d
+
     def set_host_chunks(self, chunks):
         """Number of env chunks step_host pipelines the crowd half and its D2H copies in (1 = no pipelining)."""
         _lib.check(self._L.dre_env_set_host_chunks(self._h, int(chunks)))

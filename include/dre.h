@@ -220,6 +220,17 @@ int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
 int dre_env_set_host_chunks(dre_env *h, int32_t chunks);
 /* regenerate observations only (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148) */
 int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
+/*
+ * CVMM safety filter: HAAndPTEnv.cvmm_diverse_safety_pipeline(action_execute, num_steps, backup_actions)
+ * (HA_and_PT env.py:422-513) for every env. actions dev double[E][2] = the policy's (v, w); backup_actions dev
+ * double[A][2] (A <= 31; config_general.safety_module.params['action_set']); lookahead_steps = params['lookahead_steps'].
+ * -> safe_actions dev double[E][2]; info4 dev int32[E][4] or NULL = {original action safe, number of safe back-up actions,
+ * chosen back-up index or -1 for the original, 1 if it is the random fall-back taken when nothing is safe};
+ * candidate_safe dev uint8[E][A+1] or NULL = cvmm_safety_check of the original (slot 0) and of every back-up action.
+ * The env state is not modified.
+ */
+int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lookahead_steps, const double *backup_actions,
+                        int32_t num_backup, double *safe_actions, int32_t *info4, uint8_t *candidate_safe, void *stream);
 /* episode statistics accumulated on device since the last call: int64[16]
  * {steps, success, collision, safety_human_raise, timeout, deviation_end_of_path, corridor_hit,
  *  safety_corridor_raise, actuation_termination, mpc_retries, mpc_gave_up, orca_lp3, 4 spare} and

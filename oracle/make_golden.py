@@ -293,9 +293,64 @@ def golden_soft_reset():
     print("soft_reset.npz", os.path.getsize(os.path.join(OUT, "soft_reset.npz")), "bytes")
 
 
+# ------------------------------------------------------------------------------------------------------------
+# 5. CVMM safety filter: HAAndPTEnv.cvmm_safety_check / cvmm_diverse_safety_pipeline (HA_and_PT env.py:422-513) on the
+#    states of a run, for the policy's action, a noisy one and an aggressive one.
+# ------------------------------------------------------------------------------------------------------------
+def golden_cvmm():
+    from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
+    from environment.human_avoidance.utils.action import ActionRot
+    out = {}
+    for tag, Nh, seed, steps in (("h6", 6, 6, 150), ("h10", 10, 7, 90)):
+        cm = _config(Nh)
+        action_set = cm.config_general.safety_module.params['action_set']
+        nsteps = cm.config_general.safety_module.params['lookahead_steps']
+        env = HAAndPTEnv(cm, seed_addition=seed)
+        env.case_counter['train'] = seed
+        K = cm.config_PT.MPC.planning_horizon
+        S = env.reset()
+        rng = np.random.default_rng(seed)
+        rec = []
+        done_return, info = {'done': False}, None
+        for n in range(steps):
+            if done_return['done']:
+                S = env.soft_reset(done_return, info, S)
+                if S is None:
+                    break
+            mpc_a = np.array(S['PT']['MPC_actions'][0, :2], dtype=np.float64)
+            pre = _snapshot(env, K)
+            for kind in range(3):
+                if kind == 0:
+                    a = mpc_a.copy()
+                elif kind == 1:
+                    a = np.clip(mpc_a + rng.normal(0, 0.35, 2), [0, -1], [1, 1])
+                else:
+                    a = np.array([rng.uniform(0.6, 1.0), rng.choice([-1.0, 1.0]) * rng.uniform(0.3, 1.0)])
+                cand = [env.cvmm_safety_check(a, nsteps)] + [env.cvmm_safety_check(action_set[i], nsteps) for i in range(action_set.shape[0])]
+                st = np.random.get_state()
+                act, inf = env.cvmm_diverse_safety_pipeline(a, nsteps, action_set)
+                np.random.set_state(st)      # the fall-back draw must not perturb the run's goal resampling
+                rec.append({"pre": pre, "action": a, "cand_safe": np.array([c[0] for c in cand], dtype=np.uint8),
+                            "cand_dist": np.array([c[1] for c in cand]), "safe_action": np.array([act.v, act.w]),
+                            "random": np.uint8(inf['RL_action_bool'].startswith('no safe'))})
+            a = mpc_a + (rng.normal(0, 0.25, 2) if (n // 12) % 2 else 0.0)
+            S, R, done_return, info, eps = env.step(ActionRot(float(np.clip(a[0], 0, 1)), float(np.clip(a[1], -1, 1))))
+        for k in rec[0]["pre"]:
+            out[f"{tag}_pre_{k}"] = np.stack([np.asarray(r["pre"][k]) for r in rec])
+        for k in ("action", "cand_safe", "cand_dist", "safe_action", "random"):
+            out[f"{tag}_{k}"] = np.stack([np.asarray(r[k]) for r in rec])
+        cs = out[f"{tag}_cand_safe"]
+        print(tag, "queries", len(rec), "original safe", int(cs[:, 0].sum()), "none safe", int(out[f"{tag}_random"].sum()),
+              "mean safe back-ups", float(cs[:, 1:].sum(1).mean()))
+    out["action_set"] = np.asarray(action_set, dtype=np.float64)
+    out["lookahead_steps"] = np.int64(nsteps)
+    np.savez_compressed(os.path.join(OUT, "cvmm.npz"), **out)
+    print("cvmm.npz", os.path.getsize(os.path.join(OUT, "cvmm.npz")), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["orca", "mpc", "env", "soft_reset"]
+    which = sys.argv[1:] or ["orca", "mpc", "env", "soft_reset", "cvmm"]
     if "orca" in which:
         golden_orca()
     if "mpc" in which:
@@ -304,3 +359,5 @@ if __name__ == "__main__":
         golden_env()
     if "soft_reset" in which:
         golden_soft_reset()
+    if "cvmm" in which:
+        golden_cvmm()

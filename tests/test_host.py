@@ -122,6 +122,40 @@ def test_device_mpc_header_on_host_matches_oracle(oracle, golden_mpc):
             assert np.abs(wT - ob.warm_T)[same].max() < 1e-5
 
 
+def test_soft_reset_machine_on_host_follows_reference(golden_mpc):
+    """The kernel's soft-reset decision code (dr-mpc_b200/csrc/env_device.cuh: soft_reset_decide), compiled for the host,
+    replays every env.step call the reference's own HAAndPTEnv.soft_reset issued (tests/golden/soft_reset.npz): same
+    scripted-or-caller decision and the same scripted action, bit for bit, at every call."""
+    hh = os.path.join(REPO, "tests", "host_harness")
+    so = os.path.join(hh, "libenv_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include",
+                           "-o", so, os.path.join(hh, "env_host.cpp")])
+    lib = ctypes.CDLL(so)
+    g = np.load(os.path.join(REPO, "tests", "golden", "soft_reset.npz"))
+    _, tab, lens = mpc_path_table(golden_mpc)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    seen = set()
+    for tag in ("h6", "h10", "h6s"):
+        T = g[f"{tag}_action"].shape[0]
+        bits = g[f"{tag}_bits"].astype(np.uint32)
+        full = bits | (g[f"{tag}_done_HA"].astype(np.uint32) << 16) | ((bits != 0).astype(np.uint32) << 18)
+        prev = np.concatenate([[0], full[:-1]]).astype(np.uint32)
+        pose = np.ascontiguousarray(g[f"{tag}_pre_rpose"][:, :3])
+        pid = np.ascontiguousarray(g[f"{tag}_pre_path_idx"].astype(np.int32))
+        lts = np.ascontiguousarray(g[f"{tag}_pre_loc_to_start"].astype(np.uint8))
+        scripted = np.zeros(T, dtype=np.uint8); action = np.zeros((T, 2)); stuck = ctypes.c_uint8(0)
+        assert lib.host_soft_reset_replay(T, p(prev), p(pose), p(pid), p(lts), p(tab), tab.shape[2], p(lens), p(scripted), p(action),
+                                          ctypes.byref(stuck)) == 0
+        soft = g[f"{tag}_soft"].astype(bool)
+        assert np.array_equal(scripted.astype(bool), soft), np.argwhere(scripted.astype(bool) != soft)[:5]
+        assert np.array_equal(action[soft], g[f"{tag}_action"][soft])
+        assert stuck.value == 0
+        a = g[f"{tag}_action"][soft]
+        seen |= {"backup" if r[0] == -0.3 else "creep" if r[0] == 0.5 else "turn" if r[1] != 0 else "wait" for r in a}
+    assert seen == {"wait", "backup", "turn", "creep"}
+
+
 def test_shard_envs_partitions_exactly():
     from dr_mpc_b200.parallel import shard_envs
     for total, world in ((16384, 8), (65536, 8), (1000, 3), (5, 8), (16384, 1)):

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdre.so")
+LIB_PATH = os.environ.get("DRE_LIB") or os.path.join(_HERE, "libdre.so")   # DRE_LIB: A/B builds of the same library
 
 c_i32, c_u8p, c_f, c_d, c_vp, c_u64, c_i64 = (ctypes.c_int32, ctypes.POINTER(ctypes.c_uint8), ctypes.c_float,
                                               ctypes.c_double, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64)

@@ -88,7 +88,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
 // mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
 template <int G>
 __global__ void __launch_bounds__(512)
-ha_step_kernel(EnvDev D, int EPB, int mode, int write_obs, HaLayout lay)
+ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_obs, const __grid_constant__ HaLayout lay)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0), H = D.LB + 1;

@@ -35,6 +35,7 @@ struct TileGroup {
     // group-wide reductions in one REDUX instruction (sm_100a has the fp32 min/max forms; min/max are exact, so the
     // result equals the sequential scan bit for bit)
     __device__ int min_int(int v) const { return __reduce_min_sync(lane_mask(), v); }
+    __device__ int sum_int(int v) const { return __reduce_add_sync(lane_mask(), v); }
     __device__ float min_f32(float v) const
     {
         float r;
@@ -61,10 +62,14 @@ struct SerialGroup {
     DRE_HD int bcast(int v, int) const { return v; }
     DRE_HD void sync() const {}
     DRE_HD int min_int(int v) const { return v; }
+    DRE_HD int sum_int(int v) const { return v; }
     DRE_HD float min_f32(float v) const { return v; }
     DRE_HD float max_f32(float v) const { return v; }
 };
 
+#ifndef DRE_LP1_SERIAL
+#define DRE_LP1_SERIAL 4   // LP1 scans over at most this many earlier lines run redundantly on every lane (no group reduction)
+#endif
 struct OLine { float px, py, dx, dy; };   // point, direction (16 B, float4-compatible)
 
 DRE_HD int dre_ffs(unsigned b)
@@ -123,24 +128,29 @@ DRE_HD bool orca_lp1(const Grp &g, const OLine *L, int i, float radius, float ox
     const float sq = sqrtf(disc);
     float tL = -dotProduct - sq;
     float tR = -dotProduct + sq;
-    bool fail = false;
+    // The scan over the earlier lines is a min/max reduction (tL only grows, tR only shrinks, so RVO2's early exits
+    // change nothing); an infeasible parallel line is folded in as tL = +inf. Short scans -- most LP1 calls sit on one
+    // of the first lines -- are done redundantly by every lane: a group-wide reduction inside a diverged warp costs
+    // more than four line tests.
+    const bool serial = G == 1 || i <= DRE_LP1_SERIAL;
 #pragma unroll 1
-    for (int j = lane; j < i; j += G) {
+    for (int j = serial ? 0 : lane; j < i; j += serial ? 1 : G) {
         const OLine lj = L[j];
         const float den = li.dx * lj.dy - li.dy * lj.dx;
         const float num = lj.dx * (li.py - lj.py) - lj.dy * (li.px - lj.px);
         if (fabsf(den) <= DRE_RVO_EPSILON) {
-            if (num < 0.0f) fail = true;
+            if (num < 0.0f) tL = INFINITY;
         } else {
             const float t = num / den;
             if (den >= 0.0f) tR = fminf(tR, t);
             else tL = fmaxf(tL, t);
         }
     }
-    tR = g.min_f32(tR);
-    tL = g.max_f32(tL);
-    fail = g.any(fail);
-    if (fail || tL > tR) return false;
+    if (!serial) {
+        tR = g.min_f32(tR);
+        tL = g.max_f32(tL);
+    }
+    if (tL > tR) return false;
     if (dirOpt) {
         if (ox * li.dx + oy * li.dy > 0.0f) { rx = li.px + tR * li.dx; ry = li.py + tR * li.dy; }
         else { rx = li.px + tL * li.dx; ry = li.py + tL * li.dy; }
@@ -223,24 +233,23 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     const float px = ax[self], py = ay[self], vx = avx[self], vy = avy[self], rs = ar[self];
     const float rangeSq = neighborDist * neighborDist;
     const int nA4 = (nA + 3) & ~3;
+    int cnt = 0;
     for (int j = lane; j < nA4; j += G) {
         float d = INFINITY;
         if (j < nA) {
             const float dx = px - ax[j], dy = py - ay[j];
             const float dd = dx * dx + dy * dy;
-            if (j != self && dd < rangeSq) d = dd;
+            if (j != self && dd < rangeSq) { d = dd; ++cnt; }
         }
         sdist[j] = d;
     }
+    cnt = g.sum_int(cnt);   // also orders the sdist stores before the ranking reads
     g.sync();
     // rank of neighbour j = #{k : (d_k, k) < (d_j, j)} (RVO2 insertNeighbor: ascending distSq, ties by visit order).
     // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
-    int cnt = 0;
     unsigned mask = 0;
-    for (int base = 0; base < nA; base += G) {
-        const int j = base + lane;
-        const bool in = (j < nA) && (sdist[j] < INFINITY);
-        cnt += dre_popc(g.ballot(in));
+    for (int j = lane; j < nA; j += G) {
+        const bool in = sdist[j] < INFINITY;
         if (in) {
             const unsigned uj = dre_f2u(sdist[j]);
             int r = 0, eq = 0;

@@ -18,6 +18,7 @@
 //                    observations starts while later CTAs of the same launch are still computing.
 //   env_reset_kernel : reset_continuous_task (HA_and_PT env.py:263-280) + HAEnv.reset (:297-338) + spawning
 //                    (crowd_sim.py:232-262 with Philox).
+#include <cstdlib>
 #include "orca_device.cuh"
 #include "env_device.cuh"
 #include "env_launch.cuh"
@@ -679,10 +680,24 @@ int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, c
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
+// threads per CTA of ha_step_kernel; DRE_HA_THREADS / DRE_HA_AGENTS_PER_GROUP override them for A/B measurements
+static int dre_ha_threads()
+{
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("DRE_HA_THREADS"); v = e ? atoi(e) : 128; if (v != 64 && v != 128 && v != 256 && v != 512) v = 128; }
+    return v;
+}
+static int dre_ha_agents_per_group()
+{
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("DRE_HA_AGENTS_PER_GROUP"); v = e ? atoi(e) : 8; if (v < 1 || v > 64) v = 8; }
+    return v;
+}
+
 int dre_env_ha_envs_per_cta(const EnvDev &D)
 {
     const int G = dre_orca_pick_group(D.orca, D.Nh);
-    int EPB = (5 * (256 / G)) / D.Nh;
+    int EPB = (dre_ha_agents_per_group() * (dre_ha_threads() / G)) / D.Nh;
     if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     return EPB < 1 ? 1 : EPB;
 }
@@ -691,8 +706,10 @@ template <int G>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
-    // 256 threads = 256/G lane-groups; ~5 agents per group so the dynamic schedule can even out LP2 / LP3 solves
-    const int threads = 256;
+    // 128 threads = 128/G lane-groups and ~8 agents per group so the dynamic schedule can even out LP2 / LP3 solves; measured
+    // on B200 at 16384 x 20: 128 threads 0.66 ms, 256 threads 0.71 ms, 512 threads 0.88 ms (CTA barriers cost less when more,
+    // smaller CTAs share an SM)
+    const int threads = dre_ha_threads();
     const int EPB = dre_env_ha_envs_per_cta(D);
     const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
     auto kern = ha_step_kernel<G>;

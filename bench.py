@@ -278,6 +278,11 @@ def run_ours(a):
         traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
+    issue = None
+    try:
+        issue = json.load(open(os.path.join(REPO, "profiles", "issue.json")))
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": dom_bytes / (kavg[dom] * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom_bytes / (kavg[dom] * 1e-3) * 1e-9 / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                 "note": "the path is CUDA-core latency/issue bound, not HBM- or tensor-bound (SURVEY 8(d)); see roofline_compute"}
@@ -289,7 +294,11 @@ def run_ours(a):
                                             "flops_per_orca_solve": flops_solve},
                                 "mpc_solve": {"tflops": mpc_flops / (kavg["mpc_solve"] * 1e-3) * 1e-12, "frac_fp64": mpc_flops / (kavg["mpc_solve"] * 1e-3) * 1e-12 / peak64.value,
                                               "mean_lm_solves": float(mst[:, 2].mean()), "mean_lm_iters": float(mst[:, 0].mean())}},
-                        "peaks_tflops": {"fp32": peak32.value, "fp64": peak64.value}}
+                        "peaks_tflops": {"fp32": peak32.value, "fp64": peak64.value},
+                        "ncu_issue_slots": issue,
+                        "note": "algorithmic flops (SURVEY 8(d)) are a small part of the issued instructions: the kernels are bound by "
+                                "instruction issue (ha_step) and by the fp64 pipe's 2-cycle warp-instruction cadence (mpc_solve); "
+                                "ncu_issue_slots holds the issue-slot utilisation of the committed ncu capture"}
 
     # ---------------- end to end through the host-buffer C-ABI call (closed loop through host memory) ----------------
     noise_h = noise[:8].cpu().numpy()

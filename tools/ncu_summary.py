@@ -64,6 +64,7 @@ if rep:
             "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio"]
     seen = {}
     traffic = {}
+    issue = {}
     with open(os.path.join(out_dir, f"{tag}_kernels.txt"), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on  (python bench.py --steps 3 --warmup 3 --no-cpu-baseline)\n")
         for r in rows[2:]:
@@ -87,6 +88,11 @@ if rep:
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
             key = "ha_step" if "ha_step" in name else ("mpc_solve" if "mpc_coop" in name or "mpc_act" in name else ("pt_step" if "pt_step" in name else name))
             traffic[key] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+            issue[key] = {"issue_active_pct": float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]].replace(",", "")),
+                          "warps_active_pct": float(r[idx["sm__warps_active.avg.pct_of_peak_sustained_active"]].replace(",", "")),
+                          "threads_per_warp_inst": float(r[idx["smsp__thread_inst_executed_per_inst_executed.ratio"]].replace(",", "")),
+                          "warp_instructions": float(r[idx["smsp__inst_executed.sum"]].replace(",", "")), "source": f"profiles/{tag}_kernels.txt"}
     json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
+    json.dump(issue, open(os.path.join(out_dir, "issue.json"), "w"), indent=1)
     print(open(os.path.join(out_dir, f"{tag}_kernels.txt")).read()[:3000])
     print(traffic)

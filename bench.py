@@ -318,9 +318,10 @@ def run_ours(a):
     barrier()
     e2e = {"value": world * E * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 2 * 8, "d2h_bytes_per_step": env.slab_bytes,
            "steps": n_e2e, "ms_per_step": e2e_s / n_e2e * 1e3,
-           "what": "dre_env_step_host: pinned host actions -> H2D -> robot/path half + MPC solve -> crowd half in env chunks on two "
-                   "streams, each chunk's outputs copied D2H while the next computes -> the whole output slab (observations, rewards, "
-                   "done bits, MPC status) in pinned host memory; the next action is read from the host slab"}
+           "what": "dre_env_step_host: pinned host actions -> H2D -> robot/path half (its PT state travels during the MPC solve) -> MPC "
+                   "-> one crowd-half launch whose env chunks raise flags in mapped host memory as their observations are written; "
+                   "the host thread queues each chunk's D2H on a copy stream -> the whole output slab (observations, rewards, done "
+                   "bits, MPC status) in pinned host memory; the next action is read from the host slab"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -42,7 +42,7 @@ static int prof_drain(dre_env *h)
 {
     for (int i = 0; i < h->ev_used; ++i) {
         DRE_CUDA_TRY(cudaEventSynchronize(h->ev[i][4]));
-        static const int slot[4] = {1, 2, 3, 0};   // launch order pt, mpc, stats, ha -> {ha, pt, mpc, stats}
+        static const int slot[4] = {1, 0, 2, 3};   // launch order pt, ha, mpc, stats -> {ha, pt, mpc, stats}
         for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
             DRE_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[i][k], h->ev[i][k + 1]));
@@ -284,31 +284,32 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     EnvDev D = h->D;
     D.actions = actions;
-    // robot/path half + MPC solve first, crowd half (which merges rewards / dones) last: see env_kernels.cu
+    // robot/path half, crowd half (which merges rewards / dones), MPC solve: see env_kernels.cu. The crowd half and the
+    // solve only depend on pt_step; the solve goes last so that, on the host path, the crowd's copies overlap it.
     if (!h->profiling) {
         int rc = dre_env_launch_pt(D, 0, s);
         if (rc) return rc;
-        rc = env_solve_mpc(h, s);
+        rc = dre_env_launch_ha(D, 0, 1, s);
         if (rc) return rc;
-        return dre_env_launch_ha(D, 0, 1, s);
+        return env_solve_mpc(h, s);
     }
     if (h->ev_used == dre_env::PROF_RING) { const int rc = prof_drain(h); if (rc) return rc; }
     cudaEvent_t *ev = h->ev[h->ev_used];
     const int nact = n_mpc_actions(h->cfg);
-    // event order = launch order: pt_step, mpc_solve, mpc_stats, ha_step (prof_drain maps them back to the
+    // event order = launch order: pt_step, ha_step, mpc_solve, mpc_stats (prof_drain maps them back to the
     // documented {ha_step, pt_step, mpc_solve, mpc_stats} order)
     DRE_CUDA_TRY(cudaEventRecord(ev[0], s));
     int rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(ev[1], s));
+    rc = dre_env_launch_ha(D, 0, 1, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(ev[2], s));
     rc = dre_mpc_launch(dre_mpc_params_of(h->mpc), dre_mpc_state_of(h->mpc), D.path_idx, D.mpc_interp, D.rpose, 4,
                         D.out.mpc_actions, nact, nact, D.out.mpc_status, nullptr, s);
     if (rc) return rc;
-    DRE_CUDA_TRY(cudaEventRecord(ev[2], s));
-    rc = dre_env_launch_mpc_stats(D, s);
-    if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(ev[3], s));
-    rc = dre_env_launch_ha(D, 0, 1, s);
+    rc = dre_env_launch_mpc_stats(D, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(ev[4], s));
     h->ev_used++;
@@ -366,19 +367,15 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     };
     int rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
-    // the PT state (the second largest output) is final after pt_step: it travels during the MPC solve
+    // the PT state (the second largest output) and the executed actions are final after pt_step
     DRE_CUDA_TRY(cudaEventRecord(h->ev_pt, s));
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_pt, 0));
     {   // pt_state and actions_used are adjacent at the head of the slab
         const size_t head = (const char *)h->out.mpc_actions - dev;
         DRE_CUDA_TRY(cudaMemcpyAsync(host, dev, head, cudaMemcpyDeviceToHost, c));
     }
-    rc = env_solve_mpc(h, s);
-    if (rc) return rc;
-    DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));
-    DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_front, 0));
-    DRE_CUDA_TRY(d2h(h->out.mpc_actions, (size_t)n_mpc_actions(h->cfg) * sizeof(double), 0, E));
-    // chunking: whole CTAs per chunk
+    // crowd half BEFORE the MPC solve on this path: it produces 3/4 of the bytes, so its copies get the MPC solve's
+    // duration as additional cover (neither half reads the other's outputs; the merge only needs pt_step's)
     const int epb = dre_env_ha_envs_per_cta(D);
     int chunks = h->host_chunks < dre_env::MAX_CHUNKS ? h->host_chunks : dre_env::MAX_CHUNKS;
     if (chunks < 1) chunks = 1;
@@ -388,14 +385,17 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     D.chunk_flags = h->d_flags; D.chunk_count = h->d_chunk_count; D.chunk_envs = per; D.step_seq = h->step_seq;
     rc = dre_env_launch_ha(D, 0, 1, s);
     if (rc) return rc;
-    DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));
-    if (tr) { t_enq = now_us(); cudaEventSynchronize(h->ev_front); t_front = now_us(); }
+    DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));     // crowd half done
+    rc = env_solve_mpc(h, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));      // step done
+    if (tr) t_enq = now_us();
     volatile int *flags = h->h_flags;
     for (int i = 0; i < chunks; ++i) {
         const int e0 = i * per, e1 = e0 + per < E ? e0 + per : E;
         for (unsigned spin = 0; flags[i] != h->step_seq; ++spin) {
             if ((spin & 0x3ff) == 0x3ff) {   // the launch may have failed or finished without us seeing the flag yet
-                const cudaError_t q = cudaEventQuery(h->ev_done);
+                const cudaError_t q = cudaEventQuery(h->ev_front);
                 if (q == cudaSuccess) { if (flags[i] != h->step_seq) { h->h_flags[i] = h->step_seq; } break; }
                 if (q != cudaErrorNotReady) { dre_set_cuda_error(q, __FILE__, __LINE__); return DRE_ERR_CUDA; }
             }
@@ -415,10 +415,17 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
         DRE_CUDA_TRY(cudaMemcpyAsync(host + a0, dev + a0, a1 - a0, cudaMemcpyDeviceToHost, c));
         DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
     }
-    // rewards, info, done bits, MPC status, done flags (one run, ~130 B per env) once the launch is complete
+    // rewards, info, done bits once the crowd half is complete; MPC actions, MPC status and the done flags (which sit
+    // behind the status in the slab) once the solve is
+    DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_front, 0));
+    {
+        const size_t b0 = (const char *)h->out.rewards - dev, b1 = (const char *)h->out.mpc_status - dev;
+        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
+    }
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_done, 0));
     {
-        const size_t b0 = (const char *)h->out.rewards - dev, b1 = h->slab_bytes;
+        const size_t b0 = (const char *)h->out.mpc_status - dev, b1 = h->slab_bytes;
+        DRE_CUDA_TRY(d2h(h->out.mpc_actions, (size_t)n_mpc_actions(h->cfg) * sizeof(double), 0, E));
         DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
     }
     if (tr) {
@@ -426,9 +433,10 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
         const double t_done = now_us();
         cudaStreamSynchronize(c);
         const double t_end = now_us();
-        fprintf(stderr, "[host trace] enqueued %.0f us, front (pt+mpc) done %.0f, chunk flags at", t_enq - t_start, t_front - t_start);
+        (void)t_front;
+        fprintf(stderr, "[host trace] enqueued %.0f us, chunk flags at", t_enq - t_start);
         for (int i = 0; i < chunks; ++i) fprintf(stderr, " %.0f", t_flag[i] - t_start);
-        fprintf(stderr, ", crowd half done %.0f, copies done %.0f us\n", t_done - t_start, t_end - t_start);
+        fprintf(stderr, ", step (crowd half, then MPC) done %.0f, copies done %.0f us\n", t_done - t_start, t_end - t_start);
     }
     DRE_CUDA_TRY(cudaStreamSynchronize(c));
     return DRE_OK;

@@ -1,9 +1,9 @@
 // env_kernels.cu -- the batched env step around the ORCA pass and the MPC solve.
 // Compile with -fmad=false (bit-faithful fp32 ORCA, once-rounded fp64 env arithmetic).
 //
-// One env step = pt_step_kernel -> MPC solve -> ha_step_kernel. The robot's motion depends only on the action, so the
-// robot/path half of the step (and the MPC solve, which needs nothing but the new robot pose) runs FIRST: its outputs
-// can already travel to the host while the crowd half, which produces 3/4 of the output bytes, is still computing.
+// One env step = pt_step_kernel -> ha_step_kernel -> MPC solve. The robot's motion depends only on the action, so the
+// robot/path half runs FIRST; the crowd half and the MPC solve both depend on nothing but it. The crowd half, which
+// produces 3/4 of the output bytes, goes next so that on the host path its observations travel while the solve runs.
 //
 //   pt_step_kernel : robot unicycle step (agent.py:169-176) + PTEnv.step (path_tracking_env.py:80-101): 5 intermediate
 //                    poses, 2 localisations, PT rewards (reward_comp.py:20-116), optional path switch

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--horizon", type=int, default=4)
     ap.add_argument("--cpu-envs", type=int, default=4096, help="envs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dedup", action="store_true", help="skip the separately reported orca_dedup variant")
     return ap.parse_args()
 
 
@@ -300,6 +301,35 @@ def run_ours(a):
                                 "instruction issue (ha_step) and by the fp64 pipe's 2-cycle warp-instruction cadence (mpc_solve); "
                                 "ncu_issue_slots holds the issue-slot utilisation of the committed ncu capture"}
 
+    # ---------------- de-duplicated variant, reported separately: the look-ahead ORCA pass of step t IS the
+    # movement pass of step t+1 unless a goal was resampled in between; bit-identical results, one pass per step ----------------
+    dedup = None
+    if not a.no_dedup:
+        env2 = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, horizon=K, env_id_offset=rank * E, orca_dedup=True), num_envs=E, device=dev)
+        env2.reset()
+        act2 = env2.out["mpc_actions"][:, :2].clone()
+        tk = [0]
+
+        def step2():
+            torch.add(env2.out["mpc_actions"][:, :2], noise[tk[0] % 64], out=act2)
+            torch.clamp(act2, lo, hi, out=act2)
+            tk[0] += 1
+            env2.step(act2)
+
+        for _ in range(max(a.warmup, 3)):
+            step2(); flush.zero_()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        barrier()
+        for s0, s1 in ev2:
+            s0.record(); step2(); s1.record()
+            flush.zero_()
+        barrier()
+        ms2 = max_over_ranks(sum(s0.elapsed_time(s1) for s0, s1 in ev2))
+        dedup = {"value": world * E * a.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / a.steps,
+                 "what": "EngineConfig(orca_dedup=True): same steps, same policy, same results bit for bit (tests/test_gpu_env.py::"
+                         "test_orca_dedup_is_bit_identical); NOT the headline, which keeps the reference's two ORCA passes per step"}
+        del env2
+
     # ---------------- end to end through the host-buffer C-ABI call (closed loop through host memory) ----------------
     noise_h = noise[:8].cpu().numpy()
     a_host = torch.empty((E, 2), dtype=torch.float64).pin_memory().numpy()
@@ -335,7 +365,7 @@ def run_ours(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 ORCA + f64 MPC/env", "data": "synthetic", "config": workload_config(a), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "roofline": roofline, "roofline_compute": roofline_compute,
-                "kernels_ms": kavg, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
+                "kernels_ms": kavg, "dedup_variant": dedup, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
                 "episode_stats": {n: int(cnt[i]) for i, n in enumerate(d.env.STAT_NAMES)}, "reward_sums": [float(x) for x in sums[:3]]}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -63,6 +63,7 @@ class EngineConfig:
     lookbehind: int = 5
     auto_path_switch: bool = True
     soft_reset_on_device: bool = False   # run HAAndPTEnv.soft_reset as a per-env state machine inside step()
+    orca_dedup: bool = False             # reuse step t's look-ahead ORCA pass as step t+1's movement pass (bit-identical)
     seed: int = 0x00D24D9C
     env_id_offset: int = 0
 
@@ -117,4 +118,4 @@ class EngineConfig:
             self.path_advancement_scaling, self.deviation_xy, self.deviation_th, self.deviation_scale,
             self.corridor_penalty, self.corridor_max_dev, self.end_of_path_penalty, self.safety_corridor_penalty,
             self.safety_corridor_max_dev, self.lookahead, self.lookbehind, self.actions_in_input,
-            int(self.auto_path_switch), int(self.soft_reset_on_device), self.seed, self.env_id_offset)
+            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), self.seed, self.env_id_offset)

@@ -90,6 +90,9 @@ void carve_state(EnvDev &D, void *base, size_t &bytes)
     D.reset_epoch = c.take<int32_t>(E);
     D.mpc_interp = c.take<double>(E);
     D.sr_state = c.take<int32_t>(E * 4);
+    D.hvel_next = c.take<float2>(E * Nh);
+    D.goal_changed = c.take<uint8_t>(E * Nh);
+    D.cache_valid = c.take<uint8_t>(E);
     D.stat_counters = c.take<unsigned long long>(16);
     D.stat_sums = c.take<double>(4);
     bytes = (c.off + 255) / 256 * 256;
@@ -151,7 +154,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     D.corridor_max_dev = cfg->corridor_max_dev; D.eop_penalty = cfg->end_of_path_penalty;
     D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
     D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
-    D.soft_reset = cfg->soft_reset_on_device;
+    D.soft_reset = cfg->soft_reset_on_device; D.orca_dedup = cfg->orca_dedup;
     D.seed = cfg->seed; D.env_id_offset = cfg->env_id_offset;
 
     int rc = dre_mpc_create(&cfg->mpc, cfg->num_envs, &h->mpc);
@@ -446,6 +449,13 @@ extern "C" int dre_env_set_host_chunks(dre_env *h, int32_t chunks)
 {
     if (!h || chunks < 1 || chunks > dre_env::MAX_CHUNKS) return DRE_ERR_INVALID;
     h->host_chunks = chunks;
+    return DRE_OK;
+}
+
+extern "C" int dre_env_invalidate_orca_cache(dre_env *h, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    DRE_CUDA_TRY(cudaMemsetAsync(h->D.cache_valid, 0, (size_t)h->D.E, (cudaStream_t)stream));
     return DRE_OK;
 }
 

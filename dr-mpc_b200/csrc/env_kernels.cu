@@ -46,10 +46,10 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     return l;
 }
 
-template <int G>
+template <int G, bool REUSE>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
-                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter)
+                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
@@ -67,7 +67,11 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
         if (e >= D.E) continue;
         const size_t gidx = (size_t)e * Nh + i;
         float ox = 0.f, oy = 0.f;
-        if (!D.hstatic[gidx]) {
+        if (REUSE && reuse && D.cache_valid[e] && !D.goal_changed[gidx]) {
+            // orca_dedup: this solve was done as the look-ahead pass of the previous step, on this very state
+            const float2 c = D.hvel_next[gidx];
+            ox = c.x; oy = c.y;
+        } else if (!D.hstatic[gidx]) {
             const double2 P = pos_from_smem ? posd[el * Nh + i] : D.hpos[gidx];
             const double2 Gl = D.hgoal[gidx];
             const double dx = Gl.x - P.x, dy = Gl.y - P.y;
@@ -86,8 +90,27 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
     }
 }
 
+// -DDRE_HA_TRACE: thread 0 of every CTA adds the cycles it spent in each phase to stat_counters[12..15] + stat_sums
+// (measurement builds only; see tools/probe_ha_trace.py)
+#if defined(DRE_HA_TRACE)
+#define DRE_HA_T(slot) do { if (threadIdx.x == 0 && D.stat_counters && mode == 0) { const long long _n = clock64(); \
+        atomicAdd(D.stat_counters + (slot), (unsigned long long)(_n - tr_t)); tr_t = _n; } } while (0)
+#else
+#define DRE_HA_T(slot) do { } while (0)
+#endif
+#if defined(DRE_HA_TRACE) && DRE_HA_TRACE == 2   // second level: split the last phase instead
+#define DRE_HA_T2(slot) do { if (threadIdx.x == 0 && D.stat_counters && mode == 0) { const long long _n = clock64(); \
+        atomicAdd(D.stat_counters + (slot), (unsigned long long)(_n - tr_t)); tr_t = _n; } } while (0)
+#undef DRE_HA_T
+#define DRE_HA_T(slot) do { if (threadIdx.x == 0) tr_t = clock64(); } while (0)
+#else
+#define DRE_HA_T2(slot) do { } while (0)
+#endif
+
 // mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
-template <int G>
+// DEDUP: the orca_dedup variant (reuses the previous step's look-ahead pass); a separate instantiation so that the default
+// two-pass kernel carries none of its code
+template <int G, bool DEDUP>
 __global__ void __launch_bounds__(512)
 ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_obs, const __grid_constant__ HaLayout lay)
 {
@@ -109,6 +132,9 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     cg::thread_block blk = cg::this_thread_block();
     TileGroup<G> g(cg::tiled_partition<G>(blk));
     const int gi = threadIdx.x / G;
+#ifdef DRE_HA_TRACE
+    long long tr_t = clock64();
+#endif
 
     if (mode != 2) {
         // ---- stage tile ----
@@ -135,10 +161,13 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         __syncthreads();
 
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
-        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
-                          D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4]);
+        // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
+        // instruction cache together)
+        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
+                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0);
         __syncthreads();
 
+        DRE_HA_T(12);   // stage + pass 1
         // ---- integrate: robot (unicycle, agent.py:169-176) and humans (Euler, agent.py:164-168); histories ----
         for (int t = threadIdx.x; t < EPB * (Nh + 1); t += blockDim.x) {
             const int el = t / (Nh + 1), a = t - el * (Nh + 1), e = env0 + el;
@@ -255,12 +284,26 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
     }
 
+    DRE_HA_T(13);       // integrate + observation + chunk flag
     if (mode == 0) {
         // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
-        orca_pass_tile<G>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1]);
+#ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
+        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false);
+#endif
         __syncthreads();
+        if (DEDUP) {   // keep the look-ahead velocities: they are the next step's movement pass
+            for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+                const int el = t / Nh, i = t - el * Nh, e = env0 + el;
+                if (e >= D.E) continue;
+                D.hvel_next[(size_t)e * Nh + i] = vnext[el * Nh + i];
+                D.goal_changed[(size_t)e * Nh + i] = 0;
+            }
+            for (int el = threadIdx.x; el < EPB; el += blockDim.x)
+                if (env0 + el < D.E) D.cache_valid[env0 + el] = 1;
+        }
 
+        DRE_HA_T(14);   // pass 2
         // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int el = t / Nh, i = t - el * Nh, e = env0 + el;
@@ -286,6 +329,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
             pen[(el * Nh + i) * 3] = pv_; pen[(el * Nh + i) * 3 + 1] = pth_; pen[(el * Nh + i) * 3 + 2] = closest;
         }
         __syncthreads();
+        DRE_HA_T2(12);  // per-human reward terms
 
         // ---- per-env reward / done (one thread per env sums in human order, like the reference loop) ----
         for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
@@ -346,6 +390,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
     }
 
+    DRE_HA_T2(13);      // per-env merge + statistics
     // ---- goal resampling for humans that reached their goal (human_avoidance_env.py:181-184 / :109-112) ----
     if (mode != 2 && D.end_goal_changing) {
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
@@ -356,6 +401,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
             if (sqrt(dx * dx + dy * dy) < D.human_radius) atomicOr(&flags[el * 4], 1);
         }
         __syncthreads();
+        DRE_HA_T2(14);  // goal-reached detection
         for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
             const int e = env0 + el;
             if (e >= D.E || !flags[el * 4]) continue;
@@ -394,9 +440,16 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
                     if (!collide) break;
                 }
                 D.hgoal[(size_t)e * Nh + i] = make_double2(gx, gy);
+                if (DEDUP) D.goal_changed[(size_t)e * Nh + i] = 1;
             }
         }
     }
+    DRE_HA_T(15);       // rewards + merge + goal resampling
+    DRE_HA_T2(15);      // goal resampling
+    // a warm-start step moves the crowd without a look-ahead pass: whatever was cached is stale
+    if (DEDUP && mode == 1)
+        for (int el = threadIdx.x; el < EPB; el += blockDim.x)
+            if (env0 + el < D.E) D.cache_valid[env0 + el] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -543,6 +596,7 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
     D.mpc_iteration0[e] = 1;
     for (int i = 0; i < 4; ++i) { D.sr_state[(size_t)e * 4 + i] = 0; reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 16)[i] = 0u; }
     D.out.done_bits[e] = 0u;
+    D.cache_valid[e] = 0;
     const uint64_t gid = (uint64_t)(D.env_id_offset + e);
     const uint64_t stp = ((uint64_t)D.reset_epoch[e] << 20) + (1ull << 18);
     for (int i = 0; i < Nh; ++i) {
@@ -702,7 +756,7 @@ int dre_env_ha_envs_per_cta(const EnvDev &D)
     return EPB < 1 ? 1 : EPB;
 }
 
-template <int G>
+template <int G, bool DEDUP>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
@@ -712,7 +766,7 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
     const int threads = dre_ha_threads();
     const int EPB = dre_env_ha_envs_per_cta(D);
     const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
-    auto kern = ha_step_kernel<G>;
+    auto kern = ha_step_kernel<G, DEDUP>;
     if (lay.bytes > 48 * 1024) {
         if (lay.bytes > 220 * 1024) return DRE_ERR_INVALID;
         DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
@@ -724,13 +778,16 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 
 int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
-    switch (dre_orca_pick_group(D.orca, D.Nh)) {
-    case 2: return launch_ha<2>(D, mode, write_obs, s);
-    case 4: return launch_ha<4>(D, mode, write_obs, s);
-    case 8: return launch_ha<8>(D, mode, write_obs, s);
-    case 16: return launch_ha<16>(D, mode, write_obs, s);
-    default: return launch_ha<32>(D, mode, write_obs, s);
+    const int G = dre_orca_pick_group(D.orca, D.Nh);
+#define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true>(D, mode, write_obs, s) : launch_ha<g, false>(D, mode, write_obs, s)
+    switch (G) {
+    DRE_HA_CASE(2);
+    DRE_HA_CASE(4);
+    DRE_HA_CASE(8);
+    DRE_HA_CASE(16);
+    default: return D.orca_dedup ? launch_ha<32, true>(D, mode, write_obs, s) : launch_ha<32, false>(D, mode, write_obs, s);
     }
+#undef DRE_HA_CASE
 }
 
 int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s)

@@ -22,7 +22,7 @@ struct EnvDev {
     double collision_penalty, safety_dist, safety_penalty, dist_radius, dist_factor_v, dist_factor_th, act_min_vel, act_penalty;
     double pt_overall_scaling, goal_radius, goal_angle, goal_reward, path_adv_scaling, dev_xy, dev_th, dev_scale;
     double corridor_penalty, corridor_max_dev, eop_penalty, safety_corridor_penalty, safety_corridor_max_dev;
-    int lookahead, lookbehind, auto_path_switch, soft_reset;
+    int lookahead, lookbehind, auto_path_switch, soft_reset, orca_dedup;
     uint64_t seed;
     int64_t env_id_offset;
     // ---- state (structure of arrays, env-major) ----
@@ -45,6 +45,9 @@ struct EnvDev {
     double *mpc_interp;     // [E]
     uint8_t *mpc_iteration0; // [E] (aliases the MPC object's flags)
     int32_t *sr_state;      // [E][4] soft-reset state machine
+    float2 *hvel_next;      // [E][Nh] orca_dedup: look-ahead velocities of the last step (= next step's movement pass)
+    uint8_t *goal_changed;  // [E][Nh] orca_dedup: goal resampled since hvel_next was computed
+    uint8_t *cache_valid;   // [E]     orca_dedup: hvel_next belongs to the current state
     // ---- paths ----
     const double *paths;
     const int32_t *lens;

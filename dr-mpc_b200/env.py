@@ -196,6 +196,10 @@ class BatchedHAAndPTEnv:
             d['candidate_safe'] = cand
         return out, d
 
+    def invalidate_orca_cache(self):
+        """orca_dedup: call after writing human / robot state through `self.state` (the cached look-ahead is then stale)."""
+        _lib.check(self._L.dre_env_invalidate_orca_cache(self._h, self._stream()))
+
     def set_host_chunks(self, chunks):
         """Number of env chunks step_host pipelines the crowd half and its D2H copies in (1 = no pipelining)."""
         _lib.check(self._L.dre_env_set_host_chunks(self._h, int(chunks)))

@@ -146,6 +146,12 @@ typedef struct dre_env_config {
                                                     the scripted one (wait / back up / turn to the path) instead of the
                                                     caller's, and the transition is flagged (done_flags[12]) so the caller
                                                     keeps it out of the replay buffer. Needs auto_path_switch = 1.   */
+    int32_t orca_dedup;                          /* 1: reuse the look-ahead ORCA pass of step t (human_avoidance_env.py:245) as
+                                                    the movement pass of step t+1 (:129). The two are the same computation
+                                                    on the same state unless a human's goal was resampled in between
+                                                    (:181-184); those humans are solved again. Bit-identical results, one
+                                                    ORCA pass per step instead of two. Writers of the state views must call
+                                                    dre_env_invalidate_orca_cache(). Default 0 = two passes like the reference */
     uint64_t seed;                               /* Philox key for device-side spawning / goal resampling */
     int64_t env_id_offset;                       /* global id of env 0 of this shard (multi-GPU)         */
 } dre_env_config;
@@ -218,6 +224,8 @@ int dre_env_step(dre_env *h, const double *actions, void *stream);
 int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
 /* number of env chunks whose observation copies dre_env_step_host overlaps with the crowd half (1..32, default 8) */
 int dre_env_set_host_chunks(dre_env *h, int32_t chunks);
+/* orca_dedup: forget the cached look-ahead velocities (call after writing human / robot state through dre_env_state) */
+int dre_env_invalidate_orca_cache(dre_env *h, void *stream);
 /* regenerate observations only (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148) */
 int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
 /*

@@ -177,3 +177,34 @@ def test_step_host_pipeline_equals_device_step(chunks):
         for name in ("hpos", "hvel", "hgoal", "rpose", "hhist"):
             assert torch.equal(a_env.state[name], b_env.state[name]), (t, name)
         act = a_env.out["mpc_actions"][:, :2].clone()
+
+
+def test_orca_dedup_is_bit_identical():
+    """orca_dedup reuses step t's look-ahead ORCA pass (human_avoidance_env.py:245) as step t+1's movement pass (:129),
+    re-solving only humans whose goal was resampled in between (:181-184): every state array and every output of a
+    free-running batch must equal the two-pass engine's bit for bit, across goal resamplings, path switches and a reset."""
+    import torch
+    import dr_mpc_b200 as d
+    E, Nh = 2048, 10
+    a_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E)
+    b_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, orca_dedup=True), num_envs=E)
+    resampled = 0
+    for episode in range(2):
+        Sa = a_env.reset(); Sb = b_env.reset()
+        for t in range(70):
+            act = Sa['PT']['MPC_actions'][:, :2].clone()
+            g0 = a_env.state["hgoal"].clone()
+            Sa, *_ = a_env.step(act)
+            Sb, *_ = b_env.step(act)
+            resampled += int((a_env.state["hgoal"] != g0).any(-1).sum())
+            for k in a_env.out:
+                assert torch.equal(a_env.out[k], b_env.out[k]), (episode, t, k)
+            for k in ("hpos", "hvel", "hgoal", "hhist", "rpose", "path_idx"):
+                assert torch.equal(a_env.state[k], b_env.state[k]), (episode, t, k)
+    assert resampled > 100
+    # a writer of the state views has to invalidate the cache
+    b_env.state["hpos"].add_(0.125); a_env.state["hpos"].add_(0.125)
+    b_env.invalidate_orca_cache()
+    act = Sa['PT']['MPC_actions'][:, :2].clone()
+    a_env.step(act); b_env.step(act)
+    assert torch.equal(a_env.state["hvel"], b_env.state["hvel"]) and torch.equal(a_env.out["rewards"], b_env.out["rewards"])

@@ -8,7 +8,7 @@ dev = "cuda:0"
 tag = sys.argv[1] if len(sys.argv) > 1 else "base"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 E, Nh = int(os.environ.get("PROBE_E", 16384)), int(os.environ.get("PROBE_NH", 20))
-env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, group_lanes=int(os.environ.get("PROBE_G", 0))), num_envs=E)
+env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, group_lanes=int(os.environ.get("PROBE_G", 0)), orca_dedup=bool(int(os.environ.get("PROBE_DEDUP", 0)))), num_envs=E)
 S = env.reset()
 gen = torch.Generator(device=dev).manual_seed(1234)
 noise = torch.randn((64, E, 2), generator=gen, device=dev, dtype=torch.float64) * torch.tensor([0.1, 0.2], device=dev, dtype=torch.float64)

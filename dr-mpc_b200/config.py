@@ -2,6 +2,7 @@
 config_HA.py:27-36,40-56,59-77,100-106, config_PT.py:7-22,38-39,48-50); `from_config_master` reads the
 same attribute bags the reference's env classes read, so an unmodified ConfigMaster() can be passed."""
 from dataclasses import dataclass, field
+import ctypes
 from . import _lib
 
 
@@ -64,6 +65,7 @@ class EngineConfig:
     auto_path_switch: bool = True
     soft_reset_on_device: bool = False   # run HAAndPTEnv.soft_reset as a per-env state machine inside step()
     orca_dedup: bool = False             # reuse step t's look-ahead ORCA pass as step t+1's movement pass (bit-identical)
+    static_humans: tuple = ()            # ((x, y), ...) static obstacles = the LAST len(static_humans) of num_humans
     seed: int = 0x00D24D9C
     env_id_offset: int = 0
 
@@ -93,6 +95,12 @@ class EngineConfig:
             safety_corridor_max_dev=pp['safety_corridor_raise']['max_deviation'],
             lookahead=pt.PT_model_params['MLP_local'].lookahead, lookbehind=pt.PT_model_params['MLP_local'].lookbehind,
         )
+        # continuous task with static humans on: two hard-coded obstacles appended after the dynamic humans
+        # (crowd_sim.py:156-158,171-183; config_HA.py:46)
+        st = getattr(ha.sim, "include_static_humans", None)
+        if st and st.get('episode_probability', 0) > 0 and getattr(g.env, "continuous_task", True):
+            c.static_humans = ((-4.0, 0.0), (0.0, 0.0))
+            c.num_humans += 2
         for k, v in overrides.items():
             setattr(c, k, v)
         return c
@@ -118,4 +126,6 @@ class EngineConfig:
             self.path_advancement_scaling, self.deviation_xy, self.deviation_th, self.deviation_scale,
             self.corridor_penalty, self.corridor_max_dev, self.end_of_path_penalty, self.safety_corridor_penalty,
             self.safety_corridor_max_dev, self.lookahead, self.lookbehind, self.actions_in_input,
-            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), self.seed, self.env_id_offset)
+            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), len(self.static_humans),
+            (ctypes.c_double * 8)(*([float(v) for xy in self.static_humans for v in xy] + [0.0] * (8 - 2 * len(self.static_humans)))),
+            self.seed, self.env_id_offset)

@@ -135,6 +135,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
         return DRE_ERR_INVALID;
     if (cfg->lookahead + cfg->lookbehind <= 0 || !(cfg->time_step > 0)) return DRE_ERR_INVALID;
     if (cfg->soft_reset_on_device && !cfg->auto_path_switch) return DRE_ERR_INVALID;
+    if (cfg->num_static_humans < 0 || cfg->num_static_humans > 4 || cfg->num_static_humans >= cfg->num_humans) return DRE_ERR_INVALID;
     dre_env *h = new (std::nothrow) dre_env();
     if (!h) return DRE_ERR_NOMEM;
     h->cfg = *cfg;
@@ -155,6 +156,8 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
     D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
     D.soft_reset = cfg->soft_reset_on_device; D.orca_dedup = cfg->orca_dedup;
+    D.num_static = cfg->num_static_humans;
+    for (int i = 0; i < 8; ++i) D.static_pos[i] = cfg->static_pos[i];
     D.seed = cfg->seed; D.env_id_offset = cfg->env_id_offset;
 
     int rc = dre_mpc_create(&cfg->mpc, cfg->num_envs, &h->mpc);

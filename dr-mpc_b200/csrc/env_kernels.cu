@@ -602,7 +602,10 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
     for (int i = 0; i < Nh; ++i) {
         const size_t gidx = (size_t)e * Nh + i;
         double px, py, gx, gy;
-        if (hpos_init) {
+        const int si = i - (Nh - D.num_static);   // >= 0: static human (generate_static_humans, crowd_sim.py:171-183)
+        if (si >= 0 && !hpos_init) {
+            px = D.static_pos[2 * si]; py = D.static_pos[2 * si + 1]; gx = 0.0; gy = 0.0;   // human.set(px, py, 0, 0, ...)
+        } else if (hpos_init) {
             px = hpos_init[gidx].x; py = hpos_init[gidx].y;
             gx = hgoal_init ? hgoal_init[gidx].x : -px; gy = hgoal_init ? hgoal_init[gidx].y : -py;
         } else {
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
                     const double a = px - rx, b = py - ry;
                     if (sqrt(a * a + b * b) < D.human_radius + D.robot_radius + 0.5) collide = true;
                 }
-                for (int j = 0; j < i && !collide; ++j) {
+                for (int j = 0; j < i && !collide; ++j) {   // earlier (dynamic) humans; statics are appended afterwards
                     const double2 q = D.hpos[(size_t)e * Nh + j];
                     const double a = px - q.x, b = py - q.y;
                     if (sqrt(a * a + b * b) < D.human_radius + D.human_radius + 0.2) collide = true;
@@ -633,6 +636,7 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
         D.hpos[gidx] = make_double2(px, py);
         D.hgoal[gidx] = make_double2(gx, gy);
         D.hvel[gidx] = make_float2(0.f, 0.f);
+        D.hstatic[gidx] = si >= 0 ? 1 : 0;
         D.hvalid[gidx] = 1;
         for (int s = 0; s < H; ++s) D.hhist[gidx * H + s] = make_double2(px, py);
     }

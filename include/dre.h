@@ -152,6 +152,11 @@ typedef struct dre_env_config {
                                                     (:181-184); those humans are solved again. Bit-identical results, one
                                                     ORCA pass per step instead of two. Writers of the state views must call
                                                     dre_env_invalidate_orca_cache(). Default 0 = two passes like the reference */
+    int32_t num_static_humans;                   /* the LAST num_static_humans of num_humans are static obstacles (isObstacle,
+                                                    crowd_sim.py:171-183, 270-272): placed at static_pos by reset(), zero
+                                                    action, no goal resampling, no disturbance term. 0..4                */
+    double static_pos[8];                        /* (x, y) per static human; the reference's continuous task hard-codes
+                                                    (-4, 0) and (0, 0) when include_static_humans is on (crowd_sim.py:173-183) */
     uint64_t seed;                               /* Philox key for device-side spawning / goal resampling */
     int64_t env_id_offset;                       /* global id of env 0 of this shard (multi-GPU)         */
 } dre_env_config;

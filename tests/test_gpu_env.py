@@ -208,3 +208,25 @@ def test_orca_dedup_is_bit_identical():
     act = Sa['PT']['MPC_actions'][:, :2].clone()
     a_env.step(act); b_env.step(act)
     assert torch.equal(a_env.state["hvel"], b_env.state["hvel"]) and torch.equal(a_env.out["rewards"], b_env.out["rewards"])
+
+
+def test_static_humans_spawn_and_stay():
+    """include_static_humans (crowd_sim.py:171-183): the last humans of every env are obstacles at the configured spots:
+    zero action, never resampled, still seen by the other humans' ORCA and by the collision / safety tests."""
+    import torch
+    import dr_mpc_b200 as d
+    E, Nh = 512, 8
+    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, static_humans=((-4.0, 0.0), (0.0, 0.0))), num_envs=E)
+    S = env.reset()
+    st = env.state
+    assert (st["hstatic"][:, :Nh - 2] == 0).all() and (st["hstatic"][:, Nh - 2:] == 1).all()
+    spots = torch.tensor([[-4.0, 0.0], [0.0, 0.0]], dtype=torch.float64, device=env.device)
+    assert torch.equal(st["hpos"][:, Nh - 2:], spots.expand(E, 2, 2))
+    hit = torch.zeros(E, dtype=torch.bool, device=env.device)
+    for t in range(60):
+        S, R, D, info, eps = env.step(S['PT']['MPC_actions'][:, :2].clone())
+        hit |= eps['safety_human_raise'] | eps['collision']
+        assert torch.equal(st["hpos"][:, Nh - 2:], spots.expand(E, 2, 2)) and (st["hvel"][:, Nh - 2:] == 0).all()
+    assert (st["hvel"][:, :Nh - 2].abs().sum(-1) > 0).any()
+    # the circular path passes through (-4, 0): the MPC-driven robot runs into the parked human's safety range
+    assert hit.float().mean() > 0.9

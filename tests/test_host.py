@@ -91,6 +91,13 @@ def test_engine_config_reads_reference_config_objects():
     assert c == d.EngineConfig(num_humans=7, num_envs=128)             # the defaults ARE the reference's values
     e = c.env_config()
     assert abs(e.orca.radius - 0.485) < 1e-7 and e.mpc.horizon == 4 and e.safety_corridor_max_dev == 1.4
+    assert e.num_static_humans == 0 and e.soft_reset_on_device == 0 and e.orca_dedup == 0
+    # include_static_humans on (config_HA.py:46): the continuous task parks two obstacles after the dynamic humans
+    cm.config_HA.sim.include_static_humans = {'episode_probability': 1, 'max_static_humans': 2}
+    cm.config_general.env.continuous_task = True
+    c2 = d.EngineConfig.from_config_master(cm, num_envs=128)
+    e2 = c2.env_config()
+    assert c2.num_humans == 9 and e2.num_static_humans == 2 and list(e2.static_pos)[:4] == [-4.0, 0.0, 0.0, 0.0]
 
 
 def test_device_mpc_header_on_host_matches_oracle(oracle, golden_mpc):

@@ -6,9 +6,10 @@ from .orca import BatchedORCA
 from .mpc import BatchedMPC
 from . import paths
 from . import parallel
+from .replay import BatchedReplayBuffer
 try:
     from .env import BatchedHAAndPTEnv
 except ImportError:   # env module not present in minimal builds
     pass
 
-__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "paths", "parallel"]
+__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "BatchedReplayBuffer", "paths", "parallel"]

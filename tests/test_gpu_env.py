@@ -230,3 +230,28 @@ def test_static_humans_spawn_and_stay():
     assert (st["hvel"][:, :Nh - 2].abs().sum(-1) > 0).any()
     # the circular path passes through (-4, 0): the MPC-driven robot runs into the parked human's safety range
     assert hit.float().mean() > 0.9
+
+
+def test_training_loop_skeleton_with_replay_soft_reset_and_cvmm():
+    """The reference's data-collection loop (online_continuous_task.py:139-189) on a batch: safety filter on the policy's
+    action, step with the soft-reset machine on, replay insert of the non-scripted transitions straight from the slab."""
+    import torch
+    import dr_mpc_b200 as d
+    E = 1024
+    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=6, soft_reset_on_device=True), num_envs=E)
+    S = env.reset()
+    rb = d.BatchedReplayBuffer(S, buffer_size=20000)
+    clone = lambda S: {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in S.items()}
+    kept = 0
+    for t in range(40):
+        S_prev = clone(S)                                        # the slab is overwritten by step()
+        a = S['PT']['MPC_actions'][:, :2].clone()
+        a[:, 1] += 0.3 * torch.sin(torch.arange(E, device=env.device) + t)   # a sloppy policy
+        a[:, 1].clamp_(-1, 1)
+        a_safe, cinfo = env.cvmm_diverse_safety_pipeline(a)
+        S, R, D, info, eps = env.step(a_safe)
+        kept += rb.insert(S_prev, info['actions_used'], S, R['R'], D['done_for_replay'], mask=~info['soft_reset'])
+    assert 0 < kept <= 40 * E and rb.valid_entries == min(kept, 20000)
+    Sb, Ab, Spb, Rb, Db = rb.sample_from_buffer(256)
+    assert Sb['HA']['spatial_edges'].shape == (256, 6, 14) and Sb['PT']['PT_state'].shape == (256, 100)
+    assert torch.isfinite(Rb).all() and Ab.shape == (256, 2) and Sb['PT']['PT_state'].is_cuda

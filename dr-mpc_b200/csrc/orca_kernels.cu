@@ -4,6 +4,7 @@
 // Grid: one CTA per EPB consecutive envs. The CTA stages its envs' agents (humans + robot) in shared
 // memory as an fp32 structure-of-arrays tile (the fp64 -> fp32 cast is the Cython boundary of the
 // reference), then every lane-group of G lanes solves one human's LP against the tile.
+#include <cstdlib>
 #include "orca_device.cuh"
 #include "launch.cuh"
 
@@ -102,8 +103,17 @@ template <int G>
 static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
                        const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
 {
-    const int threads = 256, NGl = threads / G;
-    int EPB = (5 * NGl) / Nh;
+    // same CTA shape as the fused env kernel (env_kernels.cu: launch_ha): 128 threads, ~8 agents per lane-group;
+    // DRE_ORCA_THREADS / DRE_ORCA_AGENTS_PER_GROUP override it for A/B measurements
+    static int threads = 0, apg = 0;
+    if (threads == 0) {
+        const char *e = getenv("DRE_ORCA_THREADS"); threads = e ? atoi(e) : 128;
+        if (threads != 64 && threads != 128 && threads != 256 && threads != 512) threads = 128;
+        e = getenv("DRE_ORCA_AGENTS_PER_GROUP"); apg = e ? atoi(e) : 8;
+        if (apg < 1 || apg > 64) apg = 8;
+    }
+    const int NGl = threads / G;
+    int EPB = (apg * NGl) / Nh;
     if (EPB > (E + 591) / 592) EPB = (E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     if (EPB < 1) EPB = 1;
     const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);

@@ -125,14 +125,15 @@ def test_auto_path_switch_follows_soft_reset(golden_env):
     assert (st["path_idx"] == (g[f"{tag}_pre_path_idx"][idx] + 1) % 4).all()
 
 
-def test_free_running_full_size_invariants():
-    """C3 size, 30 free-running steps with the MPC action as policy: finite outputs, speed bounds, consistent
-    done bits, episode statistics add up, and the run is deterministic."""
+@pytest.mark.parametrize("E,Nh,K", [(16384, 20, 4), (2048, 50, 4), (100, 1, 4), (512, 6, 10), (37, 63, 1)])
+def test_free_running_full_size_invariants(E, Nh, K):
+    """C3 size (and the C4 crowd, a single human, a long horizon, the largest crowd): 30 free-running steps with the MPC
+    action as policy: finite outputs, speed bounds, consistent done bits, episode statistics add up, deterministic."""
     import torch
     import dr_mpc_b200 as d
     runs = []
     for rep in range(2):
-        env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=20), num_envs=16384)
+        env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, horizon=K), num_envs=E)
         S = env.reset()
         env.stats(reset=True)
         tot_done = 0
@@ -146,10 +147,11 @@ def test_free_running_full_size_invariants():
                 assert torch.isfinite(v).all(), k
         assert (env.state["hvel"].double().norm(dim=-1) <= 1.01).all()
         a = env.out["mpc_actions"]
+        assert a.shape == (E, 2 * min(K, 4))
         assert (a[:, 0::2] > 0).all() and (a[:, 0::2] < 1).all() and (a[:, 1::2].abs() < 1).all()
         c, s = env.stats()
         c = c.cpu().numpy()
-        assert c[0] == 16384 * 30
+        assert c[0] == E * 30
         bits = env.out["done_bits"]
         assert (((bits & 0xFF) != 0) == ((bits & (1 << 18)) != 0)).all()
         runs.append((env.state["hpos"].clone(), env.out["rewards"].clone(), c.copy()))

@@ -23,6 +23,9 @@ struct dre_env {
     static const int MAX_CHUNKS = 32;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_front = nullptr, ev_pt = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_sync = nullptr; // orders step_host (own streams) after earlier device-path calls on the caller's stream
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_set = false;
     int *h_flags = nullptr;        // mapped pinned host memory [MAX_CHUNKS]
     int *d_flags = nullptr;        // its device alias
     int *d_chunk_count = nullptr;  // device [MAX_CHUNKS]
@@ -175,6 +178,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
         (e = cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_pt, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaHostAlloc((void **)&h->h_flags, dre_env::MAX_CHUNKS * sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
         (e = cudaHostGetDevicePointer((void **)&h->d_flags, h->h_flags, 0)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_chunk_count, dre_env::MAX_CHUNKS * sizeof(int))) != cudaSuccess ||
@@ -204,6 +208,7 @@ extern "C" int dre_env_destroy(dre_env *h)
     if (h->ev_front) cudaEventDestroy(h->ev_front);
     if (h->ev_pt) cudaEventDestroy(h->ev_pt);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->d_chunk_count);
     delete h;
@@ -255,6 +260,7 @@ extern "C" int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream)
     if (!h) return DRE_ERR_INVALID;
     if (!h->D.paths) return DRE_ERR_STATE;
     cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s; h->last_stream_set = true;
     int rc = dre_env_launch_ha(h->D, 2, 1, s);
     if (rc) return rc;
     rc = dre_env_launch_pt(h->D, 1, s);
@@ -267,6 +273,7 @@ extern "C" int dre_env_reset(dre_env *h, const double *hpos_init, const double *
     if (!h) return DRE_ERR_INVALID;
     if (!h->D.paths) return DRE_ERR_STATE;
     cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s; h->last_stream_set = true;
     int rc = dre_env_launch_reset(h->D, hpos_init, hgoal_init, s);
     if (rc) return rc;
     // S_PT = PT_env.reset(...) incl. the first MPC solve (HA_and_PT env.py:268)
@@ -288,6 +295,7 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     if (!h || !actions) return DRE_ERR_INVALID;
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
     cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s; h->last_stream_set = true;
     EnvDev D = h->D;
     D.actions = actions;
     // robot/path half, crowd half (which merges rewards / dones), MPC solve: see env_kernels.cu. The crowd half and the
@@ -363,6 +371,11 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_start = tr ? now_us() : 0.0;
     double t_flag[dre_env::MAX_CHUNKS] = {}, t_front = 0.0, t_enq = 0.0;
+    if (h->last_stream_set) {   // earlier reset() / step() / observe() calls ran on the caller's stream: run after them
+        DRE_CUDA_TRY(cudaEventRecord(h->ev_sync, h->last_stream));
+        DRE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_sync, 0));
+        h->last_stream_set = false;
+    }
     DRE_CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)E * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     EnvDev D = h->D;
     D.actions = h->d_actions;

@@ -225,7 +225,9 @@ dre_mpc *dre_env_mpc(dre_env *h);                     /* the env's MPC instance 
 int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream);
 /* step(): actions dev double[E][2] = ActionRot(v,w) per env; results in the output slab. */
 int dre_env_step(dre_env *h, const double *actions, void *stream);
-/* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab) */
+/* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab; pinned
+ * memory lets the copies overlap the kernels). Synchronous: returns when the whole slab has arrived. Runs on the handle's own
+ * streams, ordered after earlier reset() / step() / observe() calls whatever stream those were given. */
 int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
 /* number of env chunks whose observation copies dre_env_step_host overlaps with the crowd half (1..32, default 8) */
 int dre_env_set_host_chunks(dre_env *h, int32_t chunks);

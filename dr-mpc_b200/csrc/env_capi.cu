@@ -23,6 +23,10 @@ struct dre_env {
     static const int MAX_CHUNKS = 32;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_front = nullptr, ev_pt = nullptr, ev_done = nullptr;
+    // the MPC solve runs on its own stream next to the crowd half: both depend on pt_step only, and each has a long,
+    // thinly occupied tail (the solve's slow problems, the crowd half's last partial wave) the other one fills
+    cudaStream_t mpc_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_sync = nullptr; // orders step_host (own streams) after earlier device-path calls on the caller's stream
     cudaStream_t last_stream = nullptr;
     bool last_stream_set = false;
@@ -179,6 +183,9 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
         (e = cudaEventCreateWithFlags(&h->ev_pt, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->mpc_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaHostAlloc((void **)&h->h_flags, dre_env::MAX_CHUNKS * sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
         (e = cudaHostGetDevicePointer((void **)&h->d_flags, h->h_flags, 0)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_chunk_count, dre_env::MAX_CHUNKS * sizeof(int))) != cudaSuccess ||
@@ -209,6 +216,9 @@ extern "C" int dre_env_destroy(dre_env *h)
     if (h->ev_pt) cudaEventDestroy(h->ev_pt);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->mpc_stream) cudaStreamDestroy(h->mpc_stream);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->d_chunk_count);
     delete h;
@@ -301,11 +311,30 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     // robot/path half, crowd half (which merges rewards / dones), MPC solve: see env_kernels.cu. The crowd half and the
     // solve only depend on pt_step; the solve goes last so that, on the host path, the crowd's copies overlap it.
     if (!h->profiling) {
+        // measured at 16384 x 20 (mean of 300 steps): serial 1.14 ms, solve launched first 1.06 ms, crowd half first 1.04 ms
+        static const int overlap = getenv("DRE_STEP_OVERLAP") ? atoi(getenv("DRE_STEP_OVERLAP")) : 2;   // 0 serial, 1 MPC first, 2 crowd first
         int rc = dre_env_launch_pt(D, 0, s);
         if (rc) return rc;
-        rc = dre_env_launch_ha(D, 0, 1, s);
+        if (overlap == 0) {
+            rc = dre_env_launch_ha(D, 0, 1, s);
+            if (rc) return rc;
+            return env_solve_mpc(h, s);
+        }
+        DRE_CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+        DRE_CUDA_TRY(cudaStreamWaitEvent(h->mpc_stream, h->ev_fork, 0));
+        if (overlap == 1) {
+            rc = env_solve_mpc(h, h->mpc_stream);
+            if (rc) return rc;
+            rc = dre_env_launch_ha(D, 0, 1, s);
+        } else {
+            rc = dre_env_launch_ha(D, 0, 1, s);
+            if (rc) return rc;
+            rc = env_solve_mpc(h, h->mpc_stream);
+        }
         if (rc) return rc;
-        return env_solve_mpc(h, s);
+        DRE_CUDA_TRY(cudaEventRecord(h->ev_join, h->mpc_stream));
+        DRE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+        return DRE_OK;
     }
     if (h->ev_used == dre_env::PROF_RING) { const int rc = prof_drain(h); if (rc) return rc; }
     cudaEvent_t *ev = h->ev[h->ev_used];
@@ -405,6 +434,9 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     rc = dre_env_launch_ha(D, 0, 1, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));     // crowd half done
+    // The solve stays BEHIND the crowd half here, not next to it as in dre_env_step: this path is bound by the copies, and
+    // a solve that shares the SMs delays the chunk flags (measured p50 1.19 ms serial vs 1.27 ms concurrent, also with the
+    // solve on a lowest-priority stream: priorities do not stop its persistent CTAs from taking freed slots early).
     rc = env_solve_mpc(h, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));      // step done

@@ -18,6 +18,7 @@
  * PARITY UNPINNED w.r.t. the real pysteam/pylgmath (absent from this container).
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
@@ -436,6 +437,10 @@ static int mpc_optimize(mpc_prob *p, const mpc_params *P, mpc_stats *st)
                     const double actual = prev - proposed;
                     const double pred = mpc_predict(&S, K, d);
                     const double ratio = (pred == 0.0) ? 0.0 : actual / pred;
+#ifdef MPC_TRACE
+                    fprintf(stderr, "iter %d nb %d bt %d lambda %.1e scale %.3e prev %.9g proposed %.9g actual %.3e pred %.3e ratio %.4f\n",
+                            iter, nb, bt, lambda, scale, prev, proposed, actual, pred, ratio);
+#endif
                     if (ratio > 0.25) {
                         *p = trial;
                         lambda = fmax(lambda * 0.1, 1e-7);

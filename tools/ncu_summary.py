@@ -41,7 +41,7 @@ if os.path.exists(launches):
     step = {k: v for k, v in agg.items() if any(o in k for o in ("ha_step", "pt_step", "mpc_coop", "mpc_act", "mpc_stats"))}
     tot = sum(v[1] for v in step.values())
     with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 3 --warmup 3 --no-cpu-baseline)\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-dedup)\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write(f"{'kernel':50s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share_of_step_kernels':>22s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -66,7 +66,7 @@ if rep:
     traffic = {}
     issue = {}
     with open(os.path.join(out_dir, f"{tag}_kernels.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on  (python bench.py --steps 3 --warmup 3 --no-cpu-baseline)\n")
+        f.write("# ncu --set full --clock-control none --import-source on  (python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-dedup)\n")
         for r in rows[2:]:
             name = short(r[idx["Kernel Name"]])
             if name in seen:

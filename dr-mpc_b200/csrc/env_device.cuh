@@ -44,19 +44,24 @@ DRE_HD PathView path_view(const double *paths, int stride, int pid, const int32_
 
 struct Localization { double ix, iy, ith, index; };
 
-// PTEnvCore.localize_on_path (reference path_tracking_core.py:21-81) with strict=False; the k=2 KD-tree query is a
-// brute-force scan (paths have <= 125 nodes).
-DRE_HD Localization localize_on_path(const PathView &P, double qx, double qy, bool localize_to_start)
+// The k=2 KD-tree query of localize_on_path as a brute-force scan (paths have <= 125 nodes): the two nearest nodes,
+// ties resolved towards the lower index (lexicographic order on (distance^2, index)).
+DRE_HD void path_nearest_two(const PathView &P, double qx, double qy, int &i0, int &i1)
 {
-    const int L = P.L;
-    int i0 = 0, i1 = 1;
+    i0 = 0; i1 = 1;
     double d0 = INFINITY, d1 = INFINITY;
-    for (int i = 0; i < L; ++i) {
+    for (int i = 0; i < P.L; ++i) {
         const double dx = P.x[i] - qx, dy = P.y[i] - qy;
         const double d = dx * dx + dy * dy;
         if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = i; }
         else if (d < d1) { d1 = d; i1 = i; }
     }
+}
+
+// PTEnvCore.localize_on_path (reference path_tracking_core.py:21-81) with strict=False, given the two nearest nodes.
+DRE_HD Localization localize_from_nearest(const PathView &P, double qx, double qy, bool localize_to_start, int i0, int i1)
+{
+    const int L = P.L;
     Localization R;
     if (localize_to_start) {
         if (i0 > 5 * L / 8 || i1 > 5 * L / 8) { R.ix = P.x[0]; R.iy = P.y[0]; R.ith = P.th[0]; R.index = 0.0; return R; }
@@ -90,17 +95,25 @@ DRE_HD Localization localize_on_path(const PathView &P, double qx, double qy, bo
     return R;
 }
 
+DRE_HD Localization localize_on_path(const PathView &P, double qx, double qy, bool localize_to_start)
+{
+    int i0, i1;
+    path_nearest_two(P, qx, qy, i0, i1);
+    return localize_from_nearest(P, qx, qy, localize_to_start, i0, i1);
+}
+
 // PTEnvCore.state_gen_MLP_local_format, continuous-task branch (path_tracking_core.py:94-145):
 // (lookbehind+lookahead) nodes around ceil(interp_index), wrapped modulo L, as [x.., y.., cos.., sin..] in the robot frame.
+// (j0, jstep): the nodes this caller fills -- (0, 1) for all of them, (lane, lanes) when a lane-group shares the work
 DRE_HD void pt_state_gen(const PathView &P, double px, double py, double pth, double interp_index, int lookahead,
-                         int lookbehind, double *out, int out_stride)
+                         int lookbehind, double *out, int out_stride, int j0 = 0, int jstep = 1)
 {
     double st, ct;
     sincos(pth, &st, &ct);
     const int n = lookahead + lookbehind;
     const int next = (int)ceil(interp_index);
     const int start = next - lookbehind;
-    for (int j = 0; j < n; ++j) {
+    for (int j = j0; j < n; j += jstep) {
         const int idx = ((start + j) % P.L + P.L) % P.L;
         const double dx = P.x[idx] - px, dy = P.y[idx] - py;
         double sr, cr;

@@ -456,104 +456,174 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
 // PT step: one thread per env
 // ---------------------------------------------------------------------------------------------------------------
 // mode 0: step; mode 1: observe only (reset / soft reset: localise + state, no rewards)
+//
+// PT_LANES = 8 lanes per env: the path scans (nearest two nodes of <= 125) and the 25-node PT state are shared by the
+// lanes, the scalar logic in between runs redundantly on all of them (identical inputs -> identical results) and lane 0
+// stores. The kernel sits on the critical path in front of both the crowd half and the MPC solve and is pure latency
+// (one thread per env: 36 us; 8 lanes per env: see profiles/README.md). Shuffles use the full-warp mask: every thread of
+// a warp stays in the kernel and takes the same branches per env group up to data-dependent `if`s without shuffles inside.
+#define PT_LANES 8
+
+// lexicographic (distance^2, index) order: what the sequential scan's strict `<` implements
+__device__ __forceinline__ bool pt_key_lt(double d, int i, double e, int j) { return d < e || (d == e && i < j); }
+
+// path_nearest_two (env_device.cuh) with the scan striped over the PT_LANES lanes of a group
+__device__ __forceinline__ void path_nearest_two_lanes(const PathView &P, double qx, double qy, int lane, int &i0, int &i1)
+{
+    double d0 = INFINITY, d1 = INFINITY;
+    int a0 = 0x7ffffff0, a1 = 0x7ffffff1;
+    for (int i = lane; i < P.L; i += PT_LANES) {
+        const double dx = P.x[i] - qx, dy = P.y[i] - qy;
+        const double d = dx * dx + dy * dy;
+        if (d < d0) { d1 = d0; a1 = a0; d0 = d; a0 = i; }
+        else if (d < d1) { d1 = d; a1 = i; }
+    }
+#pragma unroll
+    for (int o = 1; o < PT_LANES; o <<= 1) {
+        const double e0 = __shfl_xor_sync(0xffffffffu, d0, o), e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+        const int b0 = __shfl_xor_sync(0xffffffffu, a0, o), b1 = __shfl_xor_sync(0xffffffffu, a1, o);
+        if (pt_key_lt(d0, a0, e0, b0)) {                       // mine first: second = min(my second, partner's first)
+            if (pt_key_lt(e0, b0, d1, a1)) { d1 = e0; a1 = b0; }
+        } else {                                               // partner's first: second = min(partner's second, my first)
+            const double f0 = d0; const int c0 = a0;
+            d0 = e0; a0 = b0;
+            if (pt_key_lt(e1, b1, f0, c0)) { d1 = e1; a1 = b1; } else { d1 = f0; a1 = c0; }
+        }
+    }
+    i0 = a0; i1 = a1;
+}
+
+__device__ __forceinline__ Localization localize_lanes(const PathView &P, double qx, double qy, bool lts, int lane)
+{
+    int i0, i1;
+    path_nearest_two_lanes(P, qx, qy, lane, i0, i1);
+    return localize_from_nearest(P, qx, qy, lts, i0, i1);
+}
+
 __global__ void __launch_bounds__(128) pt_step_kernel(EnvDev D, int mode)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < D.E) {
-        int pid = D.path_idx[e];
-        PathView P = path_view(D.paths, D.path_stride, pid, D.lens);
-        double *rp = D.rpose + (size_t)e * 4;
-        double cx = rp[0], cy = rp[1], cth = rp[2];
-        bool lts = D.loc_to_start[e] != 0;
-        Localization cur;
-        if (mode == 0) {
-            // ---- which action runs: the caller's, or the scripted one of an env recovering from a termination ----
-            double av = D.actions[(size_t)e * 2], aw = D.actions[(size_t)e * 2 + 1];
-            uint32_t sr_flags = 0;
-            if (D.soft_reset) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = gt & (PT_LANES - 1);
+    const bool valid = (gt / PT_LANES) < D.E;
+    const int e = valid ? gt / PT_LANES : D.E - 1;            // surplus groups shadow the last env and store nothing
+    const bool writer = valid && lane == 0;
+    const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(PT_LANES - 1);
+
+    int pid = D.path_idx[e];
+    PathView P = path_view(D.paths, D.path_stride, pid, D.lens);
+    double *rp = D.rpose + (size_t)e * 4;
+    double cx = rp[0], cy = rp[1], cth = rp[2];
+    bool lts = D.loc_to_start[e] != 0;
+    const uint32_t prev_bits = D.out.done_bits[e];
+    double av = 0.0, aw = 0.0;
+    if (mode == 0) { av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1]; }
+    __syncwarp();                                             // every lane has read the state lane 0 is about to overwrite
+    Localization cur;
+    if (mode == 0) {
+        // ---- which action runs: the caller's, or the scripted one of an env recovering from a termination ----
+        uint32_t sr_flags = 0;
+        if (D.soft_reset) {
+            double sv = av, sw = aw;
+            if (lane == 0) {
                 SrState S = sr_unpack(D.sr_state + (size_t)e * 4);
                 bool stuck;
-                if (soft_reset_decide(S, D.out.done_bits[e], P, cx, cy, cth, lts, av, aw, stuck)) sr_flags |= 1u;
+                if (soft_reset_decide(S, prev_bits, P, cx, cy, cth, lts, sv, sw, stuck)) sr_flags |= 1u;
                 if (stuck) sr_flags |= 1u << 8;
-                sr_pack(S, D.sr_state + (size_t)e * 4);
+                if (writer) sr_pack(S, D.sr_state + (size_t)e * 4);
             }
+            av = __shfl_sync(0xffffffffu, sv, gshift); aw = __shfl_sync(0xffffffffu, sw, gshift);
+            sr_flags = __shfl_sync(0xffffffffu, sr_flags, gshift);
+        }
+        if (writer) {
             D.out.actions_used[(size_t)e * 2] = av; D.out.actions_used[(size_t)e * 2 + 1] = aw;
             reinterpret_cast<uint32_t *>(D.out.done_flags + (size_t)e * 16)[3] = sr_flags;
-            // ---- robot.step(action): exact-arc unicycle (agent.py:169-176 -> unicycle.py:89-126) ----
-            const double px = cx, py = cy, pth = cth;
-            unicycle_step(px, py, pth, av, aw, D.dt, cx, cy, cth);
+        }
+        // ---- robot.step(action): exact-arc unicycle (agent.py:169-176 -> unicycle.py:89-126) ----
+        const double px = cx, py = cy, pth = cth;
+        unicycle_step(px, py, pth, av, aw, D.dt, cx, cy, cth);
+        if (writer) {
             D.rprev[(size_t)e * 4] = px; D.rprev[(size_t)e * 4 + 1] = py; D.rprev[(size_t)e * 4 + 2] = pth;
             rp[0] = cx; rp[1] = cy; rp[2] = cth;
             D.gtime[e] += D.dt;
             D.step_count[e] += 1;
-            const Localization prv = localize_on_path(P, px, py, lts);
-            cur = localize_on_path(P, cx, cy, lts);
-            if (cur.index >= (double)(P.L / 3) && cur.index < (double)(2 * P.L / 3)) lts = false;
-            // ---- rewards in strategy order (config_PT.py:12; reward_comp.py:20-32), each scaled by overall_scaling ----
-            double reward = 0.0;
-            uint32_t bits = 0;
-            const double sc = D.pt_overall_scaling;
-            {   // goal (reward_comp.py:34-54)
-                const double gx = P.x[P.L - 1], gy = P.y[P.L - 1], gth = P.th[P.L - 1];
-                bool hit = false;
-                for (int i = 1; i <= 5; ++i) {
-                    double qx, qy, qth;
-                    unicycle_step(px, py, pth, av, aw, D.dt * (double)i / 5.0, qx, qy, qth);
-                    const double ddx = qx - gx, ddy = qy - gy;
-                    const double ad = fabs(np_mod(qth - gth + DRE_PI, 2.0 * DRE_PI) - DRE_PI);
-                    if (sqrt(ddx * ddx + ddy * ddy) < D.goal_radius && ad < D.goal_angle) hit = true;
-                }
-                if (hit) { reward += sc * D.goal_reward; bits |= DRE_DONE_GOAL | DRE_DONE_PT; }
-                else reward += sc * 0.0;
+        }
+        const Localization prv = localize_lanes(P, px, py, lts, lane);
+        cur = localize_lanes(P, cx, cy, lts, lane);
+        if (cur.index >= (double)(P.L / 3) && cur.index < (double)(2 * P.L / 3)) lts = false;
+        // ---- rewards in strategy order (config_PT.py:12; reward_comp.py:20-32), each scaled by overall_scaling ----
+        double reward = 0.0;
+        uint32_t bits = 0;
+        const double sc = D.pt_overall_scaling;
+        {   // goal (reward_comp.py:34-54): the five intermediate poses, one per lane
+            const double gx = P.x[P.L - 1], gy = P.y[P.L - 1], gth = P.th[P.L - 1];
+            bool hit = false;
+            for (int i = 1 + lane; i <= 5; i += PT_LANES) {
+                double qx, qy, qth;
+                unicycle_step(px, py, pth, av, aw, D.dt * (double)i / 5.0, qx, qy, qth);
+                const double ddx = qx - gx, ddy = qy - gy;
+                const double ad = fabs(np_mod(qth - gth + DRE_PI, 2.0 * DRE_PI) - DRE_PI);
+                if (sqrt(ddx * ddx + ddy * ddy) < D.goal_radius && ad < D.goal_angle) hit = true;
             }
-            double adv;
-            {   // path_advancement (reward_comp.py:101-116)
-                double pi_ = prv.index, ci_ = cur.index;
-                if (fabs(ci_ - pi_) > 10.0) {
-                    const double half = (double)(P.L / 2);
-                    pi_ = np_mod(pi_ + half, (double)P.L);
-                    ci_ = np_mod(ci_ + half, (double)P.L);
-                }
-                adv = sc * (D.path_adv_scaling * (ci_ - pi_));
-                reward += adv;
+            hit = ((__ballot_sync(0xffffffffu, hit) >> gshift) & ((1u << PT_LANES) - 1u)) != 0u;
+            if (hit) { reward += sc * D.goal_reward; bits |= DRE_DONE_GOAL | DRE_DONE_PT; }
+            else reward += sc * 0.0;
+        }
+        double adv;
+        {   // path_advancement (reward_comp.py:101-116)
+            double pi_ = prv.index, ci_ = cur.index;
+            if (fabs(ci_ - pi_) > 10.0) {
+                const double half = (double)(P.L / 2);
+                pi_ = np_mod(pi_ + half, (double)P.L);
+                ci_ = np_mod(ci_ + half, (double)P.L);
             }
-            const double ddx = cx - cur.ix, ddy = cy - cur.iy;
-            const double xy_dev = sqrt(ddx * ddx + ddy * ddy);
-            double devr;
-            {   // deviation (reward_comp.py:89-99)
-                const double th_dev = np_mod(cth - cur.ith + DRE_PI, 2.0 * DRE_PI) - DRE_PI;
-                const double th_reward = -D.dev_th * fabs(th_dev);
-                const double xy_reward = -xy_dev * D.dev_xy;
-                devr = sc * ((xy_reward + th_reward) * D.dev_scale);
-                reward += devr;
-            }
-            if (P.L - 1 == (int)prv.index) { reward += sc * D.eop_penalty; bits |= DRE_DONE_END_OF_PATH | DRE_DONE_PT; }
-            else reward += sc * 0.0;
-            if (D.corridor_max_dev < xy_dev) { reward += sc * D.corridor_penalty; bits |= DRE_DONE_CORRIDOR_HIT | DRE_DONE_PT; }
-            else reward += sc * 0.0;
-            if (D.safety_corridor_max_dev < xy_dev) { reward += sc * D.safety_corridor_penalty; bits |= DRE_DONE_SAFETY_CORRIDOR | DRE_DONE_PT; }
-            else reward += sc * 0.0;
-            // the HA half (ha_step_kernel, launched after the MPC solve) merges rewards / dones (HA_and_PT env.py:322-331)
+            adv = sc * (D.path_adv_scaling * (ci_ - pi_));
+            reward += adv;
+        }
+        const double ddx = cx - cur.ix, ddy = cy - cur.iy;
+        const double xy_dev = sqrt(ddx * ddx + ddy * ddy);
+        double devr;
+        {   // deviation (reward_comp.py:89-99)
+            const double th_dev = np_mod(cth - cur.ith + DRE_PI, 2.0 * DRE_PI) - DRE_PI;
+            const double th_reward = -D.dev_th * fabs(th_dev);
+            const double xy_reward = -xy_dev * D.dev_xy;
+            devr = sc * ((xy_reward + th_reward) * D.dev_scale);
+            reward += devr;
+        }
+        if (P.L - 1 == (int)prv.index) { reward += sc * D.eop_penalty; bits |= DRE_DONE_END_OF_PATH | DRE_DONE_PT; }
+        else reward += sc * 0.0;
+        if (D.corridor_max_dev < xy_dev) { reward += sc * D.corridor_penalty; bits |= DRE_DONE_CORRIDOR_HIT | DRE_DONE_PT; }
+        else reward += sc * 0.0;
+        if (D.safety_corridor_max_dev < xy_dev) { reward += sc * D.safety_corridor_penalty; bits |= DRE_DONE_SAFETY_CORRIDOR | DRE_DONE_PT; }
+        else reward += sc * 0.0;
+        // the HA half (ha_step_kernel) merges rewards / dones (HA_and_PT env.py:322-331)
+        if (writer) {
             D.out.rewards[(size_t)e * 3] = reward;
             D.out.done_bits[e] = bits;
             D.out.info[(size_t)e * 8 + 2] = adv; D.out.info[(size_t)e * 8 + 3] = devr;
             D.out.info[(size_t)e * 8 + 5] = cur.index; D.out.info[(size_t)e * 8 + 6] = xy_dev; D.out.info[(size_t)e * 8 + 7] = prv.index;
-            // ---- path switch on goal / end of path (what soft_reset does, HA_and_PT env.py:130-141) ----
-            if (D.auto_path_switch && (bits & (DRE_DONE_GOAL | DRE_DONE_END_OF_PATH))) {
-                pid = (pid + 1) % D.num_paths;
-                D.path_idx[e] = pid;
-                lts = true;
-                D.mpc_iteration0[e] = 1;
-                P = path_view(D.paths, D.path_stride, pid, D.lens);
-                cur = localize_on_path(P, cx, cy, lts);
-            }
-            D.loc_to_start[e] = lts ? 1 : 0;
-        } else {
-            cur = localize_on_path(P, cx, cy, lts);
         }
-        pt_state_gen(P, cx, cy, cth, cur.index, D.lookahead, D.lookbehind, D.out.pt_state + (size_t)e * (4 * (D.lookahead + D.lookbehind)), 1);
-        D.mpc_interp[e] = cur.index;
+        // ---- path switch on goal / end of path (what soft_reset does, HA_and_PT env.py:130-141) ----
+        // (`bits` is the same on all lanes of the group and on all groups' surplus shadows, so the shuffles inside
+        // localize_lanes are executed by whole groups; groups of a warp may differ, hence the explicit convergence)
+        const bool sw = D.auto_path_switch && (bits & (DRE_DONE_GOAL | DRE_DONE_END_OF_PATH));
+        const bool any_sw = __any_sync(0xffffffffu, sw);
+        if (any_sw) {
+            const int npid = sw ? (pid + 1) % D.num_paths : pid;
+            const PathView NP = path_view(D.paths, D.path_stride, npid, D.lens);
+            const Localization nl = localize_lanes(NP, cx, cy, sw ? true : lts, lane);   // all lanes of the warp take part
+            if (sw) {
+                pid = npid; P = NP; lts = true; cur = nl;
+                if (writer) { D.path_idx[e] = pid; D.mpc_iteration0[e] = 1; }
+            }
+        }
+        if (writer) D.loc_to_start[e] = lts ? 1 : 0;
+    } else {
+        cur = localize_lanes(P, cx, cy, lts, lane);
     }
+    if (valid)
+        pt_state_gen(P, cx, cy, cth, cur.index, D.lookahead, D.lookbehind, D.out.pt_state + (size_t)e * (4 * (D.lookahead + D.lookbehind)), 1,
+                     lane, PT_LANES);
+    if (writer) D.mpc_interp[e] = cur.index;
 }
 
 // MPC retry / give-up statistics after the solve
@@ -796,7 +866,8 @@ int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 
 int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s)
 {
-    pt_step_kernel<<<(D.E + 63) / 64, 64, 0, s>>>(D, mode);
+    const int threads = 128, envs_per_block = threads / 8;   // PT_LANES lanes per env
+    pt_step_kernel<<<(D.E + envs_per_block - 1) / envs_per_block, threads, 0, s>>>(D, mode);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }

@@ -71,10 +71,15 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
     const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
 
+    const bool static_sched = (p.group_lanes & 0x200) != 0;   // measurement aid: agent = group + k * NG instead of the queue
+    int next_static = gi;
     for (;;) {   // groups pull agents from a CTA-wide counter: LP3 solves are ~10x dearer than LP2 ones
         int ag = 0;
-        if (g.rank() == 0) ag = atomicAdd(work_counter, 1);
-        ag = g.bcast(ag, 0);
+        if (static_sched) { ag = next_static; next_static += NG; }
+        else {
+            if (g.rank() == 0) ag = atomicAdd(work_counter, 1);
+            ag = g.bcast(ag, 0);
+        }
         if (ag >= EPB * Nh) break;
         const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
         if (e >= E) continue;

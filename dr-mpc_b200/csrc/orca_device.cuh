@@ -251,18 +251,22 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     for (int j = lane; j < nA; j += G) {
         const bool in = sdist[j] < INFINITY;
         if (in) {
+            // (d_k, k) < (d_j, j)  <=>  k < j ? bits_k <= bits_j : bits_k < bits_j. One compare per key: chunks of four
+            // keys below j's own chunk count `<= bits_j` (= `< bits_j + 1`), the others `< bits_j`; the (rare) exact ties
+            // with a smaller index inside j's own chunk are added afterwards from that one chunk.
             const unsigned uj = dre_f2u(sdist[j]);
-            int r = 0, eq = 0;
+            const int jc = j & ~3;
+            int r = 0;
 #pragma unroll 2
             for (int k = 0; k < nA4; k += 4) {
                 const float4 q = *reinterpret_cast<const float4 *>(sdist + k);
-                const unsigned u0 = dre_f2u(q.x), u1 = dre_f2u(q.y), u2 = dre_f2u(q.z), u3 = dre_f2u(q.w);
-                r += (u0 < uj) + (u1 < uj) + (u2 < uj) + (u3 < uj);
-                eq += (u0 == uj) + (u1 == uj) + (u2 == uj) + (u3 == uj);
+                const unsigned thr = uj + (k < jc ? 1u : 0u);
+                r += (int)(dre_f2u(q.x) < thr) + (int)(dre_f2u(q.y) < thr) + (int)(dre_f2u(q.z) < thr) + (int)(dre_f2u(q.w) < thr);
             }
-            if (eq > 1) {   // exact ties (rare): earlier index first
-#pragma unroll 1
-                for (int k = 0; k < j; ++k) r += (dre_f2u(sdist[k]) == uj) ? 1 : 0;
+            {
+                const float4 q = *reinterpret_cast<const float4 *>(sdist + jc);
+                const int jr = j - jc;   // 0..3: position of j in its chunk
+                r += (int)(jr > 0 && dre_f2u(q.x) == uj) + (int)(jr > 1 && dre_f2u(q.y) == uj) + (int)(jr > 2 && dre_f2u(q.z) == uj);
             }
             if (r < maxNeighbors) L[r] = orca_make_line(px, py, vx, vy, rs, ax[j], ay[j], avx[j], avy[j], ar[j], invTH, invDt, mask);
         }

@@ -65,6 +65,8 @@ class EngineConfig:
     auto_path_switch: bool = True
     soft_reset_on_device: bool = False   # run HAAndPTEnv.soft_reset as a per-env state machine inside step()
     orca_dedup: bool = False             # reuse step t's look-ahead ORCA pass as step t+1's movement pass (bit-identical)
+    robot_sensor_restriction: bool = False   # config_HA.robot.sensor_restriction ("TODO: if True, verify correctness" upstream)
+    robot_sensor_range: float = 4.0          # config_HA.robot.sensor_range
     static_humans: tuple = ()            # ((x, y), ...) static obstacles = the LAST len(static_humans) of num_humans
     seed: int = 0x00D24D9C
     env_id_offset: int = 0
@@ -95,6 +97,8 @@ class EngineConfig:
             safety_corridor_max_dev=pp['safety_corridor_raise']['max_deviation'],
             lookahead=pt.PT_model_params['MLP_local'].lookahead, lookbehind=pt.PT_model_params['MLP_local'].lookbehind,
         )
+        c.robot_sensor_restriction = bool(getattr(ha.robot, "sensor_restriction", False))
+        c.robot_sensor_range = float(getattr(ha.robot, "sensor_range", 4.0))
         # continuous task with static humans on: two hard-coded obstacles appended after the dynamic humans
         # (crowd_sim.py:156-158,171-183; config_HA.py:46)
         st = getattr(ha.sim, "include_static_humans", None)
@@ -126,6 +130,7 @@ class EngineConfig:
             self.path_advancement_scaling, self.deviation_xy, self.deviation_th, self.deviation_scale,
             self.corridor_penalty, self.corridor_max_dev, self.end_of_path_penalty, self.safety_corridor_penalty,
             self.safety_corridor_max_dev, self.lookahead, self.lookbehind, self.actions_in_input,
-            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), len(self.static_humans),
+            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), int(self.robot_sensor_restriction), float(self.robot_sensor_range),
+            len(self.static_humans),
             (ctypes.c_double * 8)(*([float(v) for xy in self.static_humans for v in xy] + [0.0] * (8 - 2 * len(self.static_humans)))),
             self.seed, self.env_id_offset)

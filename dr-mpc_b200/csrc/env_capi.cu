@@ -163,6 +163,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
     D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
     D.soft_reset = cfg->soft_reset_on_device; D.orca_dedup = cfg->orca_dedup;
+    D.sensor_restriction = cfg->sensor_restriction; D.sensor_range = cfg->sensor_range;
     D.num_static = cfg->num_static_humans;
     for (int i = 0; i < 8; ++i) D.static_pos[i] = cfg->static_pos[i];
     D.seed = cfg->seed; D.env_id_offset = cfg->env_id_offset;

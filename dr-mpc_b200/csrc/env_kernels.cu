@@ -194,6 +194,13 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
                     hh[valid] = np_;
                     D.hvalid[gidx] = valid + 1 < H ? valid + 1 : H;
                 }
+                if (D.sensor_restriction) {   // out of the robot's sensor range: the history starts over (:102-105, :161-164)
+                    double st, ct;
+                    sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
+                    const double ddx = np_.x - D.rpose[(size_t)e * 4], ddy = np_.y - D.rpose[(size_t)e * 4 + 1];
+                    const double lx = ct * ddx + st * ddy, ly = -st * ddx + ct * ddy;
+                    if (sqrt(lx * lx + ly * ly) > D.sensor_range) D.hvalid[gidx] = 0;
+                }
             } else {
                 double *rp = D.rpose + (size_t)e * 4;
                 double av = 0.0, aw = 0.0;
@@ -227,22 +234,44 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     // ---- observation (human_avoidance_env.py:24-77), frame = 'robot' ----
     if (write_obs) {
         const int W = 2 * H;
+        // sensor restriction (:53-72): output row r shows the r-th VISIBLE human for r < nv and keeps human r's own row
+        // beyond; one thread per env builds that row map (the reward scratch is free at this point of the kernel)
+        int *src_row = reinterpret_cast<int *>(pen);
+        if (D.sensor_restriction) {
+            for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
+                const int e = env0 + el;
+                if (e >= D.E) continue;
+                int nv = 0;
+                for (int i = 0; i < Nh; ++i) src_row[el * Nh + i] = i;
+                for (int i = 0; i < Nh; ++i)
+                    if (D.hvalid[(size_t)e * Nh + i] != 0) src_row[el * Nh + nv++] = i;
+                flags[el * 4 + 1] = nv;
+            }
+            __syncthreads();
+        }
         for (int t = threadIdx.x; t < EPB * Nh * H; t += blockDim.x) {
             const int el = t / (Nh * H), r = t - el * Nh * H, i = r / H, s = r - i * H, e = env0 + el;
             if (e >= D.E) continue;
+            const int src = D.sensor_restriction ? src_row[el * Nh + i] : i;
             double st, ct;
             sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
             const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
-            const double2 q = D.hhist[((size_t)e * Nh + i) * H + s];
+            const double2 q = D.hhist[((size_t)e * Nh + src) * H + s];
             const double dx = q.x - rx, dy = q.y - ry;
             double *o = D.out.spatial_edges + ((size_t)e * Nh + i) * W + 2 * s;
             o[0] = ct * dx + st * dy;
             o[1] = -st * dx + ct * dy;
+            if (D.sensor_restriction && flags[el * 4 + 1] == 0 && i == 0) { o[0] = -10.0; o[1] = -10.0; }   // nobody in range: a fake far human (:66-68)
         }
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int el = t / Nh, i = t - el * Nh, e = env0 + el;
             if (e >= D.E) continue;
-            D.out.human_valid[(size_t)e * Nh + i] = (double)D.hvalid[(size_t)e * Nh + i];
+            double hv = (double)D.hvalid[(size_t)e * Nh + i];
+            if (D.sensor_restriction) {
+                const int nv = flags[el * 4 + 1];
+                hv = nv == 0 ? 1.0 : (i < nv ? (double)D.hvalid[(size_t)e * Nh + src_row[el * Nh + i]] : 0.0);
+            }
+            D.out.human_valid[(size_t)e * Nh + i] = hv;
         }
         for (int t = threadIdx.x; t < EPB * D.LB; t += blockDim.x) {
             const int el = t / D.LB, s = t - el * D.LB, e = env0 + el;
@@ -261,8 +290,11 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
             const int e = env0 + el;
             if (e >= D.E) continue;
             D.out.percent_episode[e] = D.gtime[e] / D.time_limit * 10.0 - 5.0;
-            D.out.detected_humans[e] = (double)Nh;
+            int det = Nh;
+            if (D.sensor_restriction) det = flags[el * 4 + 1] > 0 ? flags[el * 4 + 1] : 1;
+            D.out.detected_humans[e] = (double)det;
         }
+        if (D.sensor_restriction) __syncthreads();   // the row map lives in the reward scratch
     }
 
     // ---- the observation of this CTA's envs is final: chunk flag for the pipelined host path (threadFenceReduction
@@ -707,7 +739,15 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
         D.hgoal[gidx] = make_double2(gx, gy);
         D.hvel[gidx] = make_float2(0.f, 0.f);
         D.hstatic[gidx] = si >= 0 ? 1 : 0;
-        D.hvalid[gidx] = 1;
+        int v0 = 1;
+        if (D.sensor_restriction) {   // human_avoidance_env.py:331-334
+            double st, ct;
+            sincos(rth, &st, &ct);
+            const double ddx = px - rx, ddy = py - ry;
+            const double lx = ct * ddx + st * ddy, ly = -st * ddx + ct * ddy;
+            if (sqrt(lx * lx + ly * ly) > D.sensor_range) v0 = 0;
+        }
+        D.hvalid[gidx] = v0;
         for (int s = 0; s < H; ++s) D.hhist[gidx * H + s] = make_double2(px, py);
     }
 }

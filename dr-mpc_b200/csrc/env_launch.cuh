@@ -23,6 +23,8 @@ struct EnvDev {
     double pt_overall_scaling, goal_radius, goal_angle, goal_reward, path_adv_scaling, dev_xy, dev_th, dev_scale;
     double corridor_penalty, corridor_max_dev, eop_penalty, safety_corridor_penalty, safety_corridor_max_dev;
     int lookahead, lookbehind, auto_path_switch, soft_reset, orca_dedup;
+    int sensor_restriction;
+    double sensor_range;
     int num_static;
     double static_pos[8];
     uint64_t seed;

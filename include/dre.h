@@ -152,6 +152,10 @@ typedef struct dre_env_config {
                                                     (:181-184); those humans are solved again. Bit-identical results, one
                                                     ORCA pass per step instead of two. Writers of the state views must call
                                                     dre_env_invalidate_orca_cache(). Default 0 = two passes like the reference */
+    int32_t sensor_restriction;                  /* config_HA.robot.sensor_restriction (False): humans farther than sensor_range
+                                                    from the robot lose their history (human_avoidance_env.py:102-105,161-164,
+                                                    331-334) and the observation lists the visible ones first (:53-72)     */
+    double sensor_range;                         /* config_HA.robot.sensor_range (4)                                        */
     int32_t num_static_humans;                   /* the LAST num_static_humans of num_humans are static obstacles (isObstacle,
                                                     crowd_sim.py:171-183, 270-272): placed at static_pos by reset(), zero
                                                     action, no goal resampling, no disturbance term. 0..4                */

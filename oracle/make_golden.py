@@ -348,9 +348,62 @@ def golden_cvmm():
     print("cvmm.npz", os.path.getsize(os.path.join(OUT, "cvmm.npz")), "bytes")
 
 
+# ------------------------------------------------------------------------------------------------------------
+# 6. Robot sensor restriction (config_HA.robot.sensor_restriction = True, sensor_range 4 m): HAAndPTEnv.reset / step with
+#    humans dropping out of and coming back into range (human_avoidance_env.py:53-72,102-105,161-164,331-334)
+# ------------------------------------------------------------------------------------------------------------
+def golden_sensor():
+    from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
+    from environment.human_avoidance.utils.action import ActionRot
+    out = {}
+    for tag, Nh, seed, steps in (("h6", 6, 8, 150), ("h10", 10, 9, 90)):
+        cm = _config(Nh)
+        cm.config_HA.robot.sensor_restriction = True
+        env = HAAndPTEnv(cm, seed_addition=seed)
+        env.case_counter['train'] = seed
+        K = cm.config_PT.MPC.planning_horizon
+        S = env.reset()
+        for k, v in _flatten_S(S).items():
+            out[f"{tag}_reset_{k}"] = np.asarray(v)
+        np.random.seed(seed)
+        env2 = HAAndPTEnv(cm, seed_addition=seed)
+        env2.case_counter['train'] = seed
+        env2.config_HA.sim.warm_start = False
+        env2.reset()
+        env2.config_HA.sim.warm_start = True
+        out[f"{tag}_reset_hpos"] = np.array([[h.px, h.py] for h in env2.HA_env.humans])
+        out[f"{tag}_reset_hgoal"] = np.array([[h.gx, h.gy] for h in env2.HA_env.humans])
+        rng = np.random.default_rng(seed)
+        rec_pre, rec_post, rec_out = [], [], []
+        done_return, info = {'done': False}, None
+        for n in range(steps):
+            if done_return['done']:
+                S = env.soft_reset(done_return, info, S)
+                if S is None:
+                    break
+            a = np.array(S['PT']['MPC_actions'][0, :2], dtype=np.float64)
+            if (n // 15) % 3 == 1:
+                a = a + rng.normal(0, 0.3, 2)
+            a[0] = float(np.clip(a[0], 0, 1)); a[1] = float(np.clip(a[1], -1, 1))
+            pre = _snapshot(env, K)
+            S, R, done_return, info, eps = env.step(ActionRot(a[0], a[1]))
+            o = _flatten_S(S)
+            o.update({"action": a, "rewards": np.array([R['R_PT'], R['R_DO'], R['R']])})
+            rec_pre.append(pre); rec_post.append(_snapshot(env, K)); rec_out.append(o)
+        for name, rec in (("pre", rec_pre), ("post", rec_post), ("out", rec_out)):
+            for k in rec[0]:
+                out[f"{tag}_{name}_{k}"] = np.stack([np.asarray(r[k]) for r in rec])
+        det = out[f"{tag}_out_detected_humans"]
+        hv = out[f"{tag}_post_hvalid"]
+        print(tag, "steps", len(rec_pre), "detected humans min/mean/max", det.min(), det.mean(), det.max(), "re-entries",
+              int(((hv[1:] == 1) & (hv[:-1] == 0)).sum()), "nobody visible", int((hv.sum(1) == 0).sum()))
+    np.savez_compressed(os.path.join(OUT, "sensor_restriction.npz"), **out)
+    print("sensor_restriction.npz", os.path.getsize(os.path.join(OUT, "sensor_restriction.npz")), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["orca", "mpc", "env", "soft_reset", "cvmm"]
+    which = sys.argv[1:] or ["orca", "mpc", "env", "soft_reset", "cvmm", "sensor"]
     if "orca" in which:
         golden_orca()
     if "mpc" in which:
@@ -361,3 +414,5 @@ if __name__ == "__main__":
         golden_soft_reset()
     if "cvmm" in which:
         golden_cvmm()
+    if "sensor" in which:
+        golden_sensor()

@@ -400,7 +400,7 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     const bool tr = trace && (h->step_seq & 63) == 63;
     auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_start = tr ? now_us() : 0.0;
-    double t_flag[dre_env::MAX_CHUNKS] = {}, t_front = 0.0, t_enq = 0.0;
+    double t_flag[dre_env::MAX_CHUNKS] = {}, t_enq = 0.0;
     if (h->last_stream_set) {   // earlier reset() / step() / observe() calls ran on the caller's stream: run after them
         DRE_CUDA_TRY(cudaEventRecord(h->ev_sync, h->last_stream));
         DRE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_sync, 0));
@@ -485,7 +485,6 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
         const double t_done = now_us();
         cudaStreamSynchronize(c);
         const double t_end = now_us();
-        (void)t_front;
         fprintf(stderr, "[host trace] enqueued %.0f us, chunk flags at", t_enq - t_start);
         for (int i = 0; i < chunks; ++i) fprintf(stderr, " %.0f", t_flag[i] - t_start);
         fprintf(stderr, ", step (crowd half, then MPC) done %.0f, copies done %.0f us\n", t_done - t_start, t_end - t_start);

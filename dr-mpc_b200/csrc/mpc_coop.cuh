@@ -99,10 +99,57 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs)
     *cs = fma(z * z, pc, fma(z, -0.5, 1.0));
 }
 
+// 1/x from the hardware seed (rcp.approx: ~2^-23) and two Newton steps: within 1-2 ulp, 5 instructions instead of the
+// ~25 of an IEEE division. Every quotient of the LM attempt goes through it (each fp64 instruction costs the scheduler's
+// fp64 pipe two cycles); none of them needs correct rounding: they feed cost terms, Jacobians and threshold tests.
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+// half_cot / phi_coef / barrier_grad of mpc_device.cuh with reciprocal-multiplies
+__device__ __forceinline__ double half_cot_fast(double p, double sn, double cs)
+{
+    if (fabs(p) < 1e-3) { const double p2 = p * p; return 1.0 - p2 * (1.0 / 12.0) - p2 * p2 * (1.0 / 720.0); }
+    return cs >= 0.0 ? 0.5 * p * (1.0 + cs) * rcp_fast(sn) : 0.5 * p * sn * rcp_fast(1.0 - cs);
+}
+__device__ __forceinline__ PhiCoef phi_coef_fast(double p, double sn, double cs)
+{
+    PhiCoef q;
+    if (fabs(p) < 1e-3) {
+        const double p2 = p * p;
+        q.A = 1.0 - p2 * (1.0 / 6.0) + p2 * p2 * (1.0 / 120.0);
+        q.beta = 0.5 - p2 * (1.0 / 24.0) + p2 * p2 * (1.0 / 720.0);
+        q.B = p * q.beta;
+        q.alpha = p * (1.0 / 6.0 - p2 * (1.0 / 120.0) + p2 * p2 * (1.0 / 5040.0));
+    } else {
+        const double ip = rcp_fast(p);
+        q.A = sn * ip;
+        q.B = (1.0 - cs) * ip;
+        q.beta = q.B * ip;
+        q.alpha = (p - sn) * ip * ip;
+    }
+    return q;
+}
+__device__ __forceinline__ Aff se2_Jlinv_fast(const double e[3], double sn, double cs, double ct)
+{
+    const PhiCoef q = phi_coef_fast(e[2], sn, cs);
+    const double h = 0.5 * e[2];
+    const double qx = q.alpha * e[0] + q.beta * e[1], qy = q.alpha * e[1] - q.beta * e[0];
+    Aff a;
+    a.m[0] = ct; a.m[1] = h;  a.m[2] = -(ct * qx + h * qy);
+    a.m[3] = -h; a.m[4] = ct; a.m[5] = h * qx - ct * qy;
+    return a;
+}
+__device__ __forceinline__ double barrier_grad_fast(double x) { return (x <= 0.0 || x > 1.0) ? 10.0 : rcp_fast(x); }
+
 // log map of T whose rotation angle p (wrapped) is already known
 __device__ __forceinline__ void se2_log_known(const Se2 &T, double p, double e[3], double &ct)
 {
-    ct = half_cot(p, T.s, T.c);
+    ct = half_cot_fast(p, T.s, T.c);
     const double h = 0.5 * p;
     e[0] = ct * T.x + h * T.y;
     e[1] = ct * T.y - h * T.x;
@@ -114,7 +161,7 @@ __device__ __forceinline__ Se2h se2h_step(double rx, double ry, double p, const 
 {
     double sn, cs;
     sincos_small(p, &sn, &cs);
-    const PhiCoef q = phi_coef(p, sn, cs);
+    const PhiCoef q = phi_coef_fast(p, sn, cs);
     Se2 E;
     E.c = cs; E.s = sn;
     E.x = q.A * rx - q.B * ry;
@@ -135,7 +182,7 @@ __device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2h &
     const double p = C.dt * u[1];
     double sn, cs;
     sincos_small(p, &sn, &cs);
-    const PhiCoef q = phi_coef(p, sn, cs);
+    const PhiCoef q = phi_coef_fast(p, sn, cs);
     const Se2 E = se2_mul(se2_mul_inv(Tk1.T, Tprev.T), se2_exp_x(C.dt * u[0], p, sn, cs, q));
     se2_log_known(E, wrap_angle(Tk1.th - Tprev.th + p), e, ct);
     cost += 0.5 * 1000.0 * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
@@ -177,7 +224,7 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
         double e[3], ct;
         const Se2 E = se2_mul_inv(Mk.T, Tk1.T);
         se2_log_known(E, wrap_angle(Mk.th - Tk1.th), e, ct);
-        Aff Gm = se2_Jlinv(e, E.s, E.c, ct);
+        Aff Gm = se2_Jlinv_fast(e, E.s, E.c, ct);
         if (C.pose_jac_exact) Gm = aff_mul(Gm, se2_Ad(E));
         const double r0[3] = {-Gm.m[0], -Gm.m[1], -Gm.m[2]}, r1[3] = {-Gm.m[3], -Gm.m[4], -Gm.m[5]}, r2[3] = {0.0, 0.0, -1.0};
         acc_block<3>(D, b, 2, r0, r1, r2, e, 3.0 / s);
@@ -186,13 +233,13 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
         const double p = C.dt * u[1];
         double sn, cs;
         sincos_small(p, &sn, &cs);
-        const PhiCoef q = phi_coef(p, sn, cs);
+        const PhiCoef q = phi_coef_fast(p, sn, cs);
         const double rx = C.dt * u[0];
         const Se2 Lh = se2_mul_inv(Tk1.T, Tprev.T);
         const Se2 E = se2_mul(Lh, se2_exp_x(rx, p, sn, cs, q));
         double e[3], ct;
         se2_log_known(E, wrap_angle(Tk1.th - Tprev.th + p), e, ct);
-        const Aff Gm = se2_Jlinv(e, E.s, E.c, ct);
+        const Aff Gm = se2_Jlinv_fast(e, E.s, E.c, ct);
         Aff Jl;
         Jl.m[0] = q.A; Jl.m[1] = q.B;  Jl.m[2] = q.alpha * rx;
         Jl.m[3] = -q.B; Jl.m[4] = q.A; Jl.m[5] = q.beta * rx;
@@ -223,8 +270,8 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
         const double k500 = 1.0 / 500.0;
         const double e0 = barrier_val(x0) * k500, e1 = barrier_val(x1) * k500;
         const double e2 = barrier_val(x2) * k500, e3 = barrier_val(x3) * k500;
-        const double j0 = -k500 * barrier_grad(x0) * C.inv_vmax, j1 = k500 * barrier_grad(x1) * C.inv_vmax;
-        const double j2 = -k500 * barrier_grad(x2) * C.inv_2wmax, j3 = k500 * barrier_grad(x3) * C.inv_2wmax;
+        const double j0 = -k500 * barrier_grad_fast(x0) * C.inv_vmax, j1 = k500 * barrier_grad_fast(x1) * C.inv_vmax;
+        const double j2 = -k500 * barrier_grad_fast(x2) * C.inv_2wmax, j3 = k500 * barrier_grad_fast(x3) * C.inv_2wmax;
         b[0] -= 0.1 * (j0 * e0 + j1 * e1);
         b[1] -= 0.1 * (j2 * e2 + j3 * e3);
         D[0] += 0.1 * (j0 * j0 + j1 * j1);
@@ -477,7 +524,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 const double dp = d[c], uc = u[c];
                 const double hi = c == 0 ? C.vmax : C.wmax, lo = c == 0 ? 0.0 : -C.wmax;
                 const double maxp = dp > 0.0 ? (hi - 1e-7) - uc : (lo + 1e-7) - uc;
-                allowed[c] = (dp != 0.0 && act) ? maxp / dp : INFINITY;
+                allowed[c] = (dp != 0.0 && act) ? maxp / dp : INFINITY;   // IEEE: the 1e-7 margins of the box are part of the semantics
             }
             double scale = 1.0;
             for (int kk = 0; kk < K; ++kk) {
@@ -494,6 +541,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             // state, both trials re-evaluate `curr` bit for bit, the predicted reduction is 0 and the ratio is defined as 0
             // (lev_marq...py:110-113) -> both are rejected. Skip the two cost evaluations, keep the counters.
             if (scale == 0.0) { cost_evals += 2; ++zero_steps; }
+            double lin = 0.0, quad = 0.0;
             for (int bt = 0; bt < 2 && scale != 0.0; ++bt) {
                 if (bt > 0) {
 #pragma unroll
@@ -505,20 +553,26 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tt, ut, Mk, 1.0 / s) : 0.0;
                 proposed = g.sum_ordered(c, K);
                 ++cost_evals;
-                // predicted reduction b^T p - 1/2 p^T A p with the undamped A (lev_marq...py:167-171)
-                const double p2 = g.up(d[2]), p3 = g.up(d[3]), p4 = g.up(d[4]);
-                double gg = 0.0, qq = 0.0;
+                // predicted reduction b^T p - 1/2 p^T A p with the undamped A (lev_marq...py:167-171). The second trial's
+                // step is 0.8 x the first one's, so its linear and quadratic forms are 0.8 x and 0.64 x the first trial's
+                // (equal up to the rounding of the products; the forms only feed the ratio > 0.25 test)
+                if (bt == 0) {
+                    const double p2 = g.up(d[2]), p3 = g.up(d[3]), p4 = g.up(d[4]);
+                    double gg = 0.0, qq = 0.0;
 #pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    gg += M[CS_B + a] * d[a];
-                    double r = 0.0;
+                    for (int a = 0; a < 5; ++a) {
+                        gg += M[CS_B + a] * d[a];
+                        double r = 0.0;
 #pragma unroll
-                    for (int c2 = 0; c2 < 5; ++c2) r += M[CS_D + (a >= c2 ? a * (a + 1) / 2 + c2 : c2 * (c2 + 1) / 2 + a)] * d[c2];
-                    if (k > 0) r += 2.0 * (M[CS_O + 3 * a] * p2 + M[CS_O + 3 * a + 1] * p3 + M[CS_O + 3 * a + 2] * p4);
-                    qq += d[a] * r;
-                }
-                const double pred = g.sum_ordered(act ? gg : 0.0, K) - 0.5 * g.sum_ordered(act ? qq : 0.0, K);
-                const double ratio = (pred == 0.0) ? 0.0 : (prev - proposed) / pred;
+                        for (int c2 = 0; c2 < 5; ++c2) r += M[CS_D + (a >= c2 ? a * (a + 1) / 2 + c2 : c2 * (c2 + 1) / 2 + a)] * d[c2];
+                        if (k > 0) r += 2.0 * (M[CS_O + 3 * a] * p2 + M[CS_O + 3 * a + 1] * p3 + M[CS_O + 3 * a + 2] * p4);
+                        qq += d[a] * r;
+                    }
+                    lin = g.sum_ordered(act ? gg : 0.0, K);
+                    quad = g.sum_ordered(act ? qq : 0.0, K);
+                } else { lin *= 0.8; quad *= 0.64; }
+                const double pred = lin - 0.5 * quad;
+                const double ratio = (pred == 0.0) ? 0.0 : (prev - proposed) * rcp_fast(pred);
                 if (ratio > 0.25) { success = true; break; }
             }
         }

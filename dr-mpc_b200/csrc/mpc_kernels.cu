@@ -159,6 +159,21 @@ int dre_mpc_launch(const dre_mpc_params &p, const MpcDeviceState &st, const int3
 #undef DRE_MPC_ARGS
 }
 
+// accuracy self-test of the kernel's own reciprocal (tests/test_gpu_mpc.py)
+__global__ void mpc_math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ rc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rc[i] = rcp_fast(x[i]);
+}
+
+extern "C" int dre_mpc_math_selftest(int32_t n, const double *x_dev, double *rcp_out_dev, void *stream)
+{
+    if (n <= 0 || !x_dev || !rcp_out_dev) return DRE_ERR_INVALID;
+    mpc_math_selftest_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, x_dev, rcp_out_dev);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
 int dre_mpc_reset_launch(const MpcDeviceState &st, const uint8_t *mask, cudaStream_t s)
 {
     mpc_reset_kernel<<<(st.N + 255) / 256, 256, 0, s>>>(st.iteration0, mask, st.N);

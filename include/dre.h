@@ -261,6 +261,8 @@ int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_
  * reset, order {ha_step, pt_step, mpc_solve, mpc_stats}, and the number of profiled steps. */
 int dre_env_set_profiling(dre_env *h, int32_t on);
 int dre_env_kernel_ms(dre_env *h, double *ms4, int64_t *steps, int32_t reset);
+/* Accuracy self-test of the MPC kernel's own 1/x (hardware seed + two Newton steps): evaluates it for n device doubles */
+int dre_mpc_math_selftest(int32_t n, const double *x_dev, double *rcp_out_dev, void *stream);
 /* FMA-chain microbenchmark of the CUDA-core peaks on the current device: kind 0 = fp32, 1 = fp64 -> TFLOP/s */
 int dre_measure_peak(int32_t kind, double *tflops);
 

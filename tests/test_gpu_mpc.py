@@ -100,3 +100,24 @@ def test_reset_mask_and_full_size_properties(golden_mpc):
     m.reset(mask)
     _, _, it0 = m.get_warm()
     assert (it0[::2] == 1).all() and (it0[1::2] == 0).all()
+
+
+def test_kernel_reciprocal_accuracy():
+    """The MPC kernel's own 1/x (hardware seed + two Newton steps; used for every quotient that does not carry reference
+    semantics) over the magnitudes Jacobians, barrier gradients and ratios can present: within 2 ulp."""
+    import ctypes
+    import torch
+    from dr_mpc_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-2, 2, 200000), 10.0 ** rng.uniform(-200, 200, 200000) * rng.choice([-1.0, 1.0], 200000),
+                        np.array([1.0, -1.0, 0.5, 3.0, 1e-7, 1 - 1e-7, 2.0 ** -1000, 2.0 ** 1000])])
+    x = x[x != 0]
+    xd = torch.as_tensor(x, device="cuda")
+    rc = torch.empty_like(xd)
+    _lib.check(L.dre_mpc_math_selftest(x.size, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(rc.data_ptr()), None))
+    torch.cuda.synchronize()
+    r = rc.cpu().numpy()
+    err = np.abs(r * x - 1.0)
+    print("rcp_fast max |x r - 1| = %.2e" % err.max())
+    assert err.max() <= 2 * np.finfo(np.float64).eps

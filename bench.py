@@ -80,6 +80,25 @@ def cpu_env_steps_per_sec(a, envs, budget_s, threads):
     return envs * steps / dt, steps, dt
 
 
+def cpu_c1_single_env(a, budget_s=2.0):
+    """BASELINE config 1: the default scenario's shape (1 env, 6 humans, K = 4) on ONE host core, oracle port."""
+    import importlib.util
+    from oracle import oracle as O
+    spec = importlib.util.spec_from_file_location("dre_paths", os.path.join(REPO, "dr-mpc_b200", "paths.py"))
+    P = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(P)
+    O.build()
+    tab, lens = P.pack_paths(P.continuous_task_paths())
+    env = O.EnvRef(1, 6, tab, lens, K=4)
+    arr = env.reset(nthreads=1)
+    act = arr["mpc_actions"][:, :2].copy()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        arr = env.step(act, nthreads=1); act = arr["mpc_actions"][:, :2].copy()
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -358,7 +377,10 @@ def run_ours(a):
         threads = os.cpu_count() or 1
         v, nst, dt = cpu_env_steps_per_sec(a, a.cpu_envs, 12.0, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{a.cpu_envs} of the {E} envs x {Nh} humans, {nst} steps ({dt:.1f} s), oracle/env_ref.c with OpenMP over envs"}
+                        "sample": f"{a.cpu_envs} of the {E} envs x {Nh} humans, {nst} steps ({dt:.1f} s), oracle/env_ref.c with OpenMP over envs",
+                        "c1_single_env_1core": {"value": cpu_c1_single_env(a), "unit": UNIT,
+                                                "what": "BASELINE configs[0] shape: 1 env x 6 humans, K = 4, one host core, same oracle port "
+                                                        "(the reference's own Python on the API shims does ~43 env-steps/s on this shape)"}}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),

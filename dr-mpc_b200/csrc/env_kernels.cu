@@ -9,13 +9,15 @@
 //                    poses, 2 localisations, PT rewards (reward_comp.py:20-116), optional path switch
 //                    (HA_and_PT env.py:130-141), PT state (path_tracking_core.py:94-145).
 //   ha_step_kernel : HAEnv.step / warm_start (reference human_avoidance_env.py:128-186, 79-125) for EPB envs per CTA:
-//                    ORCA pass 1 (robot at its previous pose) -> human Euler integration -> history roll -> ORCA pass 2
-//                    (disturbance look-ahead, :245) -> collision / safety / disturbance / actuation rewards (:189-291)
-//                    -> merge with the PT rewards / dones (HA_and_PT env.py:311-416), episode statistics
-//                    -> observation (:24-77) -> goal resampling (:181-184, crowd_sim.py:114-144 with Philox).
+//                    ORCA pass 1 (robot at its previous pose) -> human Euler integration -> history roll (+ sensor range)
+//                    -> observation (:24-77; final here, it does not need the look-ahead) -> ORCA pass 2 (disturbance
+//                    look-ahead, :245) -> collision / safety / disturbance / actuation rewards (:189-291) -> merge with
+//                    the PT rewards / dones (HA_and_PT env.py:311-416), episode statistics -> goal resampling
+//                    (:181-184, crowd_sim.py:114-144 with Philox).
 //                    The env's agents live in a shared-memory fp32 SoA tile for both ORCA passes. For the host path the
 //                    last CTA of every chunk of envs raises a flag in mapped host memory, so the D2H copy of a chunk's
 //                    observations starts while later CTAs of the same launch are still computing.
+//   cvmm_filter_kernel : cvmm_diverse_safety_pipeline / cvmm_safety_check (HA_and_PT env.py:422-513), one warp per env.
 //   env_reset_kernel : reset_continuous_task (HA_and_PT env.py:263-280) + HAEnv.reset (:297-338) + spawning
 //                    (crowd_sim.py:232-262 with Philox).
 #include <cstdlib>

@@ -5,7 +5,8 @@
 // sorted by squared distance, one half-plane per neighbour, LP2 with LP3 fallback), in the same
 // fp32 operation order, but with the G lanes of a group working on the neighbours / lines in
 // parallel: distances, ranking and half-plane construction are per-lane; LP1's scan over earlier
-// lines is a min/max reduction with shuffles; LP2/LP3 find the next violated line with a ballot.
+// lines is a min/max reduction (REDUX, or done redundantly per lane when short); LP2 and LP3 share one
+// loop body and find the next violated line with a per-lane scan + one REDUX.MIN.
 // This translation unit must be compiled with -fmad=false so every operation rounds once like the
 // SSE build of RVO2 (bit-exact parity with the oracle).
 #pragma once

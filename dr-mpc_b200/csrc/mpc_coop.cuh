@@ -76,26 +76,42 @@ __device__ __forceinline__ double wrap_angle(double a)
     return a - (2.0 * DRE_PI) * rint(a * (1.0 / (2.0 * DRE_PI)));
 }
 
+// Polynomial coefficients live in constant memory: a 64-bit immediate costs two extra MOVs per DFMA, a constant-bank
+// operand costs none (the kernel is instruction-fetch bound, see sincos_full).
+static __constant__ double DRE_PS[7] = {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0,
+                                        -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};                       // sin: -1/15! .. -1/3!
+static __constant__ double DRE_PC[7] = {1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0,
+                                        1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0};                      // cos: 1/16! .. 1/4!
+static __constant__ double DRE_PL[12] = {2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0,
+                                         2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0, 1.9082149292705877e-10, 0.693147180369123816490};   // 2 atanh, ln2 lo / hi
+
+// One out-of-line copy of the full-range sincos (rare: |x| > 0.5). The kernel is instruction-fetch bound when every warp
+// is busy (154 KB of SASS before the diet: 59 % i-cache hit rate in the post-path-switch steps), so rare paths stay out
+// of the hot loop's footprint.
+__device__ __noinline__ void sincos_full(double x, double *sn, double *cs) { sincos(x, sn, cs); }
+
+__device__ __noinline__ double atan2_full(double y, double x) { return atan2(y, x); }
+// se2_from_pose_inv of mpc_device.cuh through the shared sincos copy (once per problem, not in the LM loop)
+__device__ __forceinline__ Se2 se2_from_pose_inv_ool(double x, double y, double th)
+{
+    double sn, cs;
+    sincos_full(th, &sn, &cs);
+    Se2 r;
+    r.c = cs; r.s = -sn;
+    r.x = -(cs * x + sn * y);
+    r.y = sn * x - cs * y;
+    return r;
+}
+
 // sin and cos for |x| <= 0.5 by Taylor series (truncation < 5e-17 relative); larger arguments fall back
 __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs)
 {
-    if (fabs(x) > 0.5) { sincos(x, sn, cs); return; }
+    if (fabs(x) > 0.5) { sincos_full(x, sn, cs); return; }
     const double z = x * x;
-    double ps = -1.0 / 1307674368000.0;                 // -1/15!
-    ps = fma(ps, z, 1.0 / 6227020800.0);                // +1/13!
-    ps = fma(ps, z, -1.0 / 39916800.0);                 // -1/11!
-    ps = fma(ps, z, 1.0 / 362880.0);                    // +1/9!
-    ps = fma(ps, z, -1.0 / 5040.0);                     // -1/7!
-    ps = fma(ps, z, 1.0 / 120.0);                       // +1/5!
-    ps = fma(ps, z, -1.0 / 6.0);                        // -1/3!
+    double ps = DRE_PS[0], pc = DRE_PC[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) { ps = fma(ps, z, DRE_PS[i]); pc = fma(pc, z, DRE_PC[i]); }
     *sn = fma(x * z, ps, x);
-    double pc = 1.0 / 20922789888000.0;                 // +1/16!
-    pc = fma(pc, z, -1.0 / 87178291200.0);              // -1/14!
-    pc = fma(pc, z, 1.0 / 479001600.0);                 // +1/12!
-    pc = fma(pc, z, -1.0 / 3628800.0);                  // -1/10!
-    pc = fma(pc, z, 1.0 / 40320.0);                     // +1/8!
-    pc = fma(pc, z, -1.0 / 720.0);                      // -1/6!
-    pc = fma(pc, z, 1.0 / 24.0);                        // +1/4!
     *cs = fma(z * z, pc, fma(z, -0.5, 1.0));
 }
 
@@ -110,6 +126,32 @@ __device__ __forceinline__ double rcp_fast(double x)
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
+// ln x for 0 < x <= 1 in ~35 instructions (CUDA's log() is ~90 and there are four per cost evaluation): x = 2^e m with
+// m in [sqrt(1/2), sqrt(2)), ln m = 2 atanh(s), s = (m - 1)/(m + 1), |s| < 0.1716 -> 10 odd terms (truncation < 3e-17).
+// Measured against log() over (1e-9, 1]: <= 2 ulp (tests/test_gpu_mpc.py). Subnormal arguments take the library routine.
+__device__ __noinline__ double log_full(double x) { return log(x); }
+__device__ __forceinline__ double log_unit(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    if (hi < 0x00100000) return log_full(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s;
+    double q = DRE_PL[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) q = fma(q, z, DRE_PL[i]);
+    const double ed = (double)e;
+    // ln 2 split: hi part exact in 32 bits of mantissa so ed * hi is exact
+    const double r = fma(s * z, q, fma(ed, DRE_PL[10], 2.0 * s));
+    return fma(ed, DRE_PL[11], r);
+}
+// barrier_val of mpc_device.cuh with the compact logarithm
+__device__ __forceinline__ double barrier_val_fast(double x) { return x <= 0.0 ? -500.0 : (x > 1.0 ? 500.0 : log_unit(x)); }
+
 // half_cot / phi_coef / barrier_grad of mpc_device.cuh with reciprocal-multiplies
 __device__ __forceinline__ double half_cot_fast(double p, double sn, double cs)
 {
@@ -173,8 +215,9 @@ __device__ __forceinline__ Se2h se2h_step(double rx, double ry, double p, const 
 }
 
 // per-lane cost of step k: pose + kinematic + 4 barriers (mpc.py:99-142)
+// bv[0..3]: the four barrier values at u, reused by the linearisation if this state becomes the current one
 __device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2h &Tprev, const Se2h &Tk1, const double u[2],
-                                                 const Se2h &Mk, double inv_s)
+                                                 const Se2h &Mk, double inv_s, double bv[4])
 {
     double e[3], ct;
     se2_log_known(se2_mul_inv(Mk.T, Tk1.T), wrap_angle(Mk.th - Tk1.th), e, ct);
@@ -186,9 +229,10 @@ __device__ __forceinline__ double coop_lane_cost(const MpcConst &C, const Se2h &
     const Se2 E = se2_mul(se2_mul_inv(Tk1.T, Tprev.T), se2_exp_x(C.dt * u[0], p, sn, cs, q));
     se2_log_known(E, wrap_angle(Tk1.th - Tprev.th + p), e, ct);
     cost += 0.5 * 1000.0 * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-    const double b0 = barrier_val((C.vmax - u[0]) * C.inv_vmax), b1 = barrier_val(u[0] * C.inv_vmax);
-    const double b2 = barrier_val((C.wmax - u[1]) * C.inv_2wmax), b3 = barrier_val((u[1] + C.wmax) * C.inv_2wmax);
+    const double b0 = barrier_val_fast((C.vmax - u[0]) * C.inv_vmax), b1 = barrier_val_fast(u[0] * C.inv_vmax);
+    const double b2 = barrier_val_fast((C.wmax - u[1]) * C.inv_2wmax), b3 = barrier_val_fast((u[1] + C.wmax) * C.inv_2wmax);
     cost += 0.5 * 0.1 * (1.0 / 250000.0) * (b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3);
+    bv[0] = b0; bv[1] = b1; bv[2] = b2; bv[3] = b3;
     return cost;
 }
 
@@ -197,18 +241,19 @@ struct CoopCol {
     double *col;
     __device__ double &operator[](int i) const { return col[i * DRE_MPC_CTA]; }
 };
-enum { CS_D = 0, CS_O = 15, CS_B = 30, CS_TI = 35, CS_UI = 40, CS_SLOTS = 42 };   // D 15, O 15, b 5, Tinit (c,s,x,y,th), uinit 2
+enum { CS_D = 0, CS_O = 15, CS_B = 30, CS_TI = 35, CS_UI = 40, CS_BV = 42, CS_SLOTS = 50 };   // D 15, O 15, b 5, Tinit (c,s,x,y,th), uinit 2,
+                                                                                              // barrier values of the current / the trial state 2 x 4
 
 struct CoopFactor {
-    double L[15];   // Cholesky factor of the Schur complement, diagonal slots hold the INVERSE pivots
-    double B[15];   // O L_{prev}^{-T}
+    double L[6];    // Cholesky factor of the reduced 3x3 pose pivot block (packed lower; diagonal slots hold INVERSE pivots)
+    double B[9];    // reduced coupling block, then (in place) coupling * L_{prev}^{-T}
 };
 
 // Build block row k into the shared-memory column (lane 0's T_k is the locked current pose: no coupling and no
 // contribution to a previous block). Returns this lane's |b_k|^2.
 template <int G>
 __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const MpcConst &C, const Se2h &Tprev, const Se2h &Tk1,
-                                                  const double u[2], const Se2h &Mk, double s, bool act, const CoopCol &M)
+                                                  const double u[2], const Se2h &Mk, double s, bool act, const CoopCol &M, int bv_slot)
 {
     const int k = g.lane;
     const bool first = k == 0;
@@ -268,8 +313,8 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
         const double x0 = (C.vmax - v) * C.inv_vmax, x1 = v * C.inv_vmax;
         const double x2 = (C.wmax - w) * C.inv_2wmax, x3 = (w + C.wmax) * C.inv_2wmax;
         const double k500 = 1.0 / 500.0;
-        const double e0 = barrier_val(x0) * k500, e1 = barrier_val(x1) * k500;
-        const double e2 = barrier_val(x2) * k500, e3 = barrier_val(x3) * k500;
+        // the barrier values of this state were computed by the cost evaluation that made it the current state
+        const double e0 = M[bv_slot] * k500, e1 = M[bv_slot + 1] * k500, e2 = M[bv_slot + 2] * k500, e3 = M[bv_slot + 3] * k500;
         const double j0 = -k500 * barrier_grad_fast(x0) * C.inv_vmax, j1 = k500 * barrier_grad_fast(x1) * C.inv_vmax;
         const double j2 = -k500 * barrier_grad_fast(x2) * C.inv_2wmax, j3 = k500 * barrier_grad_fast(x3) * C.inv_2wmax;
         b[0] -= 0.1 * (j0 * e0 + j1 * e1);
@@ -303,91 +348,133 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
     return bb;
 }
 
-// Damped block-tridiagonal Cholesky as a K-stage lane pipeline. Returns false (group-uniform) on a non-positive pivot.
-// The diagonal slots of R.L hold the INVERSE pivots 1/l_cc (computed with one rsqrt per pivot): every later use of a
-// pivot is a division, so the dependent chain of a stage is multiplications only.
+// Lu^{-1} applied to the control rows of block row k: Wv = Lu^{-1} V^T, Wo = Lu^{-1} O_u, wb = Lu^{-1} b_u (Lu = [1/i0, 0; l10, 1/i1])
+__device__ __forceinline__ void coop_control_rows(const CoopCol &M, double i0, double l10, double i1, double wv0[3], double wv1[3],
+                                                  double wo0[3], double wo1[3], double &wb0, double &wb1)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        wv0[a] = M[CS_D + (2 + a) * (3 + a) / 2] * i0;
+        wv1[a] = (M[CS_D + (2 + a) * (3 + a) / 2 + 1] - l10 * wv0[a]) * i1;
+        wo0[a] = M[CS_O + a] * i0;
+        wo1[a] = (M[CS_O + 3 + a] - l10 * wo0[a]) * i1;
+    }
+    wb0 = M[CS_B] * i0;
+    wb1 = (M[CS_B + 1] - l10 * wb0) * i1;
+}
+
+// Damped block-tridiagonal solve (A with diag * (1 + lambda)) d = b. Returns false (group-uniform) on a non-positive pivot.
+//
+// Block row k couples [u_k (2); p_k (3)] with p_{k-1} only, so the controls are eliminated first, by every lane at once
+// (2x2 Cholesky, Schur complement onto p_k and, by one shuffle, onto p_{k-1}); what is left for the K sequential pipeline
+// stages is a block-tridiagonal system of 3x3 blocks in the poses -- less than half the dependent fp64 chain of 5x5 stages.
+// Diagonal slots of the factors hold the INVERSE pivots (one rsqrt per pivot; every later use is a multiplication).
 template <int G>
 __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, const CoopCol &M, CoopFactor &R, double lambda, double d[5])
 {
     const double damp = 1.0 + lambda;
-    double y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     bool ok = true;
+    const bool has_next = g.lane + 1 < K;
+    // ---- (1) controls: U = Lu Lu^T, Wv = Lu^{-1} V^T, Wo = Lu^{-1} O_u, wb = Lu^{-1} b_u
+    double u00 = M[CS_D + 0] * damp, t11;
+    if (!(u00 > 0.0)) { ok = false; u00 = 1.0; }
+    const double i0 = rsqrt(u00), l10 = M[CS_D + 1] * i0;
+    t11 = M[CS_D + 2] * damp - l10 * l10;
+    if (!(t11 > 0.0)) { ok = false; t11 = 1.0; }
+    const double i1 = rsqrt(t11);
+    double wv0[3], wv1[3], wo0[3], wo1[3], wb0, wb1;
+    coop_control_rows(M, i0, l10, i1, wv0, wv1, wo0, wo1, wb0, wb1);
+    // reduced pose system: P_k = P - Wv^T Wv - (Wo^T Wo of lane k+1), C_k = O_p - Wv^T Wo, r_k = b_p - Wv^T wb - (Wo^T wb of lane k+1)
+    double P[6], r[3];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) { R.L[i] = 0.0; R.B[i] = 0.0; }
-    R.L[0] = R.L[2] = R.L[5] = R.L[9] = R.L[14] = 1.0;
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+            const double nx = g.down(wo0[a] * wo0[c] + wo1[a] * wo1[c]);
+            double v = M[CS_D + (2 + a) * (3 + a) / 2 + 2 + c];
+            if (a == c) v *= damp;
+            v -= wv0[a] * wv0[c] + wv1[a] * wv1[c];
+            if (has_next) v -= nx;
+            P[a * (a + 1) / 2 + c] = v;
+        }
+        const double nb = g.down(wo0[a] * wb0 + wo1[a] * wb1);
+        double v = M[CS_B + 2 + a] - (wv0[a] * wb0 + wv1[a] * wb1);
+        if (has_next) v -= nb;
+        r[a] = v;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R.B[3 * a + c] = M[CS_O + 3 * (2 + a) + c] - (wv0[a] * wo0[c] + wv1[a] * wo1[c]);
+    }
+    // ---- (2) forward pipeline over the 3x3 pose blocks
+    double y[3] = {0.0, 0.0, 0.0};
+    R.L[0] = R.L[2] = R.L[5] = 1.0; R.L[1] = R.L[3] = R.L[4] = 0.0;
     for (int j = 0; j < K; ++j) {
-        // factor rows 2..4 and the forward-substituted rhs of the previous block
-        const double i22 = g.up(R.L[5]), l32 = g.up(R.L[8]), i33 = g.up(R.L[9]);
-        const double l42 = g.up(R.L[12]), l43 = g.up(R.L[13]), i44 = g.up(R.L[14]);
-        const double y2 = g.up(y[2]), y3 = g.up(y[3]), y4 = g.up(y[4]);
+        const double q00 = g.up(R.L[0]), q10 = g.up(R.L[1]), q11 = g.up(R.L[2]);
+        const double q20 = g.up(R.L[3]), q21 = g.up(R.L[4]), q22 = g.up(R.L[5]);
+        const double y0 = g.up(y[0]), y1 = g.up(y[1]), y2 = g.up(y[2]);
         if (g.lane == j) {
-            double S[15], rhs[5];
-#pragma unroll
-            for (int i = 0; i < 15; ++i) S[i] = M[CS_D + i];
-            S[0] *= damp; S[2] *= damp; S[5] *= damp; S[9] *= damp; S[14] *= damp;
-#pragma unroll
-            for (int a = 0; a < 5; ++a) rhs[a] = M[CS_B + a];
             if (j > 0) {
 #pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    const double b2 = M[CS_O + 3 * a] * i22;
-                    const double b3 = (M[CS_O + 3 * a + 1] - b2 * l32) * i33;
-                    const double b4 = (M[CS_O + 3 * a + 2] - b2 * l42 - b3 * l43) * i44;
-                    R.B[3 * a] = b2; R.B[3 * a + 1] = b3; R.B[3 * a + 2] = b4;
+                for (int a = 0; a < 3; ++a) {
+                    const double b0 = R.B[3 * a] * q00;
+                    const double b1 = (R.B[3 * a + 1] - b0 * q10) * q11;
+                    const double b2 = (R.B[3 * a + 2] - b0 * q20 - b1 * q21) * q22;
+                    R.B[3 * a] = b0; R.B[3 * a + 1] = b1; R.B[3 * a + 2] = b2;
                 }
 #pragma unroll
-                for (int a = 0; a < 5; ++a) {
+                for (int a = 0; a < 3; ++a) {
 #pragma unroll
                     for (int c = 0; c <= a; ++c)
-                        S[a * (a + 1) / 2 + c] -= R.B[3 * a] * R.B[3 * c] + R.B[3 * a + 1] * R.B[3 * c + 1] + R.B[3 * a + 2] * R.B[3 * c + 2];
-                    rhs[a] -= R.B[3 * a] * y2 + R.B[3 * a + 1] * y3 + R.B[3 * a + 2] * y4;
+                        P[a * (a + 1) / 2 + c] -= R.B[3 * a] * R.B[3 * c] + R.B[3 * a + 1] * R.B[3 * c + 1] + R.B[3 * a + 2] * R.B[3 * c + 2];
+                    r[a] -= R.B[3 * a] * y0 + R.B[3 * a + 1] * y1 + R.B[3 * a + 2] * y2;
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                double dd = S[c * (c + 1) / 2 + c];
+            for (int c = 0; c < 3; ++c) {
+                double dd = P[c * (c + 1) / 2 + c];
 #pragma unroll
                 for (int m = 0; m < c; ++m) dd -= R.L[c * (c + 1) / 2 + m] * R.L[c * (c + 1) / 2 + m];
                 if (!(dd > 0.0)) { ok = false; dd = 1.0; }
                 const double ild = rsqrt(dd);
                 R.L[c * (c + 1) / 2 + c] = ild;
 #pragma unroll
-                for (int a = c + 1; a < 5; ++a) {
-                    double v = S[a * (a + 1) / 2 + c];
+                for (int a = c + 1; a < 3; ++a) {
+                    double v = P[a * (a + 1) / 2 + c];
 #pragma unroll
                     for (int m = 0; m < c; ++m) v -= R.L[a * (a + 1) / 2 + m] * R.L[c * (c + 1) / 2 + m];
                     R.L[a * (a + 1) / 2 + c] = v * ild;
                 }
             }
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                double v = rhs[a];
-#pragma unroll
-                for (int m = 0; m < a; ++m) v -= R.L[a * (a + 1) / 2 + m] * y[m];
-                y[a] = v * R.L[a * (a + 1) / 2 + a];
-            }
+            y[0] = r[0] * R.L[0];
+            y[1] = (r[1] - R.L[1] * y[0]) * R.L[2];
+            y[2] = (r[2] - R.L[3] * y[0] - R.L[4] * y[1]) * R.L[5];
         }
     }
     ok = !g.any(!ok);
-    // back substitution: L_j^T d_j = y_j - B_{j+1}^T d_{j+1}
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    // ---- (3) back substitution over the poses: L_j^T p_j = y_j - B_{j+1}^T p_{j+1}
+    double p[3] = {0.0, 0.0, 0.0}, t0 = 0.0, t1 = 0.0, t2 = 0.0;
     for (int j = K - 1; j >= 0; --j) {
         const double r0 = g.down(t0), r1 = g.down(t1), r2 = g.down(t2);
         if (g.lane == j) {
-            double rhs[5] = {y[0], y[1], y[2], y[3], y[4]};
-            if (j + 1 < K) { rhs[2] -= r0; rhs[3] -= r1; rhs[4] -= r2; }
-#pragma unroll
-            for (int a = 4; a >= 0; --a) {
-                double v = rhs[a];
-#pragma unroll
-                for (int m = a + 1; m < 5; ++m) v -= R.L[m * (m + 1) / 2 + a] * d[m];
-                d[a] = v * R.L[a * (a + 1) / 2 + a];
-            }
-            t0 = t1 = t2 = 0.0;
-#pragma unroll
-            for (int m = 0; m < 5; ++m) { t0 += R.B[3 * m] * d[m]; t1 += R.B[3 * m + 1] * d[m]; t2 += R.B[3 * m + 2] * d[m]; }
+            double h0 = y[0], h1 = y[1], h2 = y[2];
+            if (j + 1 < K) { h0 -= r0; h1 -= r1; h2 -= r2; }
+            p[2] = h2 * R.L[5];
+            p[1] = (h1 - R.L[4] * p[2]) * R.L[2];
+            p[0] = (h0 - R.L[1] * p[1] - R.L[3] * p[2]) * R.L[0];
+            t0 = R.B[0] * p[0] + R.B[3] * p[1] + R.B[6] * p[2];
+            t1 = R.B[1] * p[0] + R.B[4] * p[1] + R.B[7] * p[2];
+            t2 = R.B[2] * p[0] + R.B[5] * p[1] + R.B[8] * p[2];
         }
     }
+    // ---- (4) controls back: Lu^T u = wb - Wv p_k - Wo p_{k-1}   (lane 0 has Wo = 0)
+    // (Wv, Wo, wb are recomputed from the shared-memory column: 21 multiply-adds instead of 14 registers held across the pipeline)
+    const double pp0 = g.up(p[0]), pp1 = g.up(p[1]), pp2 = g.up(p[2]);
+    double xv0[3], xv1[3], xo0[3], xo1[3], xb0, xb1;
+    coop_control_rows(M, i0, l10, i1, xv0, xv1, xo0, xo1, xb0, xb1);
+    const double w0 = xb0 - (xv0[0] * p[0] + xv0[1] * p[1] + xv0[2] * p[2]) - (xo0[0] * pp0 + xo0[1] * pp1 + xo0[2] * pp2);
+    const double w1 = xb1 - (xv1[0] * p[0] + xv1[1] * p[1] + xv1[2] * p[2]) - (xo1[0] * pp0 + xo1[1] * pp1 + xo1[2] * pp2);
+    d[1] = w1 * i1;
+    d[0] = (w0 - l10 * d[1]) * i0;
+    d[2] = p[0]; d[3] = p[1]; d[4] = p[2];
     return ok;
 }
 
@@ -444,6 +531,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
     double s = 1.0, lambda = 1e-7, curr = 0.0, prev = 0.0, gn = 0.0;
     int iter = 0, nb = 0, retries = 0, term = 0, lm_solves = 0, cost_evals = 0, zero_steps = 0;
     bool need_cost0 = true, need_build = false;
+    int bv_cur = CS_BV;   // which of the two barrier-value slot sets belongs to the current state
     T0.T.c = 1.0; T0.T.s = 0.0; T0.T.x = 0.0; T0.T.y = 0.0; T0.th = 0.0;
     Mk = T0; Tk1 = T0;
 
@@ -463,13 +551,13 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 const double *path = B.paths + (size_t)pid * 3 * B.path_stride;
                 const int L = B.lens[pid];
                 const double *ps = B.pose + (size_t)n * B.pose_stride;
-                T0.T = se2_from_pose_inv(ps[0], ps[1], ps[2]);
+                T0.T = se2_from_pose_inv_ool(ps[0], ps[1], ps[2]);
                 T0.th = -ps[2];
                 double target = B.interp_index[n] + inc;
                 for (int i = 0; i < k && i < K; ++i) target += inc;      // accumulate like the reference loop (mpc.py:214,224)
                 double r[3];
                 mpc_ref_pose(path, B.path_stride, L, target, r);
-                Mk.T = se2_from_pose_inv(r[0], r[1], r[2]);
+                Mk.T = se2_from_pose_inv_ool(r[0], r[1], r[2]);
                 Mk.th = -r[2];
                 const bool first_call = (B.iteration0[n] != 0);
                 if (first_call || !act) { Tk1 = Mk; u[0] = prm.v_max / 2.0; u[1] = 0.0; }   // mpc.py:68-71
@@ -477,7 +565,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                     const double4 w = B.warm_T[(size_t)n * K + k];
                     const double2 uu = B.warm_u[(size_t)n * K + k];
                     Tk1.T.c = w.x; Tk1.T.s = w.y; Tk1.T.x = w.z; Tk1.T.y = w.w;
-                    Tk1.th = atan2(w.y, w.x);
+                    Tk1.th = atan2_full(w.y, w.x);
                     u[0] = uu.x; u[1] = uu.y;
                 }
                 // the initial guess is needed again only by the pose_error_scaling retry (mpc.py:188-190)
@@ -488,14 +576,23 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 need_cost0 = true; need_build = false;
             }
         }
+#ifndef DRE_MPC_NO_CTA_SYNC
+        // keep the CTA's warps on the same stretch of code (shared i-cache lines): one barrier per LM attempt
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+        if (!have) continue;
+#else
         if (!have) break;
+#endif
         if (TRACE) { tr[6] += 1; tr[7] += __popc(__activemask()) / G; }
         DRE_TR(0);
 
         // ---- LM state machine: one damped solve + up to two trials per loop iteration (lev_marq...py:43-134) ----
         if (need_cost0) {
             const Se2h Tp = lane_up(g, Tk1);
-            const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tk1, u, Mk, 1.0 / s) : 0.0;
+            double bv[4] = {0.0, 0.0, 0.0, 0.0};
+            const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tk1, u, Mk, 1.0 / s, bv) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) M[bv_cur + i] = bv[i];
             curr = g.sum_ordered(c, K);
             need_cost0 = false; need_build = true;
         }
@@ -503,7 +600,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         if (need_build) {
             ++iter; prev = curr; nb = 0; need_build = false;
             const Se2h Tp = lane_up(g, Tk1);
-            const double bb = coop_lane_build(g, C, k == 0 ? T0 : Tp, Tk1, u, Mk, s, act, M);
+            const double bb = coop_lane_build(g, C, k == 0 ? T0 : Tp, Tk1, u, Mk, s, act, M, bv_cur);
             gn = sqrt(g.sum_ordered(act ? bb : 0.0, K));
         }
         DRE_TR(2);
@@ -526,11 +623,12 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 const double maxp = dp > 0.0 ? (hi - 1e-7) - uc : (lo + 1e-7) - uc;
                 allowed[c] = (dp != 0.0 && act) ? maxp / dp : INFINITY;   // IEEE: the 1e-7 margins of the box are part of the semantics
             }
+            // a quotient >= 1 leaves the running scale untouched, so the walk only happens when some control would leave its box
             double scale = 1.0;
-            for (int kk = 0; kk < K; ++kk) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const double al = g.bcast(allowed[c], kk);
+            if (g.any(allowed[0] < 1.0 || allowed[1] < 1.0)) {
+#pragma unroll 1
+                for (int kk = 0; kk < 2 * K; ++kk) {
+                    const double al = g.bcast((kk & 1) ? allowed[1] : allowed[0], kk >> 1);
                     scale = fmin(scale, al);
                     if (al < 1.0) scale = fmax(scale - 1e-7, 0.0);
                 }
@@ -542,6 +640,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             // (lev_marq...py:110-113) -> both are rejected. Skip the two cost evaluations, keep the counters.
             if (scale == 0.0) { cost_evals += 2; ++zero_steps; }
             double lin = 0.0, quad = 0.0;
+#pragma unroll 1
             for (int bt = 0; bt < 2 && scale != 0.0; ++bt) {
                 if (bt > 0) {
 #pragma unroll
@@ -550,7 +649,10 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 ut[0] = u[0] + d[0]; ut[1] = u[1] + d[1];
                 Tt = se2h_step(d[2], d[3], d[4], Tk1);
                 const Se2h Tp = lane_up(g, Tt);
-                const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tt, ut, Mk, 1.0 / s) : 0.0;
+                double bv[4] = {0.0, 0.0, 0.0, 0.0};
+                const double c = act ? coop_lane_cost(C, k == 0 ? T0 : Tp, Tt, ut, Mk, 1.0 / s, bv) : 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) M[(bv_cur ^ (CS_BV ^ (CS_BV + 4))) + i] = bv[i];
                 proposed = g.sum_ordered(c, K);
                 ++cost_evals;
                 // predicted reduction b^T p - 1/2 p^T A p with the undamped A (lev_marq...py:167-171). The second trial's
@@ -579,6 +681,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         DRE_TR(4);
         if (success) {
             Tk1 = Tt; u[0] = ut[0]; u[1] = ut[1];
+            bv_cur ^= CS_BV ^ (CS_BV + 4);
             lambda = fmax(lambda * 0.1, 1e-7);
             curr = proposed;
         } else {

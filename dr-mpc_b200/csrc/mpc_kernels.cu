@@ -50,6 +50,9 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
         int dev = 0, sms = 0, per_sm = 0;
         DRE_CUDA_TRY(cudaGetDevice(&dev));
         DRE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DRE_CUDA_TRY(cudaFuncSetAttribute(mpc_coop_kernel<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (G == 4 && MINB == 3)
+            DRE_CUDA_TRY(cudaFuncSetAttribute(mpc_coop_kernel<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, smem));
         resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }

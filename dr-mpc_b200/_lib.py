@@ -108,6 +108,7 @@ def load():
         L.dre_env_kernel_ms.argtypes = [c_vp, c_vp, c_vp, c_i32]
     L.dre_measure_peak.argtypes = [c_i32, P(c_d)]
     L.dre_mpc_math_selftest.argtypes = [c_i32, c_vp, c_vp, c_vp]
+    L.dre_mpc_math_selftest_fn.argtypes = [c_i32, c_i32, c_vp, c_vp, c_vp]
     _lib = L
     return L
 

@@ -169,6 +169,27 @@ __global__ void mpc_math_selftest_kernel(int n, const double *__restrict__ x, do
     if (i < n) rc[i] = rcp_fast(x[i]);
 }
 
+// fn: 0 = rcp_fast, 1 = barrier_val_fast (compact ln with the reference's clamps), 2 / 3 = sin / cos of sincos_small
+__global__ void mpc_math_selftest_fn_kernel(int fn, int n, const double *__restrict__ x, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sn, cs;
+    switch (fn) {
+    case 0: out[i] = rcp_fast(x[i]); break;
+    case 1: out[i] = barrier_val_fast(x[i]); break;
+    default: sincos_small(x[i], &sn, &cs); out[i] = fn == 2 ? sn : cs; break;
+    }
+}
+
+extern "C" int dre_mpc_math_selftest_fn(int32_t fn, int32_t n, const double *x_dev, double *out_dev, void *stream)
+{
+    if (fn < 0 || fn > 3 || n <= 0 || !x_dev || !out_dev) return DRE_ERR_INVALID;
+    mpc_math_selftest_fn_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(fn, n, x_dev, out_dev);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
 extern "C" int dre_mpc_math_selftest(int32_t n, const double *x_dev, double *rcp_out_dev, void *stream)
 {
     if (n <= 0 || !x_dev || !rcp_out_dev) return DRE_ERR_INVALID;

@@ -263,6 +263,9 @@ int dre_env_set_profiling(dre_env *h, int32_t on);
 int dre_env_kernel_ms(dre_env *h, double *ms4, int64_t *steps, int32_t reset);
 /* Accuracy self-test of the MPC kernel's own 1/x (hardware seed + two Newton steps): evaluates it for n device doubles */
 int dre_mpc_math_selftest(int32_t n, const double *x_dev, double *rcp_out_dev, void *stream);
+/* Same for the kernel's other in-house elementary functions: fn 0 = 1/x, 1 = barrier value (ln x on (0,1], -500 for x <= 0,
+ * 500 for x > 1: mpc.py's barrier), 2 / 3 = sin / cos of the small-angle routine (falls back to the library beyond 0.5 rad) */
+int dre_mpc_math_selftest_fn(int32_t fn, int32_t n, const double *x_dev, double *out_dev, void *stream);
 /* FMA-chain microbenchmark of the CUDA-core peaks on the current device: kind 0 = fp32, 1 = fp64 -> TFLOP/s */
 int dre_measure_peak(int32_t kind, double *tflops);
 

@@ -121,3 +121,40 @@ def test_kernel_reciprocal_accuracy():
     err = np.abs(r * x - 1.0)
     print("rcp_fast max |x r - 1| = %.2e" % err.max())
     assert err.max() <= 2 * np.finfo(np.float64).eps
+
+
+def test_kernel_elementary_functions_accuracy():
+    """The MPC kernel's compact ln (barrier terms) and small-angle sin/cos against numpy in float64: a few ulp, with the
+    reference barrier's clamps (mpc.py: -500 at or below 0, 500 above 1)."""
+    import ctypes
+    import torch
+    from dr_mpc_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(1)
+
+    def run(fn, x):
+        xd = torch.as_tensor(x, device="cuda")
+        out = torch.empty_like(xd)
+        _lib.check(L.dre_mpc_math_selftest_fn(fn, x.size, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    eps = np.finfo(np.float64).eps
+    x = np.concatenate([rng.uniform(0, 1, 300000), 10.0 ** rng.uniform(-12, 0, 300000), 1.0 - 10.0 ** rng.uniform(-16, -1, 100000),
+                        np.array([1.0, 0.5, 2.0 ** -0.5, np.nextafter(2.0 ** -0.5, 0), 1e-7, 1 - 1e-7, 1e-300, 5e-324, 2.2e-308])])
+    x = x[(x > 0) & (x <= 1)]
+    y = run(1, x)
+    ref = np.log(x)
+    err = np.abs(y - ref) / np.maximum(np.abs(ref), np.finfo(np.float64).tiny)
+    # near x = 1 the result is tiny: measure against the spacing of the argument as well (ln(1 - d) ~ -d)
+    ulp = np.abs(y - ref) / np.maximum(np.spacing(np.abs(ref)), eps * np.abs(1 - x))
+    print("ln: max rel %.2e, max ulp %.2f" % (err[ref != 0].max(), ulp[ref != 0].max()))
+    assert ulp[ref != 0].max() <= 4 and np.all(y[ref == 0] == 0)
+    assert np.array_equal(run(1, np.array([0.0, -1.0, -1e-300, 1.0 + 1e-15, 2.0, 1e300])), np.array([-500.0, -500.0, -500.0, 500.0, 500.0, 500.0]))
+    a = np.concatenate([rng.uniform(-0.5, 0.5, 300000), 10.0 ** rng.uniform(-300, -1, 100000), rng.uniform(-4, 4, 100000), np.array([0.0, 0.5, -0.5, 0.25])])
+    for fn, f in ((2, np.sin), (3, np.cos)):
+        y = run(fn, a)
+        ref = f(a)
+        u = np.abs(y - ref) / np.spacing(np.abs(ref))
+        print("%s: max ulp %.2f" % (f.__name__, u.max()))
+        assert u.max() <= 2

@@ -1,6 +1,6 @@
 // mpc_coop.cuh -- lane-per-horizon-step cooperative LM solve (the fast path of the MPC kernel).
 //
-// A group of G lanes (G = 4, 8, 16 or 32 >= K) owns one problem; lane k owns horizon step k: pose T_{k+1}, control
+// A group of G lanes (G = 4, 8, 16, 32, or 64 = a pair of warps, G >= K) owns one problem; lane k owns horizon step k: pose T_{k+1}, control
 // u_k, reference M_k and block row k of the block-tridiagonal normal equations (diagonal block D_k packed 5x5,
 // coupling block O_k 5x3, rhs b_k). Residuals, Jacobians and trial costs are embarrassingly parallel over lanes (the
 // neighbour pose comes by shuffle); the block Cholesky runs as K pipeline stages in which lane j consumes lane j-1's
@@ -36,9 +36,22 @@ struct LaneGroup {
         lane = (int)(wl & (G - 1));
         mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(unsigned)(G - 1)));
     }
+    __device__ void attach(double *) {}
     __device__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ int bcast_i(int v, int src) const { return __shfl_sync(mask, v, src, G); }
     __device__ double up(double v) const { return __shfl_up_sync(mask, v, 1, G); }
     __device__ double down(double v) const { return __shfl_down_sync(mask, v, 1, G); }
+    // N values from lane-1 / lane+1 (`boundary`: only the two-warp group cares, see LaneGroup<64>)
+    template <int N> __device__ void up_n(const double *in, double *out, bool boundary = true) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = up(in[i]);
+    }
+    template <int N> __device__ void down_n(const double *in, double *out, bool boundary = true) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = down(in[i]);
+    }
     __device__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
     // sum over lanes 0..K-1 in lane order (every lane gets the same bits)
     __device__ double sum_ordered(double v, int K) const
@@ -59,14 +72,102 @@ struct LaneGroup {
     }
 };
 
+// K > 32: one problem per PAIR of warps (lane = threadIdx & 63). Inside a warp everything is a shuffle as above; what crosses
+// the warp boundary (lane 31 <-> lane 32, broadcasts, votes, sums) goes through a small shared-memory exchange area and a
+// named barrier of the pair's 64 threads. The area is double-buffered by the parity of the operation count, so one barrier
+// per operation is enough (a warp cannot get two operations ahead of its partner). The pipeline stages of the solve hand
+// data across the boundary only at stage 32 (forward) / 31 (backward): the other stages pass `boundary = false`.
+template <>
+struct LaneGroup<64> {
+    unsigned mask;
+    int lane;
+    double *xch;          // [2][16] doubles of this pair
+    mutable int par;
+    int bar_id;
+    __device__ LaneGroup() : mask(0xffffffffu), lane((int)(threadIdx.x & 63u)), xch(nullptr), par(0), bar_id(1 + (int)(threadIdx.x >> 6)) {}
+    __device__ void attach(double *area) { xch = area + (threadIdx.x >> 6) * 32; }
+    __device__ void pair_sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+    __device__ double *buf() const { double *b = xch + par * 16; par ^= 1; return b; }
+    __device__ double bcast(double v, int src) const
+    {
+        double *b = buf();
+        if (lane == src) b[0] = v;
+        pair_sync();
+        return b[0];
+    }
+    __device__ int bcast_i(int v, int src) const
+    {
+        double *b = buf();
+        if (lane == src) reinterpret_cast<int *>(b)[0] = v;
+        pair_sync();
+        return reinterpret_cast<int *>(b)[0];
+    }
+    template <int N> __device__ void up_n(const double *in, double *out, bool boundary = true) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = __shfl_up_sync(0xffffffffu, in[i], 1);
+        if (boundary) {
+            double *b = buf();
+            if (lane == 31) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) b[i] = in[i];
+            }
+            pair_sync();
+            if (lane == 32) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) out[i] = b[i];
+            }
+        }
+    }
+    template <int N> __device__ void down_n(const double *in, double *out, bool boundary = true) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = __shfl_down_sync(0xffffffffu, in[i], 1);
+        if (boundary) {
+            double *b = buf();
+            if (lane == 32) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) b[i] = in[i];
+            }
+            pair_sync();
+            if (lane == 31) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) out[i] = b[i];
+            }
+        }
+    }
+    __device__ double up(double v) const { double r; up_n<1>(&v, &r); return r; }
+    __device__ double down(double v) const { double r; down_n<1>(&v, &r); return r; }
+    __device__ bool any(bool p) const
+    {
+        const unsigned w = __ballot_sync(0xffffffffu, p);
+        unsigned *b = reinterpret_cast<unsigned *>(buf());
+        if ((lane & 31) == 0) b[lane >> 5] = w;
+        pair_sync();
+        return (b[0] | b[1]) != 0u;
+    }
+    __device__ double sum_ordered(double v, int) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        double *b = buf();
+        if ((lane & 31) == 0) b[lane >> 5] = v;
+        pair_sync();
+        return b[0] + b[1];
+    }
+};
+
 // pose with its heading: th == atan2(s, c) modulo 2 pi, tracked additively
 struct Se2h { Se2 T; double th; };
 
 template <int G>
 __device__ __forceinline__ Se2h lane_up(const LaneGroup<G> &g, const Se2h &a)
 {
+    const double in[5] = {a.T.c, a.T.s, a.T.x, a.T.y, a.th};
+    double out[5];
+    g.template up_n<5>(in, out);
     Se2h r;
-    r.T.c = g.up(a.T.c); r.T.s = g.up(a.T.s); r.T.x = g.up(a.T.x); r.T.y = g.up(a.T.y); r.th = g.up(a.th);
+    r.T.c = out[0]; r.T.s = out[1]; r.T.x = out[2]; r.T.y = out[3]; r.th = out[4];
     return r;
 }
 
@@ -323,15 +424,18 @@ __device__ __forceinline__ double coop_lane_build(const LaneGroup<G> &g, const M
         D[2] += 0.1 * (j2 * j2 + j3 * j3);
     }
     // this step's kinematic term also lands on the previous block's delta-delta part: receive from lane k+1
+    {
+        const double snd[9] = {pc6[0], pc6[1], pc6[2], pc6[3], pc6[4], pc6[5], pcb[0], pcb[1], pcb[2]};
+        double rcv[9];
+        g.template down_n<9>(snd, rcv);
+        if (k + 1 < C.K) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double rb = g.down(pcb[a]);
+            for (int a = 0; a < 3; ++a) {
 #pragma unroll
-        for (int c = 0; c <= a; ++c) {
-            const double rv = g.down(pc6[a * (a + 1) / 2 + c]);
-            if (k + 1 < C.K) D[(2 + a) * (3 + a) / 2 + 2 + c] += rv;
+                for (int c = 0; c <= a; ++c) D[(2 + a) * (3 + a) / 2 + 2 + c] += rcv[a * (a + 1) / 2 + c];
+                b[2 + a] += rcv[6 + a];
+            }
         }
-        if (k + 1 < C.K) b[2 + a] += rb;
     }
     if (!act) {   // padding lanes: identity block, zero rhs
 #pragma unroll
@@ -386,31 +490,41 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, const C
     coop_control_rows(M, i0, l10, i1, wv0, wv1, wo0, wo1, wb0, wb1);
     // reduced pose system: P_k = P - Wv^T Wv - (Wo^T Wo of lane k+1), C_k = O_p - Wv^T Wo, r_k = b_p - Wv^T wb - (Wo^T wb of lane k+1)
     double P[6], r[3];
+    {
+        double snd[9], rcv[9];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < 3; ++a) {
 #pragma unroll
-        for (int c = 0; c <= a; ++c) {
-            const double nx = g.down(wo0[a] * wo0[c] + wo1[a] * wo1[c]);
-            double v = M[CS_D + (2 + a) * (3 + a) / 2 + 2 + c];
-            if (a == c) v *= damp;
-            v -= wv0[a] * wv0[c] + wv1[a] * wv1[c];
-            if (has_next) v -= nx;
-            P[a * (a + 1) / 2 + c] = v;
+            for (int c = 0; c <= a; ++c) snd[a * (a + 1) / 2 + c] = wo0[a] * wo0[c] + wo1[a] * wo1[c];
+            snd[6 + a] = wo0[a] * wb0 + wo1[a] * wb1;
         }
-        const double nb = g.down(wo0[a] * wb0 + wo1[a] * wb1);
-        double v = M[CS_B + 2 + a] - (wv0[a] * wb0 + wv1[a] * wb1);
-        if (has_next) v -= nb;
-        r[a] = v;
+        g.template down_n<9>(snd, rcv);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) R.B[3 * a + c] = M[CS_O + 3 * (2 + a) + c] - (wv0[a] * wo0[c] + wv1[a] * wo1[c]);
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int c = 0; c <= a; ++c) {
+                double v = M[CS_D + (2 + a) * (3 + a) / 2 + 2 + c];
+                if (a == c) v *= damp;
+                v -= wv0[a] * wv0[c] + wv1[a] * wv1[c];
+                if (has_next) v -= rcv[a * (a + 1) / 2 + c];
+                P[a * (a + 1) / 2 + c] = v;
+            }
+            double v = M[CS_B + 2 + a] - (wv0[a] * wb0 + wv1[a] * wb1);
+            if (has_next) v -= rcv[6 + a];
+            r[a] = v;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R.B[3 * a + c] = M[CS_O + 3 * (2 + a) + c] - (wv0[a] * wo0[c] + wv1[a] * wo1[c]);
+        }
     }
     // ---- (2) forward pipeline over the 3x3 pose blocks
     double y[3] = {0.0, 0.0, 0.0};
     R.L[0] = R.L[2] = R.L[5] = 1.0; R.L[1] = R.L[3] = R.L[4] = 0.0;
     for (int j = 0; j < K; ++j) {
-        const double q00 = g.up(R.L[0]), q10 = g.up(R.L[1]), q11 = g.up(R.L[2]);
-        const double q20 = g.up(R.L[3]), q21 = g.up(R.L[4]), q22 = g.up(R.L[5]);
-        const double y0 = g.up(y[0]), y1 = g.up(y[1]), y2 = g.up(y[2]);
+        const double snd[9] = {R.L[0], R.L[1], R.L[2], R.L[3], R.L[4], R.L[5], y[0], y[1], y[2]};
+        double rcv[9];
+        g.template up_n<9>(snd, rcv, j == 32);
+        const double q00 = rcv[0], q10 = rcv[1], q11 = rcv[2], q20 = rcv[3], q21 = rcv[4], q22 = rcv[5];
+        const double y0 = rcv[6], y1 = rcv[7], y2 = rcv[8];
         if (g.lane == j) {
             if (j > 0) {
 #pragma unroll
@@ -453,7 +567,10 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, const C
     // ---- (3) back substitution over the poses: L_j^T p_j = y_j - B_{j+1}^T p_{j+1}
     double p[3] = {0.0, 0.0, 0.0}, t0 = 0.0, t1 = 0.0, t2 = 0.0;
     for (int j = K - 1; j >= 0; --j) {
-        const double r0 = g.down(t0), r1 = g.down(t1), r2 = g.down(t2);
+        const double tsnd[3] = {t0, t1, t2};
+        double trcv[3];
+        g.template down_n<3>(tsnd, trcv, j == 31);
+        const double r0 = trcv[0], r1 = trcv[1], r2 = trcv[2];
         if (g.lane == j) {
             double h0 = y[0], h1 = y[1], h2 = y[2];
             if (j + 1 < K) { h0 -= r0; h1 -= r1; h2 -= r2; }
@@ -467,7 +584,9 @@ __device__ __forceinline__ bool coop_solve(const LaneGroup<G> &g, int K, const C
     }
     // ---- (4) controls back: Lu^T u = wb - Wv p_k - Wo p_{k-1}   (lane 0 has Wo = 0)
     // (Wv, Wo, wb are recomputed from the shared-memory column: 21 multiply-adds instead of 14 registers held across the pipeline)
-    const double pp0 = g.up(p[0]), pp1 = g.up(p[1]), pp2 = g.up(p[2]);
+    double ppv[3];
+    g.template up_n<3>(p, ppv);
+    const double pp0 = ppv[0], pp1 = ppv[1], pp2 = ppv[2];
     double xv0[3], xv1[3], xo0[3], xo1[3], xb0, xb1;
     coop_control_rows(M, i0, l10, i1, xv0, xv1, xo0, xo1, xb0, xb1);
     const double w0 = xb0 - (xv0[0] * p[0] + xv0[1] * p[1] + xv0[2] * p[2]) - (xo0[0] * pp0 + xo0[1] * pp1 + xo0[2] * pp2);
@@ -541,7 +660,7 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
             for (;;) {
                 int t = 0;
                 if (g.lane == 0) t = atomicAdd(B.queue, 1);
-                t = __shfl_sync(g.mask, t, 0, G);
+                t = g.bcast_i(t, 0);
                 if (t >= B.N) { exhausted = true; break; }
                 if (B.active_mask == nullptr || B.active_mask[t]) { n = t; have = true; break; }
             }
@@ -659,7 +778,9 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 // step is 0.8 x the first one's, so its linear and quadratic forms are 0.8 x and 0.64 x the first trial's
                 // (equal up to the rounding of the products; the forms only feed the ratio > 0.25 test)
                 if (bt == 0) {
-                    const double p2 = g.up(d[2]), p3 = g.up(d[3]), p4 = g.up(d[4]);
+                    double dpv[3];
+                    g.template up_n<3>(d + 2, dpv);
+                    const double p2 = dpv[0], p3 = dpv[1], p4 = dpv[2];
                     double gg = 0.0, qq = 0.0;
 #pragma unroll
                     for (int a = 0; a < 5; ++a) {

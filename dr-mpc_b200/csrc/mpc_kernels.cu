@@ -1,9 +1,10 @@
 // mpc_kernels.cu -- batched MPC.act (reference environment/path_tracking/utils/mpc.py:58-206).
 //
 // Two kernels:
-//   mpc_coop_kernel<G> : K <= 32. A group of G lanes per problem, lane k = horizon step k, everything in registers
-//                        (mpc_coop.cuh). This is the fast path.
-//   mpc_act_kernel<KC> : K > 32 fallback, one thread per problem with the system in local memory.
+//   mpc_coop_kernel<G> : a group of G >= K lanes per problem (4, 8, 16, 32, or a pair of warps for K > 32), lane k = horizon
+//                        step k (mpc_coop.cuh). This is the product path for every K <= DRE_MAX_HORIZON.
+//   mpc_act_kernel<KC> : one thread per problem with the system in local memory: DRE_MPC_SERIAL=1 only (A/B measurements,
+//                        and the host-compilable semantic reference of the tests).
 // Data layout: warm-start poses/controls are problem-major ([N][K] double4 / double2), so the lanes of a warp
 // (G-lane groups of consecutive problems) read/write one contiguous run; per-problem inputs and outputs likewise.
 #include <cstdlib>
@@ -19,6 +20,7 @@ mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
     extern __shared__ __align__(16) double coop_smem[];   // CS_SLOTS columns of DRE_MPC_CTA doubles
     LaneGroup<G> g;
+    g.attach(coop_smem + CS_SLOTS * DRE_MPC_CTA);   // exchange area of the two-warp groups (K > 32)
     mpc_coop_persistent<G, TRACE>(g, prm, B, coop_smem);
 }
 
@@ -44,7 +46,7 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
                            dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
 {
     const int threads = DRE_MPC_CTA, per_block = threads / G;
-    const size_t smem = (size_t)CS_SLOTS * DRE_MPC_CTA * sizeof(double);
+    const size_t smem = ((size_t)CS_SLOTS * DRE_MPC_CTA + (G == 64 ? 64 : 0)) * sizeof(double);
     static int resident_blocks = 0;           // persistent grid: as many CTAs as fit on the device at once
     if (resident_blocks == 0) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -154,6 +156,7 @@ int dre_mpc_launch(const dre_mpc_params &p, const MpcDeviceState &st, const int3
         if (K <= 8) return launch_mpc_coop<8, 3>(DRE_MPC_ARGS);
         if (K <= 16) return launch_mpc_coop<16, 3>(DRE_MPC_ARGS);
         if (K <= 32) return launch_mpc_coop<32, 3>(DRE_MPC_ARGS);
+        return launch_mpc_coop<64, 3>(DRE_MPC_ARGS);   // one problem per pair of warps
     }
     if (K <= 4) return launch_mpc<4>(DRE_MPC_ARGS);
     if (K <= 10) return launch_mpc<10>(DRE_MPC_ARGS);

@@ -137,7 +137,7 @@ def run_reference(a):
                     "path pinned to golden vectors of the reference's own Python; Python-RVO2 / pysteam / pylgmath are not "
                     "vendored by the reference and absent here, and /root/reference does not exist on the GPU box",
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -389,13 +389,34 @@ def run_ours(a):
                 "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "roofline": roofline, "roofline_compute": roofline_compute,
                 "kernels_ms": kavg, "dedup_variant": dedup, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
                 "episode_stats": {n: int(cnt[i]) for i, n in enumerate(d.env.STAT_NAMES)}, "reward_sums": [float(x) for x in sums[:3]]}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The JSON line goes to the process's real stdout; everything else written to fd 1 (NCCL's version banner, library
+    chatter) was pointed at stderr by _quiet_stdout so that stdout carries exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    sys.stdout.flush()
+    while data:
+        data = data[os.write(fd, data):]
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -866,9 +866,18 @@ static int dre_ha_agents_per_group()
     return v;
 }
 
+// the fused step kernel only has the lane-group passes: the stand-alone thread-per-agent variant (group_lanes = 1, a measurement
+// aid of BatchedORCA) maps to the automatic choice here
+static int dre_env_pick_group(const EnvDev &D)
+{
+    dre_orca_params q = D.orca;
+    if ((q.group_lanes & 0xff) == 1) q.group_lanes = 0;
+    return dre_orca_pick_group(q, D.Nh);
+}
+
 int dre_env_ha_envs_per_cta(const EnvDev &D)
 {
-    const int G = dre_orca_pick_group(D.orca, D.Nh);
+    const int G = dre_env_pick_group(D);
     int EPB = (dre_ha_agents_per_group() * (dre_ha_threads() / G)) / D.Nh;
     if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     return EPB < 1 ? 1 : EPB;
@@ -896,7 +905,7 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 
 int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
-    const int G = dre_orca_pick_group(D.orca, D.Nh);
+    const int G = dre_env_pick_group(D);
 #define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true>(D, mode, write_obs, s) : launch_ha<g, false>(D, mode, write_obs, s)
     switch (G) {
     DRE_HA_CASE(2);

@@ -73,6 +73,26 @@ struct SerialGroup {
 #endif
 struct OLine { float px, py, dx, dy; };   // point, direction (16 B, float4-compatible)
 
+// Scratch accessors. The lane-group kernels give every group contiguous arrays (plain pointers); the thread-per-agent
+// kernel interleaves its threads' arrays (element i of thread t at base[i * stride + t]: conflict-free 16 B accesses).
+DRE_HD float4 dre_ld4(const float *p, int k) { return *reinterpret_cast<const float4 *>(p + k); }
+struct StridedLines {
+    OLine *p; int stride;
+    DRE_HD OLine &operator[](int i) const { return p[(size_t)i * stride]; }
+    DRE_HD StridedLines operator+(int n) const { StridedLines r = {p + (size_t)n * stride, stride}; return r; }
+};
+// lines [0, split) in one strided array (shared memory), [split, ...) in another (global scratch)
+struct TwoSpaceLines {
+    OLine *a; int sa; OLine *b; int sb; int split; int off;
+    DRE_HD OLine &operator[](int i) const { const int k = i + off; return k < split ? a[(size_t)k * sa] : b[(size_t)(k - split) * sb]; }
+    DRE_HD TwoSpaceLines operator+(int n) const { TwoSpaceLines r = *this; r.off += n; return r; }
+};
+struct StridedDist {   // float4 chunks interleaved across threads
+    float4 *p; int stride;
+    DRE_HD float &operator[](int j) const { return reinterpret_cast<float *>(p + (size_t)(j >> 2) * stride)[j & 3]; }
+};
+DRE_HD float4 dre_ld4(const StridedDist &d, int k) { return d.p[(size_t)(k >> 2) * d.stride]; }
+
 DRE_HD int dre_ffs(unsigned b)
 {
 #if defined(__CUDA_ARCH__)
@@ -101,8 +121,8 @@ DRE_HD unsigned dre_f2u(float f)
 
 // first line index i in [cursor, m) with det(dir_i, point_i - res) > thresh, else m.
 // Every lane tests all of its lines (independent loads, no loop-carried vote), then one group-wide min.
-template <class Grp>
-DRE_HD int orca_first_violated(const Grp &g, const OLine *L, int m, int cursor, float rx, float ry, float thresh)
+template <class Grp, class LinesT>
+DRE_HD int orca_first_violated(const Grp &g, const LinesT &L, int m, int cursor, float rx, float ry, float thresh)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
@@ -117,8 +137,8 @@ DRE_HD int orca_first_violated(const Grp &g, const OLine *L, int m, int cursor, 
 }
 
 // RVO2 linearProgram1 on pivot line i; lanes share the scan over lines j < i
-template <class Grp>
-DRE_HD bool orca_lp1(const Grp &g, const OLine *L, int i, float radius, float ox, float oy, bool dirOpt, float &rx, float &ry)
+template <class Grp, class LinesT>
+DRE_HD bool orca_lp1(const Grp &g, const LinesT &L, int i, float radius, float ox, float oy, bool dirOpt, float &rx, float &ry)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
@@ -223,10 +243,10 @@ DRE_HD OLine orca_make_line(float px, float py, float vx, float vy, float rs, fl
 // lines with the preferred velocity; if it fails at line `fail`, every later violated line i re-enters the same body
 // with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
 // solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
-template <class Grp>
+template <class Grp, class DistT, class LinesT>
 DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
-                             int maxNeighbors, float invTH, float invDt, float *sdist, OLine *L, float &outx, float &outy,
+                             int maxNeighbors, float invTH, float invDt, DistT sdist, LinesT L, float &outx, float &outy,
                              dre_orca_stats *st, bool debug_skip_lp3 = false)
 {
     constexpr int G = Grp::size;
@@ -260,12 +280,12 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
             int r = 0;
 #pragma unroll 2
             for (int k = 0; k < nA4; k += 4) {
-                const float4 q = *reinterpret_cast<const float4 *>(sdist + k);
+                const float4 q = dre_ld4(sdist, k);
                 const unsigned thr = uj + (k < jc ? 1u : 0u);
                 r += (int)(dre_f2u(q.x) < thr) + (int)(dre_f2u(q.y) < thr) + (int)(dre_f2u(q.z) < thr) + (int)(dre_f2u(q.w) < thr);
             }
             {
-                const float4 q = *reinterpret_cast<const float4 *>(sdist + jc);
+                const float4 q = dre_ld4(sdist, jc);
                 const int jr = j - jc;   // 0..3: position of j in its chunk
                 r += (int)(jr > 0 && dre_f2u(q.x) == uj) + (int)(jr > 1 && dre_f2u(q.y) == uj) + (int)(jr > 2 && dre_f2u(q.z) == uj);
             }
@@ -275,11 +295,11 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     const int m = cnt < maxNeighbors ? cnt : maxNeighbors;
     g.sync();
 
-    OLine *P = L + nA;                       // LP3's projected lines
+    LinesT P = L + nA;                       // LP3's projected lines
     float rx = 0.0f, ry = 0.0f;
     int n_lp1 = 0, lp1_work = 0, nproj = 0, fail = m;
     // arguments of the current LP2 run
-    const OLine *cl = L;
+    LinesT cl = L;
     int cm = m;
     float cox = prefx, coy = prefy;
     bool dirOpt = false;

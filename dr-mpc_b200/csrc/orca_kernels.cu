@@ -134,9 +134,107 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
     return DRE_OK;
 }
 
+// ---- thread-per-agent variant (group_lanes = 1): one thread solves one agent with the sequential RVO2 control flow; the
+// per-thread scratch arrays are interleaved across the CTA's threads (conflict-free 16 B accesses). P_GLOBAL: LP3's
+// projected lines live in a global scratch buffer instead of shared memory (halves the footprint -> 4 CTAs per SM).
+#define DRE_TP_THREADS 128
+template <bool P_GLOBAL>
+__global__ void __launch_bounds__(DRE_TP_THREADS)
+orca_thread_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__restrict__ hpos,
+                   const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
+                   const double2 *__restrict__ rpos, const uint8_t *__restrict__ is_static,
+                   float2 *__restrict__ vnew, dre_orca_stats *__restrict__ stats, OLine *__restrict__ pscratch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nA = Nh + (p.robot_visible ? 1 : 0), nA4 = (nA + 3) & ~3;
+    OLine *lines = reinterpret_cast<OLine *>(smem_raw);                                   // [nA or 2 nA][threads]
+    const size_t nl = (size_t)(P_GLOBAL ? nA : 2 * nA) * DRE_TP_THREADS;
+    float4 *dist = reinterpret_cast<float4 *>(smem_raw + nl * sizeof(OLine));              // [nA4/4][threads]
+    float *agents = reinterpret_cast<float *>(smem_raw + nl * sizeof(OLine) + (size_t)(nA4 / 4) * DRE_TP_THREADS * sizeof(float4));
+    const int env0 = blockIdx.x * EPB;
+    for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
+        const int el = t / nA, a = t - el * nA, e = env0 + el;
+        float *A = agents + (size_t)el * 5 * nA;
+        float x = 0.f, y = 0.f, vx = 0.f, vy = 0.f;
+        if (e < E) {
+            if (a < Nh) {
+                const double2 q = hpos[(size_t)e * Nh + a];
+                const float2 v = hvel[(size_t)e * Nh + a];
+                x = (float)q.x; y = (float)q.y; vx = v.x; vy = v.y;
+            } else {
+                const double2 q = rpos[e];
+                x = (float)q.x; y = (float)q.y;
+            }
+        }
+        A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = p.radius;
+    }
+    __syncthreads();
+    const int ag = threadIdx.x;
+    if (ag >= EPB * Nh) return;
+    const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
+    if (e >= E) return;
+    const size_t gidx = (size_t)e * Nh + i;
+    float ox = 0.f, oy = 0.f;
+    if (is_static != nullptr && is_static[gidx]) {
+        if (stats) { dre_orca_stats z = {0, 0, 0, 0, 0u, 0}; stats[gidx] = z; }
+    } else {
+        const double2 P = hpos[gidx], Gl = goal[gidx];
+        const double dx = Gl.x - P.x, dy = Gl.y - P.y;
+        const double speed = sqrt(dx * dx + dy * dy);
+        double pvx = dx, pvy = dy;
+        if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
+        const float *A = agents + (size_t)el * 5 * nA;
+        const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
+        const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
+        StridedDist sd = {dist + threadIdx.x, DRE_TP_THREADS};
+        SerialGroup g;
+        if (P_GLOBAL) {
+            // L in shared memory, P in the global scratch: one accessor type -> generic addressing for both
+            TwoSpaceLines L = {lines + threadIdx.x, DRE_TP_THREADS,
+                               pscratch + (size_t)blockIdx.x * nA * DRE_TP_THREADS + threadIdx.x, DRE_TP_THREADS, nA, 0};
+            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy, p.max_speed_self,
+                             p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
+        } else {
+            StridedLines L = {lines + threadIdx.x, DRE_TP_THREADS};
+            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy, p.max_speed_self,
+                             p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
+        }
+    }
+    vnew[gidx] = make_float2(ox, oy);
+}
+
+static int launch_orca_thread(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
+                              const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
+{
+    const int nA = Nh + (p.robot_visible ? 1 : 0), nA4 = (nA + 3) & ~3;
+    int EPB = DRE_TP_THREADS / Nh;
+    if (EPB < 1) return DRE_ERR_INVALID;
+    const size_t fixed = (size_t)(nA4 / 4) * DRE_TP_THREADS * sizeof(float4) + (size_t)EPB * 5 * nA * sizeof(float);
+    // large crowds: both line arrays do not fit in shared memory -> projected lines in the global scratch
+    const bool pglobal = (p.group_lanes & 0x400) != 0 || (size_t)2 * nA * DRE_TP_THREADS * sizeof(OLine) + fixed > 200 * 1024;
+    const size_t bytes = (size_t)(pglobal ? nA : 2 * nA) * DRE_TP_THREADS * sizeof(OLine) + fixed;
+    if (bytes > 220 * 1024) return DRE_ERR_INVALID;
+    const int blocks = (E + EPB - 1) / EPB;
+    static OLine *scratch = nullptr; static size_t scratch_n = 0;
+    if (pglobal) {
+        const size_t need = (size_t)blocks * nA * DRE_TP_THREADS;
+        if (need > scratch_n) { if (scratch) cudaFree(scratch); DRE_CUDA_TRY(cudaMalloc(&scratch, need * sizeof(OLine))); scratch_n = need; }
+        DRE_CUDA_TRY(cudaFuncSetAttribute(orca_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        orca_thread_kernel<true><<<blocks, DRE_TP_THREADS, bytes, s>>>(p, E, Nh, EPB, (const double2 *)hpos, (const float2 *)hvel, (const double2 *)goal,
+                                                                        (const double2 *)rpos, is_static, (float2 *)vnew, stats, scratch);
+    } else {
+        DRE_CUDA_TRY(cudaFuncSetAttribute(orca_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        orca_thread_kernel<false><<<blocks, DRE_TP_THREADS, bytes, s>>>(p, E, Nh, EPB, (const double2 *)hpos, (const float2 *)hvel, (const double2 *)goal,
+                                                                         (const double2 *)rpos, is_static, (float2 *)vnew, stats, nullptr);
+    }
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
 int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
     const int gl = p.group_lanes & 0xff;
+    if (gl == 1) return 1;
     if (gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32) return gl;
     if (p.group_lanes == 2 || p.group_lanes == 4 || p.group_lanes == 8 || p.group_lanes == 16 || p.group_lanes == 32) return p.group_lanes;
     const int nA = Nh + (p.robot_visible ? 1 : 0);
@@ -148,6 +246,7 @@ int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos,
 {
     if (E <= 0 || Nh <= 0 || Nh > DRE_MAX_HUMANS) return DRE_ERR_INVALID;
     switch (dre_orca_pick_group(p, Nh)) {
+    case 1: return launch_orca_thread(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     case 2: return launch_orca<2>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     case 4: return launch_orca<4>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     case 8: return launch_orca<8>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);

@@ -12,7 +12,7 @@ def _engine(group_lanes=0, **kw):
     return d.BatchedORCA(d.EngineConfig(group_lanes=group_lanes, **kw))
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32, 1, 1 | 0x400])   # 1: thread-per-agent variant (0x400: projected lines in global scratch)
 @pytest.mark.parametrize("key", ORCA_KEYS)
 def test_cuda_matches_reference_golden_bit_exact(golden_orca, key, lanes):
     g = golden_orca

@@ -234,20 +234,11 @@ DRE_HD OLine orca_make_line(float px, float py, float vx, float vy, float rs, fl
     return line;
 }
 
-// Full solve for agent `self` of a tile of nA agents held in (shared) arrays ax..ar. The other agents are the
-// tile's agents in index order skipping `self` (crowd_sim.py:274-280: other humans in list order, robot last).
-//   sdist : scratch float[round_up(nA,4)], 16 B aligned, private to the group
-//   L     : scratch OLine[2*nA] private to the group (ORCA lines, then LP3's projected lines)
-//
-// RVO2's linearProgram2 / linearProgram3 are driven from ONE loop with a single LP2 body: stage 0 runs LP2 on the ORCA
-// lines with the preferred velocity; if it fails at line `fail`, every later violated line i re-enters the same body
-// with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
-// solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
+// Neighbour ranking + ORCA lines of agent `self` into L[0..m) (sorted like RVO2's neighbour list). Returns m.
 template <class Grp, class DistT, class LinesT>
-DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
-                             const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
-                             int maxNeighbors, float invTH, float invDt, DistT sdist, LinesT L, float &outx, float &outy,
-                             dre_orca_stats *st, bool debug_skip_lp3 = false)
+DRE_HD int orca_build_lines(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+                            const float *ar, int self, float neighborDist, int maxNeighbors, float invTH, float invDt,
+                            DistT sdist, LinesT L, unsigned &mask)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
@@ -268,7 +259,6 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     g.sync();
     // rank of neighbour j = #{k : (d_k, k) < (d_j, j)} (RVO2 insertNeighbor: ascending distSq, ties by visit order).
     // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
-    unsigned mask = 0;
     for (int j = lane; j < nA; j += G) {
         const bool in = sdist[j] < INFINITY;
         if (in) {
@@ -294,6 +284,65 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     }
     const int m = cnt < maxNeighbors ? cnt : maxNeighbors;
     g.sync();
+
+    return m;
+}
+
+// RVO2 linearProgram3's projection of the lines before line i onto line i (li3 = L[i]) into P[0..pc). Returns pc.
+template <class Grp, class LinesT>
+DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine &li3, const LinesT &P)
+{
+    constexpr int G = Grp::size;
+    const int lane = g.rank();
+    int pc = 0;
+    for (int base = 0; base < i; base += G) {
+        const int j = base + lane;
+        bool keep = false;
+        OLine ln;
+        ln.px = ln.py = ln.dx = ln.dy = 0.0f;
+        if (j < i) {
+            const OLine lj = L[j];
+            const float determinant = li3.dx * lj.dy - li3.dy * lj.dx;
+            keep = true;
+            if (fabsf(determinant) <= DRE_RVO_EPSILON) {
+                if (li3.dx * lj.dx + li3.dy * lj.dy > 0.0f) keep = false;
+                else { ln.px = 0.5f * (li3.px + lj.px); ln.py = 0.5f * (li3.py + lj.py); }
+            } else {
+                const float t = (lj.dx * (li3.py - lj.py) - lj.dy * (li3.px - lj.px)) / determinant;
+                ln.px = li3.px + t * li3.dx; ln.py = li3.py + t * li3.dy;
+            }
+            if (keep) {
+                const float ex = lj.dx - li3.dx, ey = lj.dy - li3.dy;
+                const float inv = 1.0f / sqrtf(ex * ex + ey * ey);
+                ln.dx = ex * inv; ln.dy = ey * inv;
+            }
+        }
+        const unsigned b = g.ballot(keep);
+        if (keep) P[pc + dre_popc(b & ((1u << lane) - 1u))] = ln;
+        pc += dre_popc(b);
+    }
+    return pc;
+}
+
+// Full solve for agent `self` of a tile of nA agents held in (shared) arrays ax..ar. The other agents are the
+// tile's agents in index order skipping `self` (crowd_sim.py:274-280: other humans in list order, robot last).
+//   sdist : scratch float[round_up(nA,4)], 16 B aligned, private to the group
+//   L     : scratch OLine[2*nA] private to the group (ORCA lines, then LP3's projected lines)
+//
+// RVO2's linearProgram2 / linearProgram3 are driven from ONE loop with a single LP2 body: stage 0 runs LP2 on the ORCA
+// lines with the preferred velocity; if it fails at line `fail`, every later violated line i re-enters the same body
+// with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
+// solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
+template <class Grp, class DistT, class LinesT>
+DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+                             const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
+                             int maxNeighbors, float invTH, float invDt, DistT sdist, LinesT L, float &outx, float &outy,
+                             dre_orca_stats *st, bool debug_skip_lp3 = false)
+{
+    constexpr int G = Grp::size;
+    const int lane = g.rank();
+    unsigned mask = 0;
+    const int m = orca_build_lines(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, L, mask);
 
     LinesT P = L + nA;                       // LP3's projected lines
     float rx = 0.0f, ry = 0.0f;
@@ -341,33 +390,7 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
         if (i >= m) break;
         i3 = i;
         li3 = L[i];
-        int pc = 0;
-        for (int base = 0; base < i; base += G) {
-            const int j = base + lane;
-            bool keep = false;
-            OLine ln;
-            ln.px = ln.py = ln.dx = ln.dy = 0.0f;
-            if (j < i) {
-                const OLine lj = L[j];
-                const float determinant = li3.dx * lj.dy - li3.dy * lj.dx;
-                keep = true;
-                if (fabsf(determinant) <= DRE_RVO_EPSILON) {
-                    if (li3.dx * lj.dx + li3.dy * lj.dy > 0.0f) keep = false;
-                    else { ln.px = 0.5f * (li3.px + lj.px); ln.py = 0.5f * (li3.py + lj.py); }
-                } else {
-                    const float t = (lj.dx * (li3.py - lj.py) - lj.dy * (li3.px - lj.px)) / determinant;
-                    ln.px = li3.px + t * li3.dx; ln.py = li3.py + t * li3.dy;
-                }
-                if (keep) {
-                    const float ex = lj.dx - li3.dx, ey = lj.dy - li3.dy;
-                    const float inv = 1.0f / sqrtf(ex * ex + ey * ey);
-                    ln.dx = ex * inv; ln.dy = ey * inv;
-                }
-            }
-            const unsigned b = g.ballot(keep);
-            if (keep) P[pc + dre_popc(b & ((1u << lane) - 1u))] = ln;
-            pc += dre_popc(b);
-        }
+        const int pc = orca_project_lines(g, L, i, li3, P);
         g.sync();
         tx = rx; ty = ry;
         ++nproj;

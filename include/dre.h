@@ -43,7 +43,8 @@ typedef struct dre_orca_params {
     float max_speed_self;  /* human v_max (orca.py:86)                                   */
     int32_t max_neighbors; /* <=0: all others (orca.py:77: len(state.human_states))      */
     int32_t robot_visible; /* config_HA.robot.visible                                    */
-    int32_t group_lanes;   /* lanes cooperating on one agent: 8, 16 or 32 (0 = auto)     */
+    int32_t group_lanes;   /* lanes cooperating on one agent: 2..32 (0 = auto: 8 from 9 agents up). 1 (| 0x400: projected
+                            * lines in global scratch) = thread-per-agent variant of the stand-alone pass, a measurement aid */
 } dre_orca_params;
 
 /* per-solve diagnostics, used to count "LP-branch divergences" against the oracle */

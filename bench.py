@@ -353,15 +353,23 @@ def run_ours(a):
     noise_h = noise[:8].cpu().numpy()
     a_host = torch.empty((E, 2), dtype=torch.float64).pin_memory().numpy()
     a_host[:] = env.out["mpc_actions"][:, :2].cpu().numpy()
+    noise_c = np.ascontiguousarray(noise_h.transpose(0, 2, 1))   # [8][2][E]: the policy works column by column (numpy's inner
+    a0_h, a1_h = a_host[:, 0], a_host[:, 1]                      # loop over a trailing dimension of 2 costs 4x more)
+
+    def host_policy(views, i):
+        ma = views["mpc_actions"]
+        np.add(ma[:, 0], noise_c[i % 8, 0], out=a0_h); np.clip(a0_h, 0.0, 1.0, out=a0_h)
+        np.add(ma[:, 1], noise_c[i % 8, 1], out=a1_h); np.clip(a1_h, -1.0, 1.0, out=a1_h)
+
     for i in range(3):
         views = env.step_host(a_host)
-        np.clip(views["mpc_actions"][:, :2] + noise_h[i % 8], [0.0, -1.0], [1.0, 1.0], out=a_host)
-    n_e2e = min(a.steps, 50)
+        host_policy(views, i)
+    n_e2e = a.steps   # whole laps of the path-switch cycle, like the device-resident loop
     barrier()
     t0 = time.perf_counter()
     for i in range(n_e2e):
         views = env.step_host(a_host)
-        np.clip(views["mpc_actions"][:, :2] + noise_h[i % 8], [0.0, -1.0], [1.0, 1.0], out=a_host)   # host-side policy
+        host_policy(views, i)   # the next action is read from the host slab
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()

@@ -28,3 +28,9 @@ for G in (8, 1, 1 | 0x400):
     if ref is None: ref = v
     same = torch.equal(v.view(torch.int32), ref.view(torch.int32))
     print(f"G={G:#x}: {ms:.4f} ms per pass ({E_}x{Nh}), bit-identical to G=8: {same}, mismatching agents {(v != ref).any(-1).sum().item()}", flush=True)
+o = d.BatchedORCA(d.EngineConfig(group_lanes=8))
+o.predict(hpos, hvel, goal, rpos, want_stats=True)
+st = o.last_stats.cpu().numpy().reshape(-1, 6).astype(np.int64)
+lp3 = st[:, 1] < st[:, 0]
+print(f"agents {len(st)}: lines mean {st[:,0].mean():.1f}, LP1 calls mean {st[:,2].mean():.2f} (max {st[:,2].max()}), LP1 scan work mean {st[:,3].mean():.1f}, "
+      f"LP3 agents {lp3.mean()*100:.1f} %, projections per LP3 agent {st[lp3,5].mean():.2f} (max {st[:,5].max()}), fail line mean {st[lp3,1].mean():.1f}")

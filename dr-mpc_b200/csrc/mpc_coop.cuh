@@ -644,6 +644,11 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
     // ---- per-problem state (registers) ----
     int n = -1;
     bool have = false, exhausted = false;
+    const int warps_per_cta = G > 32 ? DRE_MPC_CTA / G : DRE_MPC_CTA / 32;   // G = 64: a pair of warps counts as one
+    const int total_groups = (int)gridDim.x * (DRE_MPC_CTA / G), total_warps = (int)gridDim.x * warps_per_cta;
+    const int my_warp = (int)blockIdx.x * warps_per_cta + (G > 32 ? (int)threadIdx.x / G : (int)threadIdx.x / 32);
+    const int my_slot = G >= 32 ? 0 : ((int)threadIdx.x & 31) / G;
+    int first_rank = my_slot * total_warps + my_warp;   // < total_groups
     Se2h T0, Mk, Tk1;
     double u[2] = {0.0, 0.0};
     CoopFactor R;
@@ -658,9 +663,16 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
         // ---- fetch + initialise the next problem ----
         if (!have && !exhausted) {
             for (;;) {
-                int t = 0;
-                if (g.lane == 0) t = atomicAdd(B.queue, 1);
-                t = g.bcast_i(t, 0);
+                // A group's first problem is assigned statically, slot-major: slot 0 of every warp of the grid first, then slot
+                // 1, ... so a batch smaller than the grid's group count is spread one problem per warp (a warp pays for every
+                // phase any of its groups needs, and a small batch lasts as long as its slowest warp). Later problems come from
+                // the shared counter, which therefore starts behind the static range.
+                int t = first_rank;
+                if (t < 0) {
+                    if (g.lane == 0) t = atomicAdd(B.queue, 1) + total_groups;
+                    t = g.bcast_i(t, 0);
+                }
+                first_rank = -1;
                 if (t >= B.N) { exhausted = true; break; }
                 if (B.active_mask == nullptr || B.active_mask[t]) { n = t; have = true; break; }
             }

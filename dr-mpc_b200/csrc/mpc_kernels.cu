@@ -45,7 +45,7 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
                            const double *pose, int pose_stride, double *controls, int controls_stride, int controls_count,
                            dre_mpc_status *status, const uint8_t *active_mask, cudaStream_t s)
 {
-    const int threads = DRE_MPC_CTA, per_block = threads / G;
+    const int threads = DRE_MPC_CTA;
     const size_t smem = ((size_t)CS_SLOTS * DRE_MPC_CTA + (G == 64 ? 64 : 0)) * sizeof(double);
     static int resident_blocks = 0;           // persistent grid: as many CTAs as fit on the device at once
     if (resident_blocks == 0) {
@@ -58,7 +58,9 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
         DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, smem));
         resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
-    int blocks = (st.N + per_block - 1) / per_block;
+    // small batches: one problem per warp rather than filling the warps of a few CTAs (see the fetch in mpc_coop.cuh)
+    const int warps_per_block = G > 32 ? threads / G : threads / 32;
+    int blocks = (st.N + warps_per_block - 1) / warps_per_block;
     if (blocks > resident_blocks) blocks = resident_blocks;
     CoopBatch B;
     B.N = st.N; B.path_id = path_id; B.interp_index = interp_index; B.pose = pose; B.pose_stride = pose_stride;

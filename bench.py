@@ -317,7 +317,7 @@ def run_ours(a):
                         "peaks_tflops": {"fp32": peak32.value, "fp64": peak64.value},
                         "ncu_issue_slots": issue,
                         "note": "algorithmic flops (SURVEY 8(d)) are a small part of the issued instructions: the kernels are bound by "
-                                "instruction issue (ha_step) and by the fp64 pipe's 2-cycle warp-instruction cadence (mpc_solve); "
+                                "instruction issue (ha_step) and by dependent fp64 chains / instruction issue and fetch (mpc_solve, profiles/README.md); "
                                 "ncu_issue_slots holds the issue-slot utilisation of the committed ncu capture"}
 
     # ---------------- de-duplicated variant, reported separately: the look-ahead ORCA pass of step t IS the

@@ -1,20 +1,23 @@
 // mpc_coop.cuh -- lane-per-horizon-step cooperative LM solve (the fast path of the MPC kernel).
 //
-// A group of G lanes (G = 4, 8, 16, 32, or 64 = a pair of warps, G >= K) owns one problem; lane k owns horizon step k: pose T_{k+1}, control
-// u_k, reference M_k and block row k of the block-tridiagonal normal equations (diagonal block D_k packed 5x5,
-// coupling block O_k 5x3, rhs b_k). Residuals, Jacobians and trial costs are embarrassingly parallel over lanes (the
-// neighbour pose comes by shuffle); the block Cholesky runs as K pipeline stages in which lane j consumes lane j-1's
-// factor rows (9 doubles by shuffle); sums over the horizon are taken in step order so they round like the
-// sequential reference.
+// A group of G lanes (G = 4, 8, 16, 32, or 64 = a pair of warps, G >= K) owns one problem; lane k owns horizon step k:
+// pose T_{k+1}, control u_k, reference M_k and block row k of the block-tridiagonal normal equations (diagonal block D_k
+// packed 5x5, coupling block O_k 5x3, rhs b_k). Residuals, Jacobians and trial costs are embarrassingly parallel over
+// lanes (the neighbour pose comes by shuffle). The damped solve first eliminates every step's two controls in parallel,
+// then runs a block Cholesky over the remaining 3x3 pose blocks as K pipeline stages in which lane j consumes lane j-1's
+// factor rows (9 doubles by shuffle); sums over the horizon are taken in step order so they round like the sequential
+// reference.
 //
-// The kernel is bound by the LATENCY of fp64 dependency chains (measured: ~6.7 cycles per warp instruction with 2 warps
-// per scheduler), so everything here is about (a) more resident warps and (b) fewer instructions on the chain:
-//   * the linearisation (D, O, b: 35 doubles per lane, read-only between rebuilds) and the retry guess live in a
-//     conflict-free shared-memory column per thread instead of registers -> 168 registers, 3 CTAs (12 warps) per SM;
+// What bounds the kernel (profiles/README.md): in steady tracking the dependent fp64 chains of its longest problem; when
+// every warp is busy (the steps after a path switch) instruction issue and, before the code-size diet, instruction FETCH
+// (154 KB of SASS, 59 % i-cache hit rate). Hence:
+//   * the linearisation (D, O, b: 35 doubles per lane, read-only between rebuilds), the retry guess and the barrier values
+//     live in a conflict-free shared-memory column per thread instead of registers -> 168 registers, 3 CTAs per SM;
 //   * every pose carries its heading, updated additively by the LM step, so the two log maps per cost / build take their
 //     angle from a subtraction + wrap instead of atan2;
-//   * sin/cos of the small angles (dt*w and the LM step) use a branch-free Taylor kernel;
-//   * the factor stores inverse pivots (one rsqrt per pivot, no divisions on the chain).
+//   * sin/cos of the small angles (dt*w and the LM step) use a Taylor kernel, ln x on (0, 1] a 45-instruction routine, with
+//     the polynomial coefficients in constant memory; the full-range routines sit out of line;
+//   * the factors store inverse pivots (one rsqrt per pivot, no divisions on the chain).
 //
 // Control flow is a per-group state machine with the phases in a fixed order (initial cost -> build -> damped solve ->
 // trial 1 -> trial 2 -> bookkeeping), so the groups of a warp, which follow different LM paths, re-converge at every

@@ -34,7 +34,7 @@ def test_cuda_matches_reference_golden(golden_mpc, K):
     assert (st["term"] > 0).all()
 
 
-@pytest.mark.parametrize("K,N", [(4, 4096), (10, 2048), (20, 1024), (32, 384), (33, 300), (40, 512), (3, 257), (1, 64)])
+@pytest.mark.parametrize("K,N", [(4, 4096), (10, 2048), (20, 1024), (32, 384), (33, 300), (40, 512), (3, 257), (1, 64), (8, 640), (16, 320), (5, 1000)])
 def test_cuda_matches_oracle_warm_sequences(oracle, golden_mpc, K, N):
     """iteration0 solve + 3 warm re-solves, teacher-forcing the oracle's warm state every step."""
     import torch

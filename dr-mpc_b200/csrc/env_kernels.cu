@@ -892,7 +892,12 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
     // smaller CTAs share an SM)
     const int threads = dre_ha_threads();
     const int EPB = dre_env_ha_envs_per_cta(D);
-    const HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
+    HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
+    {   // DRE_HA_SMEM_PAD_KB: extra dynamic shared memory per CTA (measurement aid: caps the CTAs per SM)
+        static int pad = -1;
+        if (pad < 0) { const char *e = getenv("DRE_HA_SMEM_PAD_KB"); pad = e ? atoi(e) : 0; }
+        lay.bytes += (size_t)pad * 1024;
+    }
     auto kern = ha_step_kernel<G, DEDUP>;
     if (lay.bytes > 48 * 1024) {
         if (lay.bytes > 220 * 1024) return DRE_ERR_INVALID;

@@ -56,6 +56,9 @@ static int launch_mpc_coop(const dre_mpc_params &p, const MpcDeviceState &st, co
         if (G == 4 && MINB == 3)
             DRE_CUDA_TRY(cudaFuncSetAttribute(mpc_coop_kernel<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpc_coop_kernel<G, MINB>, threads, smem));
+        // DRE_MPC_CTAS_PER_SM caps the persistent grid (measurement aid: leaves register file to a co-running kernel)
+        const char *cap = getenv("DRE_MPC_CTAS_PER_SM");
+        if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
         resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
     // small batches: one problem per warp rather than filling the warps of a few CTAs (see the fetch in mpc_coop.cuh)

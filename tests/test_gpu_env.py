@@ -262,7 +262,8 @@ def test_training_loop_skeleton_with_replay_soft_reset_and_cvmm():
 
 @pytest.mark.parametrize("E,Nh,variant", [(2048, 20, {}), (1024, 10, {}), (256, 50, {}),
                                           (512, 12, {"robot_visible": False}), (512, 8, {"end_goal_changing": False}),
-                                          (512, 8, {"auto_path_switch": False}), (384, 16, {"neighbor_dist": 3.0})])
+                                          (512, 8, {"auto_path_switch": False}), (384, 16, {"neighbor_dist": 3.0}),
+                                          (256, 6, {"horizon": 10}), (192, 6, {"horizon": 40})])
 def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
     """CUDA env step vs the CPU oracle (oracle/env_ref.c) on thousands of states the free-running engine itself reaches
     (dense and sparse crowds, goal resampling by the shared Philox streams, path switches): the device state is copied into
@@ -276,6 +277,7 @@ def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
     S = env.reset()
     ov = dict(variant)
     ref_kw = {k: ov.pop(k) for k in ("auto_path_switch", "end_goal_changing", "neighbor_dist") if k in ov}
+    if "horizon" in ov: ref_kw["K"] = ov.pop("horizon")
     ref = oracle.EnvRef(E, Nh, tab, lens, **ref_kw, **{k: int(v) for k, v in ov.items()})
     ref.reset()
     gen = torch.Generator(device=env.device).manual_seed(7)

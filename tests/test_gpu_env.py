@@ -125,7 +125,7 @@ def test_auto_path_switch_follows_soft_reset(golden_env):
     assert (st["path_idx"] == (g[f"{tag}_pre_path_idx"][idx] + 1) % 4).all()
 
 
-@pytest.mark.parametrize("E,Nh,K", [(16384, 20, 4), (2048, 50, 4), (100, 1, 4), (512, 6, 10), (37, 63, 1), (300, 5, 40)])
+@pytest.mark.parametrize("E,Nh,K", [(16384, 20, 4), (2048, 50, 4), (100, 1, 4), (512, 6, 10), (37, 63, 1), (300, 5, 40), (3, 64, 4), (1, 6, 4)])
 def test_free_running_full_size_invariants(E, Nh, K):
     """C3 size (and the C4 crowd, a single human, a long horizon, the largest crowd, the longest horizon on its two-warp
     MPC groups): 30 free-running steps with the MPC

@@ -22,7 +22,7 @@ def test_cuda_matches_reference_golden_bit_exact(golden_orca, key, lanes):
     assert np.array_equal(v.view(np.uint32), ref.view(np.uint32)), np.abs(v - ref).max()
 
 
-@pytest.mark.parametrize("E,Nh,spread", [(1024, 10, 4.0), (2048, 20, 5.0), (512, 50, 8.0), (4096, 6, 1.5), (333, 1, 1.0), (7, 63, 6.0)])
+@pytest.mark.parametrize("E,Nh,spread", [(1024, 10, 4.0), (2048, 20, 5.0), (512, 50, 8.0), (4096, 6, 1.5), (333, 1, 1.0), (7, 63, 6.0), (5, 64, 6.0), (1, 2, 0.4)])
 def test_cuda_matches_oracle_random_crowds(oracle, E, Nh, spread):
     import torch
     rng = np.random.default_rng(E + Nh)

@@ -210,11 +210,21 @@ DRE_HD int soft_reset_decide(SrState &S, uint32_t prev_bits, const PathView &P, 
     return 1;
 }
 
-// uniform doubles for (env, step, stream id, draw): two per Philox call
-DRE_HD void env_uniform2(uint64_t seed, uint64_t env_id, uint64_t step, uint32_t stream, uint32_t draw, double &u0, double &u1)
+// Uniform doubles for (env, reset epoch, kind of draw, step, stream id, draw): two per Philox call. Every field has its
+// own bits of the 64-bit key / 128-bit counter, so no two draws of a run share a counter:
+//   key     = seed, with the reset epoch added to its high word
+//   c0, c1  = global env id
+//   c2      = step count of the episode (low 32 bits)
+//   c3      = draw (bits 0..15) | stream (16..23: the human index, or 0xC7 for the safety filter) | kind (24..25) |
+//             sub-step (26..31: the warm-start step of a reset)
+enum { DRE_RNG_STEP = 0, DRE_RNG_RESET = 1, DRE_RNG_WARM = 2, DRE_RNG_CVMM = 3 };
+DRE_HD void env_uniform2(uint64_t seed, uint32_t epoch, uint64_t env_id, uint32_t kind, uint32_t sub, uint64_t step, uint32_t stream,
+                         uint32_t draw, double &u0, double &u1)
 {
     uint32_t r[4];
-    philox4x32_10(seed, env_id, (step << 24) ^ ((uint64_t)stream << 48) ^ (uint64_t)draw, r);
+    const uint64_t key = seed + ((uint64_t)epoch << 32);
+    const uint32_t c3 = (draw & 0xFFFFu) | ((stream & 0xFFu) << 16) | ((kind & 3u) << 24) | ((sub & 0x3Fu) << 26);
+    philox4x32_10(key, env_id, (uint64_t)(uint32_t)step | ((uint64_t)c3 << 32), r);
     u0 = u01_from_bits(r[0], r[1]);
     u1 = u01_from_bits(r[2], r[3]);
 }

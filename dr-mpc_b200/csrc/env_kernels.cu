@@ -440,7 +440,8 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
             const int e = env0 + el;
             if (e >= D.E || !flags[el * 4]) continue;
             const uint64_t gid = (uint64_t)(D.env_id_offset + e);
-            const uint64_t stp = (uint64_t)D.step_count[e] + ((uint64_t)D.reset_epoch[e] << 20) + (mode == 1 ? (1ull << 19) + (uint64_t)D.rvalid[e] : 0ull);
+            const uint64_t stp = (uint64_t)D.step_count[e];
+            const uint32_t epoch = (uint32_t)D.reset_epoch[e], kind = mode == 1 ? DRE_RNG_WARM : DRE_RNG_STEP, sub = mode == 1 ? (uint32_t)D.rvalid[e] : 0u;
             const double rgx = 0.0, rgy = D.circle_radius;   // robot goal, HA_and_PT env.py:293-299
             const double rpx = D.rpose[(size_t)e * 4], rpy = D.rpose[(size_t)e * 4 + 1];
             for (int i = 0; i < Nh; ++i) {
@@ -453,8 +454,8 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
                 double gx = gl.x, gy = gl.y;
                 for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
                     double u0, u1, u2, u3;
-                    env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt, u0, u1);
-                    env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt + 1, u2, u3);
+                    env_uniform2(D.seed, epoch, gid, kind, sub, stp, (uint32_t)i, 2 * attempt, u0, u1);
+                    env_uniform2(D.seed, epoch, gid, kind, sub, stp, (uint32_t)i, 2 * attempt + 1, u2, u3);
                     const double angle = u0 * DRE_PI * 2.0;
                     double sa, ca;
                     sincos(angle, &sa, &ca);
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
     D.out.done_bits[e] = 0u;
     D.cache_valid[e] = 0;
     const uint64_t gid = (uint64_t)(D.env_id_offset + e);
-    const uint64_t stp = ((uint64_t)D.reset_epoch[e] << 20) + (1ull << 18);
+    const uint32_t epoch = (uint32_t)D.reset_epoch[e];
     for (int i = 0; i < Nh; ++i) {
         const size_t gidx = (size_t)e * Nh + i;
         double px, py, gx, gy;
@@ -719,8 +720,8 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
             px = 0.0; py = 0.0;
             for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
                 double u0, u1, u2, u3;
-                env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt, u0, u1);
-                env_uniform2(D.seed, gid, stp, (uint32_t)i, 2 * attempt + 1, u2, u3);
+                env_uniform2(D.seed, epoch, gid, DRE_RNG_RESET, 0u, 0ull, (uint32_t)i, 2 * attempt, u0, u1);
+                env_uniform2(D.seed, epoch, gid, DRE_RNG_RESET, 0u, 0ull, (uint32_t)i, 2 * attempt + 1, u2, u3);
                 double sa, ca;
                 sincos(u0 * DRE_PI * 2.0, &sa, &ca);
                 px = D.circle_radius_humans * ca + u1 * 1.0;
@@ -816,7 +817,7 @@ __global__ void __launch_bounds__(128) cvmm_filter_kernel(EnvDev D, const double
         nsafe = __popc(bm);
         if (nsafe == 0) {   // random back-up action (:459-464; np.random there, Philox here)
             double u0, u1;
-            env_uniform2(D.seed, (uint64_t)(D.env_id_offset + e), (uint64_t)D.step_count[e] + ((uint64_t)D.reset_epoch[e] << 20), 0xC7u, 0u, u0, u1);
+            env_uniform2(D.seed, (uint32_t)D.reset_epoch[e], (uint64_t)(D.env_id_offset + e), DRE_RNG_CVMM, 0u, (uint64_t)D.step_count[e], 0xC7u, 0u, u0, u1);
             chosen = (int)(u0 * (double)A);
             if (chosen >= A) chosen = A - 1;
             random = 1;

@@ -694,17 +694,28 @@ __device__ void mpc_coop_persistent(const LaneGroup<G> &g, const dre_mpc_params 
                 Mk.T = se2_from_pose_inv_ool(r[0], r[1], r[2]);
                 Mk.th = -r[2];
                 const bool first_call = (B.iteration0[n] != 0);
+                // the stored warm start of the last successful solve (all zeros until one has finished)
+                double4 w = make_double4(0.0, 0.0, 0.0, 0.0);
+                double2 uu = make_double2(0.0, 0.0);
+                if (act) { w = B.warm_T[(size_t)n * K + k]; uu = B.warm_u[(size_t)n * K + k]; }
+                const bool has_stored = act && (w.x * w.x + w.y * w.y > 0.5);
                 if (first_call || !act) { Tk1 = Mk; u[0] = prm.v_max / 2.0; u[1] = 0.0; }   // mpc.py:68-71
                 else {
-                    const double4 w = B.warm_T[(size_t)n * K + k];
-                    const double2 uu = B.warm_u[(size_t)n * K + k];
                     Tk1.T.c = w.x; Tk1.T.s = w.y; Tk1.T.x = w.z; Tk1.T.y = w.w;
                     Tk1.th = atan2_full(w.y, w.x);
                     u[0] = uu.x; u[1] = uu.y;
                 }
-                // the initial guess is needed again only by the pose_error_scaling retry (mpc.py:188-190)
-                M[CS_TI] = Tk1.T.c; M[CS_TI + 1] = Tk1.T.s; M[CS_TI + 2] = Tk1.T.x; M[CS_TI + 3] = Tk1.T.y; M[CS_TI + 4] = Tk1.th;
-                M[CS_UI] = u[0]; M[CS_UI + 1] = u[1];
+                // The guess the pose_error_scaling retry starts from (mpc.py:188-190 -> :73-75). Reference quirk: iteration0
+                // is cleared BEFORE the solve (mpc.py:72), so the retry of a failed FIRST solve deep-copies the stored warm
+                // start -- the one from before the reset(). With nothing stored the reference raises outside its try; the
+                // batch uses the iteration0 guess again.
+                if (first_call && has_stored) {
+                    M[CS_TI] = w.x; M[CS_TI + 1] = w.y; M[CS_TI + 2] = w.z; M[CS_TI + 3] = w.w; M[CS_TI + 4] = atan2_full(w.y, w.x);
+                    M[CS_UI] = uu.x; M[CS_UI + 1] = uu.y;
+                } else {
+                    M[CS_TI] = Tk1.T.c; M[CS_TI + 1] = Tk1.T.s; M[CS_TI + 2] = Tk1.T.x; M[CS_TI + 3] = Tk1.T.y; M[CS_TI + 4] = Tk1.th;
+                    M[CS_UI] = u[0]; M[CS_UI + 1] = u[1];
+                }
                 s = 1.0; lambda = 1e-7; curr = 0.0; prev = 0.0; gn = 0.0;
                 iter = 0; nb = 0; retries = 0; term = 0; lm_solves = 0; cost_evals = 0; zero_steps = 0;
                 need_cost0 = true; need_build = false;

@@ -544,10 +544,15 @@ DRE_HD void mpc_act_one(const dre_mpc_params &prm, const double *path, int strid
     C.inv_vmax = 1.0 / prm.v_max; C.inv_2wmax = 1.0 / (2.0 * prm.w_max); C.pose_jac_exact = prm.pose_jac_exact;
     const int K = C.K;
     const double inc = (prm.v_max * 0.99) * prm.time_step / prm.node_separation;   // mpc.py:29-30
-    MpcProblem<KC> init;
+    MpcProblem<KC> init, retry_init;
     init.T[0] = se2_from_pose_inv(px, py, pth);
+    retry_init.T[0] = init.T[0];
     double target = interp_idx + inc;
     const bool first = (*it0 != 0);
+    // Reference quirk (mpc.py:72-75,188-190): iteration0 is cleared before the solve, so the pose_error_scaling retry of a
+    // failed FIRST solve starts from the stored warm start of the last successful solve (from before the reset()). Nothing
+    // stored yet (warm_T still all zeros; the reference raises there): the iteration0 guess is used again.
+    const bool has_stored = warm_T[0].x * warm_T[0].x + warm_T[0].y * warm_T[0].y > 0.5;
 DRE_UNROLL_K
     for (int k = 0; k < KC; ++k) {
         if (k >= K) break;
@@ -555,12 +560,16 @@ DRE_UNROLL_K
         mpc_ref_pose(path, stride, L, target, r);
         target += inc;
         init.M[k] = se2_from_pose_inv(r[0], r[1], r[2]);
+        retry_init.M[k] = init.M[k];
+        const double4 w = warm_T[k * ws];
+        const double2 uu = warm_u[k * ws];
+        retry_init.T[k + 1].c = w.x; retry_init.T[k + 1].s = w.y; retry_init.T[k + 1].x = w.z; retry_init.T[k + 1].y = w.w;
+        retry_init.u[k][0] = uu.x; retry_init.u[k][1] = uu.y;
         if (first) {
             init.T[k + 1] = init.M[k]; init.u[k][0] = prm.v_max / 2.0; init.u[k][1] = 0.0;   // mpc.py:68-71
+            if (!has_stored) { retry_init.T[k + 1] = init.T[k + 1]; retry_init.u[k][0] = init.u[k][0]; retry_init.u[k][1] = init.u[k][1]; }
         } else {
-            const double4 w = warm_T[k * ws];
-            const double2 uu = warm_u[k * ws];
-            init.T[k + 1].c = w.x; init.T[k + 1].s = w.y; init.T[k + 1].x = w.z; init.T[k + 1].y = w.w;
+            init.T[k + 1] = retry_init.T[k + 1];
             init.u[k][0] = uu.x; init.u[k][1] = uu.y;
         }
     }
@@ -571,7 +580,7 @@ DRE_UNROLL_K
     double s = 1.0;
     int retries = 0, term = 0;
     for (;;) {
-        P = init;
+        P = retries == 0 ? init : retry_init;
         term = mpc_optimize(C, prm, P, s, S, R);
         if (term) break;
         if (retries >= prm.max_retries) { term = -1; break; }

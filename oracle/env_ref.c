@@ -11,6 +11,9 @@
  *     environment/path_tracking/utils/path_tracking_core.py:21-81,94-145        (localisation, 100-d state)
  *     environment/path_tracking/utils/reward_comp.py:20-116                    (PT rewards)
  *     environment/path_tracking/utils/unicycle.py:89-126                       (exact-arc unicycle)
+ *     environment/HA_and_PT/human_avoidance_and_path_tracking_env.py:120-240   (soft_reset: the scripted recovery loop)
+ *     environment/human_avoidance/human_avoidance_env.py:53-72,102-105,161-164,331-334 (robot sensor restriction)
+ *     environment/human_avoidance/subENVs/crowd_sim.py:171-183,270-272         (static humans)
  * ORCA and MPC come from rvo2_ref.c / mpc_ref.c. np.random cannot be matched draw for draw, so goal resampling and
  * spawning use Philox4x32-10 keyed by (seed, env id, step, human, attempt) (SURVEY 8(d) "Seeds / RNG").
  * Pinned against tests/golden/env_rollouts.npz (the reference's own HAAndPTEnv.step run on the shims).
@@ -53,6 +56,12 @@ typedef struct {
     mpc_params mpc;
     /* paths */
     const double *paths; const int32_t *lens; int32_t num_paths, path_stride;
+    /* options off by default in the reference */
+    int32_t soft_reset;              /* run HAAndPTEnv.soft_reset's scripted loop across step() calls (needs auto_path_switch) */
+    int32_t sensor_restriction;      /* config_HA.robot.sensor_restriction */
+    int32_t num_static;              /* the last num_static humans are obstacles (crowd_sim.py:171-183) */
+    double sensor_range;             /* config_HA.robot.sensor_range */
+    double static_pos[8];
 } env_cfg;
 
 typedef struct {
@@ -63,6 +72,10 @@ typedef struct {
     /* outputs */
     double *pt_state, *mpc_actions, *robot_node, *past_robot_vel, *percent_episode, *spatial_edges, *human_valid,
         *detected_humans, *rewards, *info; uint32_t *done_bits; mpc_stats *mpc_status;
+    /* soft reset: loop variables of HAAndPTEnv.soft_reset carried from one step() call to the next, in the engine's
+     * packing {phase | out_of_trigger_because_of_backup << 8 | extra back-ups left << 16, consecutive_no_v,
+     * steps_in_soft_reset, num_backup_steps}; the action each step executed; {scripted, stuck} flags */
+    int32_t *sr_state; double *actions_used; uint8_t *soft_flags;
 } env_arrays;
 
 enum { B_COLLISION = 1, B_SAFETY = 2, B_ACT = 4, B_TIMEOUT = 8, B_GOAL = 16, B_EOP = 32, B_CORRIDOR = 64, B_SAFETY_CORRIDOR = 128,
@@ -82,10 +95,15 @@ static void philox(uint64_t seed, uint64_t lo, uint64_t hi, uint32_t out[4])
     memcpy(out, c, sizeof c);
 }
 static double u01(uint32_t hi, uint32_t lo) { return (double)(((((uint64_t)hi) << 32) | lo) >> 11) * (1.0 / 9007199254740992.0); }
-static void uniform2(uint64_t seed, uint64_t env, uint64_t step, uint32_t stream, uint32_t draw, double *a, double *b)
+/* key = seed with the reset epoch added to its high word; counter = {env id (64 bit), step count (32 bit),
+ * draw | stream << 16 | kind << 24 | sub-step << 26}: the engine's stream definition (env_device.cuh: env_uniform2) */
+enum { RNG_STEP = 0, RNG_RESET = 1, RNG_WARM = 2 };
+static void uniform2(uint64_t seed, uint32_t epoch, uint64_t env, uint32_t kind, uint32_t sub, uint64_t step, uint32_t stream,
+                     uint32_t draw, double *a, double *b)
 {
     uint32_t r[4];
-    philox(seed, env, (step << 24) ^ ((uint64_t)stream << 48) ^ (uint64_t)draw, r);
+    const uint32_t c3 = (draw & 0xFFFFu) | ((stream & 0xFFu) << 16) | ((kind & 3u) << 24) | ((sub & 0x3Fu) << 26);
+    philox(seed + ((uint64_t)epoch << 32), env, (uint64_t)(uint32_t)step | ((uint64_t)c3 << 32), r);
     *a = u01(r[0], r[1]); *b = u01(r[2], r[3]);
 }
 
@@ -169,8 +187,10 @@ static void human_actions(const env_cfg *c, const double *P, const float *V, con
 }
 
 /* crowd_sim.py:114-144 with Philox */
-static void resample_goals(const env_cfg *c, const env_arrays *A, int e, uint64_t stp)
+static void resample_goals(const env_cfg *c, const env_arrays *A, int e, uint32_t kind, uint32_t sub)
 {
+    const uint64_t stp = (uint64_t)A->step_count[e];
+    const uint32_t epoch = (uint32_t)A->reset_epoch[e];
     const int Nh = c->Nh;
     double *P = A->hpos + (size_t)e * Nh * 2, *G = A->hgoal + (size_t)e * Nh * 2;
     const uint8_t *stat = A->hstatic + (size_t)e * Nh;
@@ -184,8 +204,8 @@ static void resample_goals(const env_cfg *c, const env_arrays *A, int e, uint64_
         double gx = G[2 * i], gy = G[2 * i + 1];
         for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
             double u0, u1, u2, u3;
-            uniform2(c->seed, gid, stp, (uint32_t)i, 2 * attempt, &u0, &u1);
-            uniform2(c->seed, gid, stp, (uint32_t)i, 2 * attempt + 1, &u2, &u3);
+            uniform2(c->seed, epoch, gid, kind, sub, stp, (uint32_t)i, 2 * attempt, &u0, &u1);
+            uniform2(c->seed, epoch, gid, kind, sub, stp, (uint32_t)i, 2 * attempt + 1, &u2, &u3);
             const double angle = u0 * PI * 2.0;
             gx = c->circle_radius_humans * cos(angle) + (u1 - 0.5);
             gy = c->circle_radius_humans * sin(angle) + (u2 - 0.5);
@@ -217,6 +237,26 @@ static void write_ha_obs(const env_cfg *c, const env_arrays *A, int e)
             o[0] = ct * dx + st * dy; o[1] = -st * dx + ct * dy;
         }
     for (int i = 0; i < Nh; ++i) A->human_valid[(size_t)e * Nh + i] = (double)A->hvalid[(size_t)e * Nh + i];
+    int detected = Nh;
+    if (c->sensor_restriction) {                                                   /* :53-72 */
+        /* ob['spatial_edges'][:nv] = ob['spatial_edges'][visible]: the visible humans' rows move to the front, the
+         * rows behind them keep what they held; valid counts likewise, zero beyond nv */
+        const int *hv = A->hvalid + (size_t)e * Nh;
+        double *se = A->spatial_edges + (size_t)e * Nh * 2 * H, *hvo = A->human_valid + (size_t)e * Nh;
+        int nv = 0;
+        for (int i = 0; i < Nh; ++i)
+            if (hv[i] != 0) {
+                if (nv != i) memcpy(se + (size_t)nv * 2 * H, se + (size_t)i * 2 * H, sizeof(double) * 2 * (size_t)H);   /* nv <= i: sources are never overwritten early */
+                hvo[nv] = (double)hv[i];
+                ++nv;
+            }
+        if (nv > 0) { for (int i = nv; i < Nh; ++i) hvo[i] = 0.0; detected = nv; }
+        else {                                                                     /* a fake human far away */
+            for (int k = 0; k < 2 * H; ++k) se[k] = -10.0;
+            for (int i = 0; i < Nh; ++i) hvo[i] = 1.0;
+            detected = 1;
+        }
+    }
     for (int s = 0; s < LB; ++s) {
         const double *rh = A->rhist + ((size_t)e * H + s) * 4;
         const double dx = rh[0] - rp[0], dy = rh[1] - rp[1];
@@ -226,7 +266,7 @@ static void write_ha_obs(const env_cfg *c, const env_arrays *A, int e)
         A->past_robot_vel[(size_t)e * 2 * LB + 2 * s + 1] = A->rpastv[((size_t)e * LB + s) * 2 + 1];
     }
     A->percent_episode[e] = A->gtime[e] / c->time_limit * 10.0 - 5.0;
-    A->detected_humans[e] = (double)Nh;
+    A->detected_humans[e] = (double)detected;
 }
 
 /* HA step for env e. mode 0 step, 1 warm-start step */
@@ -271,6 +311,11 @@ static void ha_step(const env_cfg *c, const env_arrays *A, int e, const double *
         int *hv = A->hvalid + (size_t)e * Nh + i;
         if (*hv == H) { memmove(hh, hh + 2, sizeof(double) * 2 * (size_t)(H - 1)); hh[(H - 1) * 2] = P[2 * i]; hh[(H - 1) * 2 + 1] = P[2 * i + 1]; }
         else { hh[*hv * 2] = P[2 * i]; hh[*hv * 2 + 1] = P[2 * i + 1]; *hv = *hv + 1 < H ? *hv + 1 : H; }
+        if (c->sensor_restriction) {                                               /* :161-164 / :102-105 */
+            const double ct = cos(rp[2]), st = sin(rp[2]), dx = P[2 * i] - rp[0], dy = P[2 * i + 1] - rp[1];
+            const double lx = ct * dx + st * dy, ly = -st * dx + ct * dy;
+            if (sqrt(lx * lx + ly * ly) > c->sensor_range) *hv = 0;
+        }
     }
     if (mode == 0) {                                                               /* calc_reward :189-291 */
         double reward = 0.0, dmin = INFINITY; uint32_t bits = 0; int collision = 0;
@@ -307,10 +352,7 @@ static void ha_step(const env_cfg *c, const env_arrays *A, int e, const double *
         A->done_bits[e] = bits;
     }
     if (write_obs) write_ha_obs(c, A, e);
-    if (c->end_goal_changing) {
-        const uint64_t stp = (uint64_t)A->step_count[e] + ((uint64_t)A->reset_epoch[e] << 20) + (mode == 1 ? (1ull << 19) + (uint64_t)A->rvalid[e] : 0ull);
-        resample_goals(c, A, e, stp);
-    }
+    if (c->end_goal_changing) resample_goals(c, A, e, mode == 1 ? RNG_WARM : RNG_STEP, mode == 1 ? (uint32_t)A->rvalid[e] : 0u);
 }
 
 /* path_tracking_core.py:94-145 (continuous task) */
@@ -397,6 +439,67 @@ static void pt_step(const env_cfg *c, const env_arrays *A, int e, const double *
     memcpy(A->mpc_actions + (size_t)e * nact, u, sizeof(double) * (size_t)nact);
 }
 
+
+/* HAAndPTEnv.soft_reset (HA_and_PT env.py:120-240) for one env of a batch that steps in lock-step: the reference's
+ * `while done:` loop body is entered once per step() call instead of looping, with its local variables kept in
+ * sr_state between calls. Called BEFORE a step with the previous step's done word; returns 1 and the scripted action
+ * when the reference would be inside soft_reset() issuing self.step(action, soft_reset=True), 0 when control is with
+ * the caller's policy. *stuck: the "Stuck in soft reset" exit (:235-238).
+ * phase 0: outside soft_reset(); 1: a `while done` iteration has issued its step; 2: inside the 7-step extra back-up
+ * loop (:227-233). The path switch on goal / end of path (:130-181) has already happened inside the step that raised it
+ * (auto_path_switch), so those reasons just hand the new state back. */
+static int soft_reset_next(const env_cfg *c, const env_arrays *A, int e, double act[2], int *stuck)
+{
+    int32_t *st = A->sr_state + 4 * (size_t)e;
+    int phase = st[0] & 0xff, oot = (st[0] >> 8) & 0xff, extra = (st[0] >> 16) & 0xff, consec = st[1], steps = st[2], nb = st[3];
+    const uint32_t w = A->done_bits[e];
+    const int done = (w & B_ANY) != 0, done_HA = (w & B_HA) != 0;
+    const uint32_t why = w & 0xFFu;
+    int scripted = 0;
+    *stuck = 0;
+    for (;;) {
+        if (phase == 2) {                                       /* for i in range(7): step(back-up); if done: break */
+            if (!done && extra > 0) { extra -= 1; act[0] = -0.3; act[1] = 0.0; scripted = 1; break; }
+            phase = 1;                                          /* the for loop is over: fall to the checks that follow it */
+            if (steps > 250) { *stuck = 1; phase = 0; break; }
+            if (!done) { phase = 0; break; }
+            /* done: next `while` iteration */
+        } else if (phase == 1) {                                /* a while-iteration's step has just run */
+            if (!done && oot) { phase = 2; extra = 7; continue; }
+            if (steps > 250) { *stuck = 1; phase = 0; break; }
+            if (!done) { phase = 0; break; }
+        } else {                                                /* caller's loop: `if done: S = env.soft_reset(...)` */
+            if (!done) break;
+            consec = 0; steps = 0; oot = 0; nb = 0; extra = 0;
+        }
+        /* ---- top of a `while done:` iteration ---- */
+        if ((why & (B_GOAL | B_EOP)) != 0) { phase = 0; break; }                       /* :130-181 */
+        if (why == B_ACT) { phase = 0; break; }                                         /* :184-185 */
+        phase = 1;
+        if (done_HA && consec > 10 && nb < 5) { act[0] = -0.3; act[1] = 0.0; nb += 1; oot = 1; }   /* :187-190 */
+        else {
+            nb = 0; oot = 0;
+            const int pid = A->path_idx[e], L = c->lens[pid];
+            const double *px = c->paths + (size_t)pid * 3 * c->path_stride, *py = px + c->path_stride, *pth = py + c->path_stride;
+            const double *rp = A->rpose + 4 * (size_t)e;
+            const loc_t loc = localize(px, py, pth, L, rp[0], rp[1], A->loc_to_start[e] != 0);   /* query_closest_path_node_plus_one */
+            const int node = (int)(loc.index + 1.0) % L;
+            const double desired = atan2(py[node] - rp[1], px[node] - rp[0]);
+            const double th_diff = np_mod(desired - rp[2] + PI, 2.0 * PI) - PI;
+            const double turn = th_diff < 0.0 ? -0.1 : 0.1;
+            if ((why & (B_CORRIDOR | B_SAFETY_CORRIDOR)) != 0 && (why & B_SAFETY) == 0) {   /* :208-213 */
+                if (fabs(th_diff) > 0.3) { act[0] = 0.0; act[1] = turn * 7.0; } else { act[0] = 0.5; act[1] = turn; }
+                consec = 0;
+            } else { act[0] = 0.0; act[1] = 0.0; consec += 1; }                             /* :215-216 */
+        }
+        steps += 1;
+        scripted = 1;
+        break;
+    }
+    st[0] = phase | (oot << 8) | (extra << 16); st[1] = consec; st[2] = steps; st[3] = nb;
+    return scripted;
+}
+
 void env_ref_step(const env_cfg *c, const env_arrays *A, const double *actions, int nthreads)
 {
 #ifdef _OPENMP
@@ -409,8 +512,15 @@ void env_ref_step(const env_cfg *c, const env_arrays *A, const double *actions, 
 #pragma omp for schedule(dynamic, 16)
 #endif
         for (int e = 0; e < c->E; ++e) {
-            ha_step(c, A, e, actions + 2 * (size_t)e, 0, 1, scratch, NULL);
-            pt_step(c, A, e, actions + 2 * (size_t)e, 0);
+            double act[2] = {actions[2 * (size_t)e], actions[2 * (size_t)e + 1]};
+            if (c->soft_reset && A->sr_state) {
+                int stuck = 0;
+                const int scripted = soft_reset_next(c, A, e, act, &stuck);
+                if (A->soft_flags) { A->soft_flags[2 * (size_t)e] = (uint8_t)scripted; A->soft_flags[2 * (size_t)e + 1] = (uint8_t)stuck; }
+            }
+            if (A->actions_used) { A->actions_used[2 * (size_t)e] = act[0]; A->actions_used[2 * (size_t)e + 1] = act[1]; }
+            ha_step(c, A, e, act, 0, 1, scratch, NULL);
+            pt_step(c, A, e, act, 0);
         }
         free(scratch);
     }
@@ -446,17 +556,23 @@ void env_ref_reset(const env_cfg *c, const env_arrays *A, const double *hpos_ini
             memset(A->rpastv + (size_t)e * LB * 2, 0, sizeof(double) * 2 * (size_t)LB);
             A->rvalid[e] = 1; A->gtime[e] = 0.0; A->step_count[e] = 0; A->reset_epoch[e] += 1;
             A->path_idx[e] = 0; A->loc_to_start[e] = 1; A->iteration0[e] = 1;
-            const uint64_t gid = (uint64_t)(c->env_id_offset + e), stp = ((uint64_t)A->reset_epoch[e] << 20) + (1ull << 18);
+            A->done_bits[e] = 0u;
+            if (A->sr_state) memset(A->sr_state + 4 * (size_t)e, 0, 4 * sizeof(int32_t));
+            if (A->soft_flags) { A->soft_flags[2 * (size_t)e] = 0; A->soft_flags[2 * (size_t)e + 1] = 0; }
+            const uint64_t gid = (uint64_t)(c->env_id_offset + e);
+            const uint32_t epoch = (uint32_t)A->reset_epoch[e];
             for (int i = 0; i < Nh; ++i) {
                 const size_t g = (size_t)e * Nh + i;
                 double px, py, gx, gy;
-                if (hpos_init) { px = hpos_init[2 * g]; py = hpos_init[2 * g + 1]; gx = hgoal_init ? hgoal_init[2 * g] : -px; gy = hgoal_init ? hgoal_init[2 * g + 1] : -py; }
+                const int si = i - (Nh - c->num_static);                           /* >= 0: static human (crowd_sim.py:171-183) */
+                if (si >= 0 && !hpos_init) { px = c->static_pos[2 * si]; py = c->static_pos[2 * si + 1]; gx = 0.0; gy = 0.0; }
+                else if (hpos_init) { px = hpos_init[2 * g]; py = hpos_init[2 * g + 1]; gx = hgoal_init ? hgoal_init[2 * g] : -px; gy = hgoal_init ? hgoal_init[2 * g + 1] : -py; }
                 else {
                     px = py = 0.0;
                     for (uint32_t attempt = 0; attempt < 4096; ++attempt) {     /* crowd_sim.py:232-262 */
                         double u0, u1, u2, u3;
-                        uniform2(c->seed, gid, stp, (uint32_t)i, 2 * attempt, &u0, &u1);
-                        uniform2(c->seed, gid, stp, (uint32_t)i, 2 * attempt + 1, &u2, &u3);
+                        uniform2(c->seed, epoch, gid, RNG_RESET, 0u, 0ull, (uint32_t)i, 2 * attempt, &u0, &u1);
+                        uniform2(c->seed, epoch, gid, RNG_RESET, 0u, 0ull, (uint32_t)i, 2 * attempt + 1, &u2, &u3);
                         const double ang = u0 * PI * 2.0;
                         px = c->circle_radius_humans * cos(ang) + u1 * 1.0;
                         py = c->circle_radius_humans * sin(ang) + u2 * 1.0;
@@ -472,6 +588,12 @@ void env_ref_reset(const env_cfg *c, const env_arrays *A, const double *hpos_ini
                 }
                 A->hpos[2 * g] = px; A->hpos[2 * g + 1] = py; A->hgoal[2 * g] = gx; A->hgoal[2 * g + 1] = gy;
                 A->hvel[2 * g] = 0.f; A->hvel[2 * g + 1] = 0.f; A->hvalid[g] = 1;
+                A->hstatic[g] = si >= 0 ? 1 : 0;
+                if (c->sensor_restriction) {                                       /* human_avoidance_env.py:331-334 */
+                    const double ct = cos(rth), st = sin(rth), dx = px - rx, dy = py - ry;
+                    const double lx = ct * dx + st * dy, ly = -st * dx + ct * dy;
+                    if (sqrt(lx * lx + ly * ly) > c->sensor_range) A->hvalid[g] = 0;
+                }
                 for (int s = 0; s < H; ++s) { A->hhist[(g * H + s) * 2] = px; A->hhist[(g * H + s) * 2 + 1] = py; }
             }
             pt_step(c, A, e, NULL, 1);

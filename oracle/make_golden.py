@@ -98,8 +98,8 @@ def golden_mpc():
     pt = PTEnv(cm, RewardComputationPT(cm.config_PT.rewards, True))
     pt.reset(np.array([0, -4.0, np.pi]))
     out = {f"path{i}": p for i, p in enumerate(pt.paths)}
-    for K, steps in ((4, 70), (10, 24)):
-        rec = {k: [] for k in ("path_id", "interp", "pose", "warm_T", "warm_u", "it0", "u", "iters", "cost")}
+    for K, steps in ((4, 70), (10, 24), (20, 24), (40, 16)):
+        rec = {k: [] for k in ("path_id", "interp", "pose", "warm_T", "warm_u", "it0", "u", "iters", "cost", "retries")}
         for pid in range(4):
             mpc = MPC(cm, K, 0.25, True, 1.0, 1.0)
             rng = np.random.default_rng(100 * K + pid)
@@ -115,12 +115,70 @@ def golden_mpc():
                 u = mpc.act({'path': path, 'interp_index': interp_idx, 'pose': pose})
                 rec["path_id"].append(pid); rec["interp"].append(float(interp_idx)); rec["pose"].append(pose.copy())
                 rec["warm_T"].append(wT); rec["warm_u"].append(wu); rec["it0"].append(it0); rec["u"].append(u.copy())
-                rec["iters"].append(SV.TRACE[-1][0]); rec["cost"].append(SV.TRACE[-1][1])
+                rec["iters"].append(SV.TRACE[-1][0]); rec["cost"].append(SV.TRACE[-1][1]); rec["retries"].append(len(SV.TRACE) - 1)
                 a = u[:2] + rng.normal(0, 0.05, 2)
                 a[0] = np.clip(a[0], 0, 1); a[1] = np.clip(a[1], -1, 1)
                 pose = Unicycle.step_external(pose, a, 0.25)
         for k, v in rec.items():
             out[f"K{K}_{k}"] = np.array(v)
+    # ---- forced failures: solves whose LM step fails, so that the reference's own `except: pose_error_scaling *= 5;
+    # continue` (mpc.py:188-190) runs. Candidates are found with the flat oracle (test infrastructure too), then EVERY
+    # recorded number comes from the reference's MPC.act. Two kinds per path:
+    #   "stale": solve, reset(), then a failing FIRST solve -> the retry deep-copies the warm start stored before the reset
+    #            (mpc.py:72-75: iteration0 is cleared before the solve)
+    #   "warm" : solve, then a far-away pose -> a failing warm-started solve retries from the same warm start
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dre_oracle_front", os.path.join(HERE, "oracle.py"))
+    O = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(O)
+    O.build()
+    stride = max(p.shape[1] for p in pt.paths)
+    tab = np.zeros((4, 3, stride)); lens = np.zeros(4, dtype=np.int32)
+    for i, p in enumerate(pt.paths):
+        tab[i, :, :p.shape[1]] = p; lens[i] = p.shape[1]
+    for K, per_kind in ((4, 4), (10, 2)):
+        rec = {k: [] for k in ("path_id", "interp", "pose", "warm_T", "warm_u", "it0", "u", "iters", "cost", "retries", "kind")}
+        for pid in range(4):
+            path = pt.paths[pid]
+            start_pose = path[:, 5] + np.array([0.05, -0.05, 0.05])
+            _, start_idx, _ = pt.localize_on_path(pt.kd_trees[pid], start_pose[:2], path, localize_to_start=True)
+
+            def armed(reset):
+                m = MPC(cm, K, 0.25, True, 1.0, 1.0)
+                m.act({'path': path, 'interp_index': start_idx, 'pose': start_pose})
+                if reset:
+                    m.reset()
+                return m
+            for kind, reset in (("stale", True), ("warm", False)):
+                wT, wu, _ = _warm_of(armed(False), K)
+                rng = np.random.default_rng(7000 + 10 * K + pid + (100 if reset else 0))
+                N = 3000
+                node = rng.integers(0, path.shape[1] - 1, N)
+                cand = path[:, node].T + rng.uniform(-0.7, 0.7, (N, 3))
+                interp = np.array([pt.localize_on_path(pt.kd_trees[pid], c[:2], path, localize_to_start=False)[1] for c in cand], dtype=np.float64)
+                mb = O.MpcBatch(N, O.mpc_params(K=K), tab, lens)
+                mb.warm_T[:] = wT; mb.warm_u[:] = wu; mb.iteration0[:] = 1 if reset else 0
+                _, st = mb.act(np.full(N, pid, np.int32), interp, cand)
+                picks = np.nonzero(st["retries"] > 0)[0][:per_kind]
+                assert len(picks) > 0, (K, pid, kind)
+                for i in picks:
+                    m = armed(reset)
+                    wT_i, wu_i, it0_i = _warm_of(m, K)
+                    if reset:   # _warm_of reports zeros while iteration0 is set; the stale warm start is still inside the object
+                        for k in range(K):
+                            Mx = m.next_se3_state_vars[k].value.matrix()
+                            wT_i[k] = [Mx[0, 0], Mx[1, 0], Mx[0, 3], Mx[1, 3]]
+                            wu_i[k] = m.next_vspace_state_vars[k].value[:, 0]
+                    SV.TRACE.clear()
+                    u = m.act({'path': path, 'interp_index': float(interp[i]), 'pose': cand[i]})
+                    assert len(SV.TRACE) >= 2, "the reference did not take its retry path on this candidate"
+                    rec["path_id"].append(pid); rec["interp"].append(float(interp[i])); rec["pose"].append(cand[i].copy())
+                    rec["warm_T"].append(wT_i); rec["warm_u"].append(wu_i); rec["it0"].append(it0_i); rec["u"].append(u.copy())
+                    rec["iters"].append(SV.TRACE[-1][0]); rec["cost"].append(SV.TRACE[-1][1]); rec["retries"].append(len(SV.TRACE) - 1)
+                    rec["kind"].append(0 if reset else 1)
+        for k, v in rec.items():
+            out[f"F{K}_{k}"] = np.array(v)
+        print(f"forced failures K={K}:", len(rec["u"]), "solves, retries", rec["retries"])
     SV.TRACE = None
     np.savez_compressed(os.path.join(OUT, "mpc_sequences.npz"), **out)
     print("mpc_sequences.npz", {k: v.shape for k, v in out.items() if k.endswith("_u")})
@@ -161,7 +219,7 @@ def golden_env():
     from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
     from environment.human_avoidance.utils.action import ActionRot
     out = {}
-    for tag, Nh, seed, steps in (("h6", 6, 0, 260), ("h10", 10, 1, 90), ("h20", 20, 2, 50)):
+    for tag, Nh, seed, steps in (("h6", 6, 0, 500), ("h10", 10, 1, 90), ("h20", 20, 2, 50)):
         cm = _config(Nh)
         env = HAAndPTEnv(cm, seed_addition=seed)
         env.case_counter['train'] = seed

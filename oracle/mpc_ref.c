@@ -507,20 +507,32 @@ void mpc_ref_act(const mpc_params *P, const double *path, int Lstride, int L, do
     init.K = K; init.dt = P->dt; init.vmax = P->vmax; init.wmax = P->wmax; init.pose_jac_exact = P->pose_jac_exact;
     for (int k = 0; k < K; ++k) init.M[k] = pose_to_inv_se2(ref[3 * k], ref[3 * k + 1], ref[3 * k + 2]);
     init.T[0] = pose_to_inv_se2(pose[0], pose[1], pose[2]);
+    /* what `deepcopy(self.next_*_state_vars)` (mpc.py:73-75) would yield: the warm start stored by the last successful
+     * solve. next_* are the ints 0 until the first solve has finished (mpc.py:52-53): warm_T is all zeros then. */
+    mpc_prob stored = init;
+    const int has_stored = warm_T[0] * warm_T[0] + warm_T[1] * warm_T[1] > 0.5;
+    for (int k = 0; k < K; ++k) {
+        se2 T = {warm_T[4 * k], warm_T[4 * k + 1], warm_T[4 * k + 2], warm_T[4 * k + 3]};
+        stored.T[k + 1] = T; stored.u[k][0] = warm_u[2 * k]; stored.u[k][1] = warm_u[2 * k + 1];
+    }
+    mpc_prob retry_init;
     if (*iteration0) {
         for (int k = 0; k < K; ++k) { init.T[k + 1] = init.M[k]; init.u[k][0] = P->vmax / 2.0; init.u[k][1] = 0.0; }
         *iteration0 = 0;
+        /* Reference quirk (mpc.py:72): iteration0 is cleared BEFORE the solve, so the pose_error_scaling retry of a failed
+         * first solve (mpc.py:188-190 -> :73-75) starts from the STORED warm start -- the one from before the reset().
+         * If nothing was ever stored the reference dies there (`deepcopy(0).insert` raises outside the try); the batch
+         * restarts from the iteration0 guess instead. */
+        retry_init = has_stored ? stored : init;
     } else {
-        for (int k = 0; k < K; ++k) {
-            se2 T = {warm_T[4 * k], warm_T[4 * k + 1], warm_T[4 * k + 2], warm_T[4 * k + 3]};
-            init.T[k + 1] = T; init.u[k][0] = warm_u[2 * k]; init.u[k][1] = warm_u[2 * k + 1];
-        }
+        init = stored;
+        retry_init = stored;
     }
     mpc_prob p;
     double s = 1.0;
     int term = 0;
     for (;;) {
-        p = init; p.s = s;
+        p = st.retries == 0 ? init : retry_init; p.s = s;
         term = mpc_optimize(&p, P, &st);
         if (term) break;
         if (st.retries >= P->max_retries) { term = -1; break; }

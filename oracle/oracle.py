@@ -145,13 +145,14 @@ class EnvCfg(ctypes.Structure):
                [("lookahead", ctypes.c_int32), ("lookbehind", ctypes.c_int32), ("mpc_actions_in_input", ctypes.c_int32),
                 ("auto_path_switch", ctypes.c_int32), ("seed", ctypes.c_uint64), ("env_id_offset", ctypes.c_int64),
                 ("mpc", MpcParams), ("paths", ctypes.c_void_p), ("lens", ctypes.c_void_p), ("num_paths", ctypes.c_int32),
-                ("path_stride", ctypes.c_int32)]
+                ("path_stride", ctypes.c_int32), ("soft_reset", ctypes.c_int32), ("sensor_restriction", ctypes.c_int32),
+                ("num_static", ctypes.c_int32), ("sensor_range", ctypes.c_double), ("static_pos", ctypes.c_double * 8)]
 
 
 _ENV_ARRAYS = ["hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime",
                "path_idx", "loc_to_start", "step_count", "reset_epoch", "warm_T", "warm_u", "iteration0",
                "pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid",
-               "detected_humans", "rewards", "info", "done_bits", "mpc_status"]
+               "detected_humans", "rewards", "info", "done_bits", "mpc_status", "sr_state", "actions_used", "soft_flags"]
 
 
 class EnvArrays(ctypes.Structure):
@@ -162,7 +163,8 @@ class EnvRef:
     """E reference environments held in numpy arrays with the engine's state / output layout."""
 
     def __init__(self, E, Nh, paths, lens, K=4, lookback=6, seed=0x00D24D9C, env_id_offset=0, auto_path_switch=True,
-                 end_goal_changing=True, neighbor_dist=10.0, actions_in_input=4, **over):
+                 end_goal_changing=True, neighbor_dist=10.0, actions_in_input=4, soft_reset=False, sensor_restriction=False,
+                 sensor_range=4.0, static_humans=(), **over):
         self.E, self.Nh, self.K, self.LB = E, Nh, K, lookback
         H, LB = lookback + 1, lookback
         self.paths = np.ascontiguousarray(paths, dtype=np.float64)
@@ -183,6 +185,10 @@ class EnvRef:
         c.lookahead, c.lookbehind, c.mpc_actions_in_input, c.auto_path_switch = 20, 5, actions_in_input, int(auto_path_switch)
         c.seed, c.env_id_offset = seed, env_id_offset
         c.mpc = mpc_params(K=K)
+        c.soft_reset, c.sensor_restriction, c.sensor_range = int(soft_reset), int(sensor_restriction), float(sensor_range)
+        c.num_static = len(static_humans)
+        for i, xy in enumerate(static_humans):
+            c.static_pos[2 * i], c.static_pos[2 * i + 1] = float(xy[0]), float(xy[1])
         for k, v in over.items():
             setattr(c, k, v)
         c.paths, c.lens = self.paths.ctypes.data, self.lens.ctypes.data
@@ -199,6 +205,7 @@ class EnvRef:
             "pt_state": z((E, 4 * 25)), "mpc_actions": z((E, nact)), "robot_node": z((E, 2 * LB)), "past_robot_vel": z((E, 2 * LB)),
             "percent_episode": z((E, 1)), "spatial_edges": z((E, Nh, 2 * H)), "human_valid": z((E, Nh)), "detected_humans": z(E),
             "rewards": z((E, 3)), "info": z((E, 8)), "done_bits": z(E, np.uint32), "mpc_status": z(E, MPC_STATS_DTYPE),
+            "sr_state": z((E, 4), np.int32), "actions_used": z((E, 2)), "soft_flags": z((E, 2), np.uint8),
         }
         self.A = EnvArrays(*[self.a[n].ctypes.data for n in _ENV_ARRAYS])
         L = lib()

@@ -15,7 +15,13 @@ def _mpc(K, N, paths):
     return m
 
 
-@pytest.mark.parametrize("K", [4, 10])
+# same envelope as tests/test_oracle_mpc.py: every golden solve within TOL, zero LM-iteration divergences, except the golden
+# indices listed here (empty)
+GOLDEN_TOL = 1e-6
+ALLOWED_DIVERGENT = {4: (), 10: (), 20: (), 40: ()}
+
+
+@pytest.mark.parametrize("K", [4, 10, 20, 40])
 def test_cuda_matches_reference_golden(golden_mpc, K):
     g = golden_mpc
     paths, tab, lens = mpc_path_table(g)
@@ -27,10 +33,11 @@ def test_cuda_matches_reference_golden(golden_mpc, K):
     d = np.abs(u - g[f"K{K}_u"]).max(axis=1)
     same = st["iterations"] == g[f"K{K}_iters"]
     regular = g[f"K{K}_interp"] < lens[g[f"K{K}_path_id"]] - 1 - 1.2375 * K
-    tight = d <= (1e-6 if K == 4 else 2e-6)
+    tight = d <= GOLDEN_TOL
     print(f"K={K}: max|du| same-branch={d[same & regular].max():.2e}, divergences={int((~tight).sum())}/{n}, max={d.max():.2e}")
-    assert tight[regular & same].all()
-    assert (~tight).sum() <= 0.12 * n and d.max() < 0.2
+    ok = np.ones(n, dtype=bool)
+    ok[list(ALLOWED_DIVERGENT[K])] = False
+    assert tight[ok].all() and same[ok].all(), (np.nonzero(~tight | ~same)[0], d.max())
     assert (st["term"] > 0).all()
 
 
@@ -158,3 +165,21 @@ def test_kernel_elementary_functions_accuracy():
         u = np.abs(y - ref) / np.spacing(np.abs(ref))
         print("%s: max ulp %.2f" % (f.__name__, u.max()))
         assert u.max() <= 2
+
+
+@pytest.mark.parametrize("K", [4, 10])
+def test_cuda_forced_failures_take_the_reference_retry_path(golden_mpc, K):
+    """The reference's own `except: pose_error_scaling *= 5; continue` (mpc.py:188-190) recorded on solves whose LM step
+    fails (oracle/make_golden.py): failing first solves after reset() (the retry starts from the warm start stored before
+    the reset, mpc.py:72-75) and failing warm-started solves. Retry and iteration counts equal, controls 1e-6."""
+    g = golden_mpc
+    paths, tab, lens = mpc_path_table(g)
+    n = g[f"F{K}_u"].shape[0]
+    m = _mpc(K, n, paths)
+    m.set_warm(g[f"F{K}_warm_T"], g[f"F{K}_warm_u"], g[f"F{K}_it0"])
+    u = m.act({'path_id': g[f"F{K}_path_id"], 'interp_index': g[f"F{K}_interp"], 'pose': g[f"F{K}_pose"]}, want_status=True)
+    st = m.last_status
+    d = np.abs(u - g[f"F{K}_u"]).max(axis=1)
+    print(f"K={K}: {n} failing solves, max|du|={d.max():.2e}")
+    assert np.array_equal(st["retries"], g[f"F{K}_retries"]) and np.array_equal(st["iterations"], g[f"F{K}_iters"])
+    assert d.max() <= 1e-6

@@ -4,14 +4,16 @@ import numpy as np
 import pytest
 from conftest import mpc_path_table
 
-# controls agree to TOL when both solvers take the same LM decision sequence; near the end of a path (v pinned at the
-# lower bound by the feasibility scaling) the reference itself is chaotic (1e-13 input perturbations move its output by
-# 1e-3), so those steps are counted as branch divergences and only bounded loosely.
-TOL = {4: 1e-6, 10: 2e-6}
-LOOSE = 0.2
+# Measured envelope (this container, gcc -O2 -ffp-contract=off): max |du| 4.3e-8 (K=4) / 5.0e-8 (K=10) / 9e-8 (K=20, 40) over
+# every golden solve, the outer-iteration count equal on every one. The assert is that envelope with one decade of head
+# room: EVERY solve within TOL and ZERO LM-iteration divergences, except the solves listed in ALLOWED_DIVERGENT (golden
+# index per horizon; empty today). Near the end of a path (v pinned at its lower bound by the feasibility scaling) the
+# reference itself is chaotic (a 1e-13 input perturbation moves its output by 1e-3), which is why the list exists at all.
+TOL = {4: 1e-6, 10: 1e-6, 20: 1e-6, 40: 1e-6}
+ALLOWED_DIVERGENT = {4: (), 10: (), 20: (), 40: ()}
 
 
-@pytest.mark.parametrize("K", [4, 10])
+@pytest.mark.parametrize("K", [4, 10, 20, 40])
 def test_oracle_matches_reference_teacher_forced(oracle, golden_mpc, K):
     g = golden_mpc
     paths, tab, lens = mpc_path_table(g)
@@ -25,8 +27,10 @@ def test_oracle_matches_reference_teacher_forced(oracle, golden_mpc, K):
     tight = d <= TOL[K]
     print(f"K={K}: {n} solves, max|du| same-branch={d[same & regular].max():.2e}, divergences={int((~tight).sum())}, "
           f"max|du| overall={d.max():.2e}")
-    assert tight[regular & same].all()
-    assert (~tight).sum() <= 0.12 * n and d.max() < LOOSE
+    ok = np.ones(n, dtype=bool)
+    ok[list(ALLOWED_DIVERGENT[K])] = False
+    assert tight[ok].all() and same[ok].all(), (np.nonzero(~tight | ~same)[0], d.max())
+    assert (~regular).any()                      # the end-of-path clamp of the reference poses is in the fixture
     assert (st["term"] > 0).all()
     # final costs agree wherever the controls do
     assert np.allclose(st["final_cost"][tight], g[f"K{K}_cost"][tight], rtol=1e-6, atol=1e-9)
@@ -56,3 +60,23 @@ def test_controls_respect_bounds(oracle, golden_mpc):
     u, st = mb.act(pid, idx, pose)
     v, w = u[:, 0::2], u[:, 1::2]
     assert (v > 0).all() and (v < 1).all() and (np.abs(w) < 1).all()
+
+
+@pytest.mark.parametrize("K", [4, 10])
+def test_oracle_forced_failures_take_the_reference_retry_path(oracle, golden_mpc, K):
+    """Solves whose LM step fails, recorded from the reference's own MPC.act: its `except: pose_error_scaling *= 5; continue`
+    (mpc.py:188-190) ran on every one. kind 0: a failing FIRST solve after reset() -- the retry starts from the warm start
+    stored BEFORE the reset (mpc.py:72-75 clears iteration0 before the solve); kind 1: a failing warm-started solve."""
+    g = golden_mpc
+    paths, tab, lens = mpc_path_table(g)
+    n = g[f"F{K}_u"].shape[0]
+    mb = oracle.MpcBatch(n, oracle.mpc_params(K=K), tab, lens)
+    mb.warm_T[:] = g[f"F{K}_warm_T"]; mb.warm_u[:] = g[f"F{K}_warm_u"]; mb.iteration0[:] = g[f"F{K}_it0"]
+    u, st = mb.act(g[f"F{K}_path_id"], g[f"F{K}_interp"], g[f"F{K}_pose"])
+    d = np.abs(u - g[f"F{K}_u"]).max(axis=1)
+    print(f"K={K}: {n} failing solves ({int((g[f'F{K}_kind'] == 0).sum())} after reset), max|du|={d.max():.2e}, retries {st['retries'].tolist()}")
+    assert (g[f"F{K}_retries"] >= 1).all() and (g[f"F{K}_kind"] == 0).any() and (g[f"F{K}_kind"] == 1).any()
+    assert np.array_equal(st["retries"], g[f"F{K}_retries"])
+    assert np.array_equal(st["iterations"], g[f"F{K}_iters"])
+    assert d.max() <= 1e-6
+    assert np.allclose(st["final_cost"], g[f"F{K}_cost"], rtol=1e-6, atol=1e-9)

@@ -94,6 +94,15 @@ def load():
         L.dre_env_set_paths.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp]
         L.dre_env_state.argtypes = [c_vp, P(EnvStateView)]
         L.dre_env_outputs.argtypes = [c_vp, P(StepOut)]
+        L.dre_env_outputs_at.argtypes = [c_vp, c_i32, P(StepOut)]
+        L.dre_env_current_slab.argtypes = [c_vp]
+        L.dre_env_reset_masked.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.dre_env_observe_masked.argtypes = [c_vp, c_vp, c_i32, c_vp]
+        L.dre_env_switch_path.argtypes = [c_vp, c_vp, c_vp]
+        L.dre_env_soft_reset_decide.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]
+        L.dre_stats_comm_id.argtypes = [c_vp]
+        L.dre_env_stats_comm_init.argtypes = [c_vp, c_vp, c_i32, c_i32]
+        L.dre_stats_reduce.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]
         L.dre_env_mpc.restype = c_vp
         L.dre_env_mpc.argtypes = [c_vp]
         L.dre_env_reset.argtypes = [c_vp, c_vp, c_vp, c_vp]

@@ -12,6 +12,8 @@ void dre_set_cuda_error(cudaError_t e, const char *file, int line)
     snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
 }
 
+void dre_set_error_text(const char *msg) { snprintf(g_cuda_err, sizeof g_cuda_err, "%s", msg); }
+
 extern "C" const char *dre_last_cuda_error(void) { return g_cuda_err; }
 
 extern "C" const char *dre_strerror(int code)

@@ -6,16 +6,63 @@
 #include <ctime>
 #include <new>
 #include <vector>
+#include <dlfcn.h>
 #include "env_launch.cuh"
+
+namespace {
+struct NcclApi {
+    // nccl.h: ncclUniqueId is a 128-byte struct passed BY VALUE to ncclCommInitRank
+    struct UniqueId { char internal[128]; };
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return api;
+    api.GetUniqueId = (int (*)(NcclApi::UniqueId *))dlsym(lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, NcclApi::UniqueId, int))dlsym(lib, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(void *))dlsym(lib, "ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+    return api;
+}
+int nccl_fail(int rc, int line)
+{
+    const NcclApi &A = nccl_api();
+    char msg[256];
+    snprintf(msg, sizeof msg, "NCCL error %d (%s) at %s:%d", rc, A.GetErrorString ? A.GetErrorString(rc) : "?", __FILE__, line);
+    dre_set_error_text(msg);
+    return DRE_ERR_CUDA;
+}
+enum { kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };   // nccl.h: ncclDataType_t / ncclRedOp_t
+}  // namespace
 
 struct dre_env {
     dre_env_config cfg;
     EnvDev D;
     dre_mpc *mpc = nullptr;
     void *state_block = nullptr;   // one allocation for the whole SoA state
-    void *slab = nullptr;          // one allocation for all outputs of a step
+    // Outputs of a step: one contiguous slab, DOUBLE-BUFFERED -- step t writes slab t & 1, so the S a caller got from
+    // step t-1 (zero-copy views) is still intact while it holds S' of step t: `insert(S, a, S'); S = S'` needs no clone.
+    void *slabs[2] = {nullptr, nullptr};
+    dre_step_out outs[2];
+    EnvOutDev outdev[2];
+    int cur = 0;                   // slab holding the latest outputs
+    void *slab = nullptr;          // = slabs[cur]
     size_t slab_bytes = 0;
-    dre_step_out out;
+    dre_step_out out;              // = outs[cur]
     double *d_actions = nullptr;   // staging for step_host
     cudaStream_t own_stream = nullptr;
     // step_host pipeline: one crowd-half launch; the last CTA of every env chunk raises a flag in mapped host memory,
@@ -36,6 +83,7 @@ struct dre_env {
     int step_seq = 0;
     int host_chunks = 8;
     bool was_reset = false;
+    void *stats_comm = nullptr;    // ncclComm_t of dre_env_stats_comm_init (the only collective of the engine)
     // per-kernel timing (bench.py's roofline leg)
     bool profiling = false;
     static const int PROF_RING = 64;
@@ -128,6 +176,16 @@ void carve_slab(const EnvDev &D, int n_mpc_act, void *base, dre_step_out &o, Env
     o.slab_bytes = bytes;
 }
 
+// make slab `b` the one the next launches write (and dre_env_outputs reports); the other one holds the previous step
+void use_slab(dre_env *h, int b)
+{
+    h->cur = b;
+    h->slab = h->slabs[b];
+    h->out = h->outs[b];
+    h->D.out = h->outdev[b];
+    h->D.prev_done_bits = h->outdev[b ^ 1].done_bits;
+}
+
 int n_mpc_actions(const dre_env_config &c)
 {
     const int a = c.mpc_actions_in_input > 0 ? c.mpc_actions_in_input : 4;
@@ -176,7 +234,8 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     carve_slab(D, n_mpc_actions(*cfg), nullptr, h->out, od, obytes);
     cudaError_t e;
     if ((e = cudaMalloc(&h->state_block, sbytes)) != cudaSuccess || (e = cudaMemset(h->state_block, 0, sbytes)) != cudaSuccess ||
-        (e = cudaMalloc(&h->slab, obytes)) != cudaSuccess || (e = cudaMemset(h->slab, 0, obytes)) != cudaSuccess ||
+        (e = cudaMalloc(&h->slabs[0], obytes)) != cudaSuccess || (e = cudaMemset(h->slabs[0], 0, obytes)) != cudaSuccess ||
+        (e = cudaMalloc(&h->slabs[1], obytes)) != cudaSuccess || (e = cudaMemset(h->slabs[1], 0, obytes)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_actions, (size_t)D.E * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -197,8 +256,9 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     }
     memset(h->h_flags, 0, dre_env::MAX_CHUNKS * sizeof(int));
     carve_state(D, h->state_block, sbytes);
-    carve_slab(D, n_mpc_actions(*cfg), h->slab, h->out, D.out, obytes);
+    for (int b = 0; b < 2; ++b) carve_slab(D, n_mpc_actions(*cfg), h->slabs[b], h->outs[b], h->outdev[b], obytes);
     h->slab_bytes = obytes;
+    use_slab(h, 0);
     D.mpc_iteration0 = dre_mpc_state_of(h->mpc).iteration0;
     *out = h;
     return DRE_OK;
@@ -210,7 +270,7 @@ extern "C" int dre_env_destroy(dre_env *h)
     cudaDeviceSynchronize();
     dre_mpc_destroy(h->mpc);
     if (h->profiling) dre_env_set_profiling(h, 0);
-    cudaFree(h->state_block); cudaFree(h->slab); cudaFree(h->d_actions);
+    cudaFree(h->state_block); cudaFree(h->slabs[0]); cudaFree(h->slabs[1]); cudaFree(h->d_actions);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
@@ -222,6 +282,7 @@ extern "C" int dre_env_destroy(dre_env *h)
     if (h->mpc_stream) cudaStreamDestroy(h->mpc_stream);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->d_chunk_count);
+    if (h->stats_comm && nccl_api().ok) nccl_api().CommDestroy(h->stats_comm);
     delete h;
     return DRE_OK;
 }
@@ -254,51 +315,87 @@ extern "C" int dre_env_outputs(dre_env *h, dre_step_out *out)
     return DRE_OK;
 }
 
+extern "C" int dre_env_outputs_at(dre_env *h, int32_t which, dre_step_out *out)
+{
+    if (!h || !out || (which != 0 && which != 1)) return DRE_ERR_INVALID;
+    *out = h->outs[which];
+    return DRE_OK;
+}
+
+extern "C" int dre_env_current_slab(dre_env *h) { return h ? h->cur : DRE_ERR_INVALID; }
+
 extern "C" dre_mpc *dre_env_mpc(dre_env *h) { return h ? h->mpc : nullptr; }
 
-static int env_solve_mpc(dre_env *h, cudaStream_t s)
+static int env_solve_mpc(dre_env *h, const EnvDev &D, cudaStream_t s)
 {
-    const EnvDev &D = h->D;
     const int nact = n_mpc_actions(h->cfg);
     int rc = dre_mpc_launch(dre_mpc_params_of(h->mpc), dre_mpc_state_of(h->mpc), D.path_idx, D.mpc_interp, D.rpose, 4,
-                            D.out.mpc_actions, nact, nact, D.out.mpc_status, nullptr, s);
+                            D.out.mpc_actions, nact, nact, D.out.mpc_status, D.env_mask, s);
     if (rc) return rc;
     return dre_env_launch_mpc_stats(D, s);
 }
 
-extern "C" int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream)
+extern "C" int dre_env_observe_masked(dre_env *h, const uint8_t *env_mask, int32_t solve_mpc, void *stream)
 {
     if (!h) return DRE_ERR_INVALID;
     if (!h->D.paths) return DRE_ERR_STATE;
     cudaStream_t s = (cudaStream_t)stream;
     h->last_stream = s; h->last_stream_set = true;
-    int rc = dre_env_launch_ha(h->D, 2, 1, s);
+    EnvDev D = h->D;
+    D.env_mask = env_mask;
+    int rc = dre_env_launch_ha(D, 2, 1, s);
     if (rc) return rc;
-    rc = dre_env_launch_pt(h->D, 1, s);
+    rc = dre_env_launch_pt(D, 1, s);
     if (rc) return rc;
-    return solve_mpc ? env_solve_mpc(h, s) : DRE_OK;
+    return solve_mpc ? env_solve_mpc(h, D, s) : DRE_OK;
 }
 
-extern "C" int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream)
+extern "C" int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream) { return dre_env_observe_masked(h, nullptr, solve_mpc, stream); }
+
+extern "C" int dre_env_reset_masked(dre_env *h, const uint8_t *env_mask, const double *hpos_init, const double *hgoal_init, void *stream)
 {
     if (!h) return DRE_ERR_INVALID;
     if (!h->D.paths) return DRE_ERR_STATE;
+    if (env_mask && !h->was_reset) return DRE_ERR_STATE;   // the other envs must hold a valid episode
     cudaStream_t s = (cudaStream_t)stream;
     h->last_stream = s; h->last_stream_set = true;
-    int rc = dre_env_launch_reset(h->D, hpos_init, hgoal_init, s);
+    EnvDev D = h->D;
+    D.env_mask = env_mask;
+    int rc = dre_env_launch_reset(D, hpos_init, hgoal_init, s);
     if (rc) return rc;
     // S_PT = PT_env.reset(...) incl. the first MPC solve (HA_and_PT env.py:268)
-    rc = dre_env_launch_pt(h->D, 1, s);
+    rc = dre_env_launch_pt(D, 1, s);
     if (rc) return rc;
-    rc = env_solve_mpc(h, s);
+    rc = env_solve_mpc(h, D, s);
     if (rc) return rc;
     // HA_env.reset + warm_start(lookback) (HA_and_PT env.py:274-276)
-    for (int w = 0; w < h->D.LB; ++w) {
-        rc = dre_env_launch_ha(h->D, 1, w == h->D.LB - 1 ? 1 : 0, s);
+    for (int w = 0; w < D.LB; ++w) {
+        rc = dre_env_launch_ha(D, 1, w == D.LB - 1 ? 1 : 0, s);
         if (rc) return rc;
     }
     h->was_reset = true;
     return DRE_OK;
+}
+
+extern "C" int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream)
+{
+    return dre_env_reset_masked(h, nullptr, hpos_init, hgoal_init, stream);
+}
+
+extern "C" int dre_env_switch_path(dre_env *h, const uint8_t *env_mask, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    EnvDev D = h->D;
+    D.env_mask = env_mask;
+    return dre_env_launch_switch_path(D, (cudaStream_t)stream);
+}
+
+extern "C" int dre_env_soft_reset_decide(dre_env *h, int32_t commit, uint8_t *scripted, double *actions, uint8_t *stuck, void *stream)
+{
+    if (!h || !scripted || !actions) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    return dre_env_launch_sr_decide(h->D, commit, scripted, actions, stuck, (cudaStream_t)stream);
 }
 
 extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
@@ -307,6 +404,7 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
     cudaStream_t s = (cudaStream_t)stream;
     h->last_stream = s; h->last_stream_set = true;
+    use_slab(h, h->cur ^ 1);       // this step's outputs go to the other slab; the previous step's stay readable
     EnvDev D = h->D;
     D.actions = actions;
     // robot/path half, crowd half (which merges rewards / dones), MPC solve: see env_kernels.cu. The crowd half and the
@@ -319,18 +417,18 @@ extern "C" int dre_env_step(dre_env *h, const double *actions, void *stream)
         if (overlap == 0) {
             rc = dre_env_launch_ha(D, 0, 1, s);
             if (rc) return rc;
-            return env_solve_mpc(h, s);
+            return env_solve_mpc(h, D, s);
         }
         DRE_CUDA_TRY(cudaEventRecord(h->ev_fork, s));
         DRE_CUDA_TRY(cudaStreamWaitEvent(h->mpc_stream, h->ev_fork, 0));
         if (overlap == 1) {
-            rc = env_solve_mpc(h, h->mpc_stream);
+            rc = env_solve_mpc(h, D, h->mpc_stream);
             if (rc) return rc;
             rc = dre_env_launch_ha(D, 0, 1, s);
         } else {
             rc = dre_env_launch_ha(D, 0, 1, s);
             if (rc) return rc;
-            rc = env_solve_mpc(h, h->mpc_stream);
+            rc = env_solve_mpc(h, D, h->mpc_stream);
         }
         if (rc) return rc;
         DRE_CUDA_TRY(cudaEventRecord(h->ev_join, h->mpc_stream));
@@ -407,6 +505,7 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
         h->last_stream_set = false;
     }
     DRE_CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)E * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    use_slab(h, h->cur ^ 1);
     EnvDev D = h->D;
     D.actions = h->d_actions;
     char *dev = (char *)h->slab, *host = (char *)slab_host;
@@ -438,7 +537,7 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     // The solve stays BEHIND the crowd half here, not next to it as in dre_env_step: this path is bound by the copies, and
     // a solve that shares the SMs delays the chunk flags (measured p50 1.19 ms serial vs 1.27 ms concurrent, also with the
     // solve on a lowest-priority stream: priorities do not stop its persistent CTAs from taking freed slots early).
-    rc = env_solve_mpc(h, s);
+    rc = env_solve_mpc(h, D, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));      // step done
     if (tr) t_enq = now_us();
@@ -526,5 +625,52 @@ extern "C" int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_d
         DRE_CUDA_TRY(cudaMemsetAsync(h->D.stat_counters, 0, 16 * sizeof(int64_t), s));
         DRE_CUDA_TRY(cudaMemsetAsync(h->D.stat_sums, 0, 4 * sizeof(double), s));
     }
+    return DRE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Episode statistics across GPUs: the ONE collective of the engine: an all-reduce(sum) of 16 counters + 4
+// sums over NCCL / NVLink per reporting interval. libnccl is not linked: the entry points are resolved at run time from
+// the libnccl.so.2 the process has loaded (torch's) or can load; a process that never reduces never needs it.
+// ---------------------------------------------------------------------------------------------------------------
+
+extern "C" int dre_stats_comm_id(char *id128)
+{
+    if (!id128) return DRE_ERR_INVALID;
+    const NcclApi &A = nccl_api();
+    if (!A.ok) { dre_set_error_text("libnccl.so.2 could not be loaded"); return DRE_ERR_CUDA; }
+    NcclApi::UniqueId id;
+    const int rc = A.GetUniqueId(&id);
+    if (rc) return nccl_fail(rc, __LINE__);
+    memcpy(id128, id.internal, 128);
+    return DRE_OK;
+}
+
+extern "C" int dre_env_stats_comm_init(dre_env *h, const char *id128, int32_t rank, int32_t world)
+{
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return DRE_ERR_INVALID;
+    const NcclApi &A = nccl_api();
+    if (!A.ok) { dre_set_error_text("libnccl.so.2 could not be loaded"); return DRE_ERR_CUDA; }
+    if (h->stats_comm) { A.CommDestroy(h->stats_comm); h->stats_comm = nullptr; }
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = A.CommInitRank(&h->stats_comm, world, id, rank);
+    if (rc) return nccl_fail(rc, __LINE__);
+    return DRE_OK;
+}
+
+extern "C" int dre_stats_reduce(dre_env *h, void *nccl_comm, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream)
+{
+    if (!h || !counters_dev16 || !sums_dev4) return DRE_ERR_INVALID;
+    void *comm = nccl_comm ? nccl_comm : h->stats_comm;
+    if (!comm) return DRE_ERR_STATE;
+    const NcclApi &A = nccl_api();
+    if (!A.ok) { dre_set_error_text("libnccl.so.2 could not be loaded"); return DRE_ERR_CUDA; }
+    int rc = dre_env_stats(h, counters_dev16, sums_dev4, reset, stream);
+    if (rc) return rc;
+    rc = A.AllReduce(counters_dev16, counters_dev16, 16, kNcclInt64, kNcclSum, comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(rc, __LINE__);
+    rc = A.AllReduce(sums_dev4, sums_dev4, 4, kNcclFloat64, kNcclSum, comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(rc, __LINE__);
     return DRE_OK;
 }

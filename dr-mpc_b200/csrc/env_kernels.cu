@@ -51,7 +51,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
 template <int G, bool REUSE>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
-                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse)
+                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse, const int *flags)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
@@ -66,7 +66,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
         ag = g.bcast(ag, 0);
         if (ag >= EPB * Nh) break;
         const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
-        if (e >= D.E) continue;
+        if (flags[el * 4 + 2] == 0) continue;
         const size_t gidx = (size_t)e * Nh + i;
         float ox = 0.f, oy = 0.f;
         if (REUSE && reuse && D.cache_valid[e] && !D.goal_changed[gidx]) {
@@ -138,13 +138,24 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     long long tr_t = clock64();
 #endif
 
+    // per-env flags: [0] a goal was reached, [1] visible humans (sensor restriction), [2] the env takes part in this launch
+    // (in range and selected by the mask of a masked reset / observe), [3] spare; then the two ORCA work counters
+    for (int t = threadIdx.x; t < EPB * 4 + 2; t += blockDim.x) {
+        int v = 0;
+        if (t < EPB * 4 && (t & 3) == 2) { const int e = env0 + (t >> 2); v = e < D.E && (D.env_mask == nullptr || D.env_mask[e] != 0); }
+        flags[t] = v;
+    }
+    if (threadIdx.x < 12) s_cnt[threadIdx.x] = 0ull;   // 9 counters + 3 double sums (0.0 == all-zero bits)
+    __syncthreads();
+#define ENV_OFF(el) (flags[(el) * 4 + 2] == 0)
+
     if (mode != 2) {
         // ---- stage tile ----
         for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
             const int el = t / nA, a = t - el * nA, e = env0 + el;
             float *A = agents + (size_t)el * 5 * nA;
             float x = 0.f, y = 0.f, vx = 0.f, vy = 0.f;
-            if (e < D.E) {
+            if (!ENV_OFF(el)) {
                 if (a < Nh) {
                     const double2 q = D.hpos[(size_t)e * Nh + a];
                     const float2 v = D.hvel[(size_t)e * Nh + a];
@@ -158,22 +169,20 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
             }
             A[a] = x; A[nA + a] = y; A[2 * nA + a] = vx; A[3 * nA + a] = vy; A[4 * nA + a] = D.orca.radius;
         }
-        for (int t = threadIdx.x; t < EPB * 4 + 2; t += blockDim.x) flags[t] = 0;
-        if (threadIdx.x < 12) s_cnt[threadIdx.x] = 0ull;   // 9 counters + 3 double sums (0.0 == all-zero bits)
         __syncthreads();
 
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
         // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
         // instruction cache together)
         orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
-                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0);
+                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0, flags);
         __syncthreads();
 
         DRE_HA_T(12);   // stage + pass 1
         // ---- integrate: robot (unicycle, agent.py:169-176) and humans (Euler, agent.py:164-168); histories ----
         for (int t = threadIdx.x; t < EPB * (Nh + 1); t += blockDim.x) {
             const int el = t / (Nh + 1), a = t - el * (Nh + 1), e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             if (a < Nh) {
                 const size_t gidx = (size_t)e * Nh + a;
                 const double2 q = D.hpos[gidx];
@@ -242,7 +251,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         if (D.sensor_restriction) {
             for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
                 const int e = env0 + el;
-                if (e >= D.E) continue;
+                if (ENV_OFF(el)) continue;
                 int nv = 0;
                 for (int i = 0; i < Nh; ++i) src_row[el * Nh + i] = i;
                 for (int i = 0; i < Nh; ++i)
@@ -253,7 +262,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
         for (int t = threadIdx.x; t < EPB * Nh * H; t += blockDim.x) {
             const int el = t / (Nh * H), r = t - el * Nh * H, i = r / H, s = r - i * H, e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             const int src = D.sensor_restriction ? src_row[el * Nh + i] : i;
             double st, ct;
             sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
@@ -267,7 +276,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int el = t / Nh, i = t - el * Nh, e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             double hv = (double)D.hvalid[(size_t)e * Nh + i];
             if (D.sensor_restriction) {
                 const int nv = flags[el * 4 + 1];
@@ -277,7 +286,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
         for (int t = threadIdx.x; t < EPB * D.LB; t += blockDim.x) {
             const int el = t / D.LB, s = t - el * D.LB, e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             double st, ct;
             sincos(D.rpose[(size_t)e * 4 + 2], &st, &ct);
             const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
@@ -290,7 +299,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
         for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
             const int e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             D.out.percent_episode[e] = D.gtime[e] / D.time_limit * 10.0 - 5.0;
             int det = Nh;
             if (D.sensor_restriction) det = flags[el * 4 + 1] > 0 ? flags[el * 4 + 1] : 1;
@@ -323,25 +332,25 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
 #ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
-        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false);
+        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags);
 #endif
         __syncthreads();
         if (DEDUP) {   // keep the look-ahead velocities: they are the next step's movement pass
             for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
                 const int el = t / Nh, i = t - el * Nh, e = env0 + el;
-                if (e >= D.E) continue;
+                if (ENV_OFF(el)) continue;
                 D.hvel_next[(size_t)e * Nh + i] = vnext[el * Nh + i];
                 D.goal_changed[(size_t)e * Nh + i] = 0;
             }
             for (int el = threadIdx.x; el < EPB; el += blockDim.x)
-                if (env0 + el < D.E) D.cache_valid[env0 + el] = 1;
+                if (!ENV_OFF(el)) D.cache_valid[env0 + el] = 1;
         }
 
         DRE_HA_T(14);   // pass 2
         // ---- per-human reward terms (human_avoidance_env.py:205-216, 247-273) ----
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int el = t / Nh, i = t - el * Nh, e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             const double2 hp = posd[el * Nh + i];
             const double rx = D.rpose[(size_t)e * 4], ry = D.rpose[(size_t)e * 4 + 1];
             const double dx = hp.x - rx, dy = hp.y - ry;
@@ -368,7 +377,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- per-env reward / done (one thread per env sums in human order, like the reference loop) ----
         for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
             const int e = env0 + el;
-            if (e >= D.E) continue;
+            if (ENV_OFF(el)) continue;
             double dmin = INFINITY, pen_v = 0.0, pen_th = 0.0;
             bool collision = false;
             for (int i = 0; i < Nh; ++i) {
@@ -429,7 +438,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     if (mode != 2 && D.end_goal_changing) {
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int el = t / Nh, i = t - el * Nh, e = env0 + el;
-            if (e >= D.E || D.hstatic[(size_t)e * Nh + i]) continue;
+            if (ENV_OFF(el) || D.hstatic[(size_t)e * Nh + i]) continue;
             const double2 p = posd[el * Nh + i], gl = D.hgoal[(size_t)e * Nh + i];
             const double dx = gl.x - p.x, dy = gl.y - p.y;
             if (sqrt(dx * dx + dy * dy) < D.human_radius) atomicOr(&flags[el * 4], 1);
@@ -438,7 +447,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         DRE_HA_T2(14);  // goal-reached detection
         for (int el = threadIdx.x; el < EPB; el += blockDim.x) {
             const int e = env0 + el;
-            if (e >= D.E || !flags[el * 4]) continue;
+            if (ENV_OFF(el) || !flags[el * 4]) continue;
             const uint64_t gid = (uint64_t)(D.env_id_offset + e);
             const uint64_t stp = (uint64_t)D.step_count[e];
             const uint32_t epoch = (uint32_t)D.reset_epoch[e], kind = mode == 1 ? DRE_RNG_WARM : DRE_RNG_STEP, sub = mode == 1 ? (uint32_t)D.rvalid[e] : 0u;
@@ -484,7 +493,8 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     // a warm-start step moves the crowd without a look-ahead pass: whatever was cached is stale
     if (DEDUP && mode == 1)
         for (int el = threadIdx.x; el < EPB; el += blockDim.x)
-            if (env0 + el < D.E) D.cache_valid[env0 + el] = 0;
+            if (!ENV_OFF(el)) D.cache_valid[env0 + el] = 0;
+#undef ENV_OFF
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -541,19 +551,27 @@ __global__ void __launch_bounds__(128, 8) pt_step_kernel(EnvDev D, int mode)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = gt & (PT_LANES - 1);
-    const bool valid = (gt / PT_LANES) < D.E;
-    const int e = valid ? gt / PT_LANES : D.E - 1;            // surplus groups shadow the last env and store nothing
+    const bool in_range = (gt / PT_LANES) < D.E;
+    // Surplus groups of the last warp (and envs a masked launch leaves alone) run the same code -- the shuffles below use the
+    // full-warp mask -- and store nothing. Surplus groups work on constants: they must not read state another group writes.
+    const int e = in_range ? gt / PT_LANES : 0;
+    const bool valid = in_range && (D.env_mask == nullptr || D.env_mask[e] != 0);
     const bool writer = valid && lane == 0;
     const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(PT_LANES - 1);
 
-    int pid = D.path_idx[e];
+    int pid = in_range ? D.path_idx[e] : 0;
     PathView P = path_view(D.paths, D.path_stride, pid, D.lens);
     double *rp = D.rpose + (size_t)e * 4;
-    double cx = rp[0], cy = rp[1], cth = rp[2];
-    bool lts = D.loc_to_start[e] != 0;
-    const uint32_t prev_bits = D.out.done_bits[e];
+    double cx = 0.0, cy = 0.0, cth = 0.0;
+    bool lts = true;
+    uint32_t prev_bits = 0u;
     double av = 0.0, aw = 0.0;
-    if (mode == 0) { av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1]; }
+    if (in_range) {
+        cx = rp[0]; cy = rp[1]; cth = rp[2];
+        lts = D.loc_to_start[e] != 0;
+        prev_bits = D.prev_done_bits[e];
+        if (mode == 0) { av = D.actions[(size_t)e * 2]; aw = D.actions[(size_t)e * 2 + 1]; }
+    }
     __syncwarp();                                             // every lane has read the state lane 0 is about to overwrite
     Localization cur;
     if (mode == 0) {
@@ -561,7 +579,7 @@ __global__ void __launch_bounds__(128, 8) pt_step_kernel(EnvDev D, int mode)
         uint32_t sr_flags = 0;
         if (D.soft_reset) {
             double sv = av, sw = aw;
-            if (lane == 0) {
+            if (lane == 0 && in_range) {
                 SrState S = sr_unpack(D.sr_state + (size_t)e * 4);
                 bool stuck;
                 if (soft_reset_decide(S, prev_bits, P, cx, cy, cth, lts, sv, sw, stuck)) sr_flags |= 1u;
@@ -668,7 +686,7 @@ __global__ void mpc_stats_kernel(EnvDev D)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long r = 0, gup = 0;
-    if (e < D.E) { r = (unsigned long long)D.out.mpc_status[e].retries; gup = D.out.mpc_status[e].term < 0 ? 1 : 0; }
+    if (e < D.E && (D.env_mask == nullptr || D.env_mask[e] != 0)) { r = (unsigned long long)D.out.mpc_status[e].retries; gup = D.out.mpc_status[e].term < 0 ? 1 : 0; }
     for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); gup += __shfl_xor_sync(0xffffffffu, gup, o); }
     if ((threadIdx.x & 31) == 0) {
         if (r) atomicAdd(D.stat_counters + 9, r);
@@ -682,7 +700,7 @@ __global__ void mpc_stats_kernel(EnvDev D)
 __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 *hpos_init, const double2 *hgoal_init)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= D.E) return;
+    if (e >= D.E || (D.env_mask != nullptr && D.env_mask[e] == 0)) return;
     const int Nh = D.Nh, H = D.LB + 1;
     const double rx = 0.0, ry = -D.circle_radius, rth = DRE_PI;   // set_robot_reset(start_angle=pi), HA_and_PT env.py:264,286-299
     double *rp = D.rpose + (size_t)e * 4;
@@ -935,6 +953,49 @@ int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s)
 {
     if (!D.stat_counters) return DRE_OK;
     mpc_stats_kernel<<<(D.E + 255) / 256, 256, 0, s>>>(D);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+// HAAndPTEnv.soft_reset's path switch (HA_and_PT env.py:130-141) for the masked envs: next path, localise to its start,
+// MPC.reset(). The caller regenerates S with dre_env_observe_masked(mask, solve_mpc = 1) like PT_env.soft_reset (:141-148).
+__global__ void switch_path_kernel(EnvDev D)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D.E || (D.env_mask != nullptr && D.env_mask[e] == 0)) return;
+    D.path_idx[e] = (D.path_idx[e] + 1) % D.num_paths;
+    D.loc_to_start[e] = 1;
+    D.mpc_iteration0[e] = 1;
+}
+
+int dre_env_launch_switch_path(const EnvDev &D, cudaStream_t s)
+{
+    switch_path_kernel<<<(D.E + 127) / 128, 128, 0, s>>>(D);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+// The soft-reset machine's decision for the NEXT step of every env, from the latest step's done word: what a host-side
+// caller that drives HAAndPTEnv.soft_reset's loop itself (one self.step(action, soft_reset=True) per decision) needs.
+__global__ void sr_decide_kernel(EnvDev D, int commit, uint8_t *__restrict__ scripted, double *__restrict__ actions, uint8_t *__restrict__ stuck_out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D.E) return;
+    SrState S = sr_unpack(D.sr_state + (size_t)e * 4);
+    const PathView P = path_view(D.paths, D.path_stride, D.path_idx[e], D.lens);
+    double av = 0.0, aw = 0.0;
+    bool stuck = false;
+    const int sc = soft_reset_decide(S, D.out.done_bits[e], P, D.rpose[(size_t)e * 4], D.rpose[(size_t)e * 4 + 1], D.rpose[(size_t)e * 4 + 2],
+                                     D.loc_to_start[e] != 0, av, aw, stuck);
+    if (commit) sr_pack(S, D.sr_state + (size_t)e * 4);
+    scripted[e] = (uint8_t)sc;
+    actions[(size_t)e * 2] = av; actions[(size_t)e * 2 + 1] = aw;
+    if (stuck_out) stuck_out[e] = stuck ? 1 : 0;
+}
+
+int dre_env_launch_sr_decide(const EnvDev &D, int commit, uint8_t *scripted, double *actions, uint8_t *stuck, cudaStream_t s)
+{
+    sr_decide_kernel<<<(D.E + 127) / 128, 128, 0, s>>>(D, commit, scripted, actions, stuck);
     DRE_CUDA_TRY(cudaGetLastError());
     return DRE_OK;
 }

@@ -58,6 +58,8 @@ struct EnvDev {
     int num_paths, path_stride;
     // ---- per-step input / output ----
     const double *actions;  // [E][2]
+    const uint8_t *env_mask;            // [E] or nullptr: masked reset / observe touch only the envs whose byte is non-zero
+    const uint32_t *prev_done_bits;     // [E] done word of the previous step (the output slab is double-buffered)
     EnvOutDev out;
     unsigned long long *stat_counters;  // [16]
     double *stat_sums;                  // [4]
@@ -70,6 +72,8 @@ int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s);
 int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, const double *backup, int A, double *safe_out,
                         int32_t *info, uint8_t *cand_safe, cudaStream_t s);
 int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s);
+int dre_env_launch_switch_path(const EnvDev &D, cudaStream_t s);
+int dre_env_launch_sr_decide(const EnvDev &D, int commit, uint8_t *scripted, double *actions, uint8_t *stuck, cudaStream_t s);
 
 // capi.cu accessors
 struct dre_mpc;

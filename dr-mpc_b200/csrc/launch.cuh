@@ -4,6 +4,7 @@
 #include "dre_common.cuh"
 
 void dre_set_cuda_error(cudaError_t e, const char *file, int line);
+void dre_set_error_text(const char *msg);   // what dre_last_cuda_error() reports for a non-CUDA failure behind DRE_ERR_CUDA
 
 #define DRE_CUDA_TRY(call)                                      \
     do {                                                        \

@@ -19,19 +19,34 @@ from .parallel import STAT_NAMES
 
 
 class _DevArray:
-    """Minimal __cuda_array_interface__ carrier so torch can view engine-owned HBM without copying."""
+    """Minimal __cuda_array_interface__ carrier so torch can view engine-owned HBM without copying. torch keeps this object
+    alive for as long as the tensor (or any view of it) lives; `owner` in turn keeps the engine handle, and with it the
+    memory, alive: a view never dangles."""
 
-    def __init__(self, ptr, shape, typestr):
+    def __init__(self, ptr, shape, typestr, owner=None):
+        self.owner = owner
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 3, "strides": None}
+
+
+class _Handle:
+    """Owns the dre_env handle; destroyed when the env object AND every tensor viewing its memory are gone."""
+
+    def __init__(self, L, h):
+        self.L, self.h = L, h
+
+    def __del__(self):
+        if self.h is not None and self.L is not None:
+            self.L.dre_env_destroy(self.h)
+            self.h = None
 
 
 _TYPESTR = {"f8": "<f8", "f4": "<f4", "i4": "<i4", "u4": "<u4", "u1": "|u1", "i8": "<i8"}
 
 
-def _view(ptr, shape, kind, device):
+def _view(ptr, shape, kind, device, owner=None):
     import torch
-    return torch.as_tensor(_DevArray(ptr, shape, _TYPESTR[kind]), device=device)
+    return torch.as_tensor(_DevArray(ptr, shape, _TYPESTR[kind], owner), device=device)
 
 
 class BatchedHAAndPTEnv:
@@ -62,6 +77,7 @@ class BatchedHAAndPTEnv:
         c = cfg.env_config()
         _lib.check(self._L.dre_env_create(ctypes.byref(c), ctypes.byref(h)))
         self._h = h
+        self._owner = _Handle(self._L, h)
         self.paths = continuous_task_paths(cfg.circle_radius, cfg.time_step, cfg.node_separation)
         tab, lens = pack_paths(self.paths)
         _lib.check(self._L.dre_env_set_paths(self._h, tab.ctypes.data_as(ctypes.c_void_p), tab.shape[0], tab.shape[2],
@@ -69,42 +85,53 @@ class BatchedHAAndPTEnv:
         self._bind_views()
         self._host_slab = None
 
-    def __del__(self):
-        if getattr(self, "_h", None) and self._L is not None:
-            self._L.dre_env_destroy(self._h)
-            self._h = None
-
     # ---- zero-copy views ----
+    def _slab_layout(self, o):
+        E, Nh, LB, H = self.E, self.Nh, self.LB, self.LB + 1
+        nact = 2 * min(self.K, self.cfg.actions_in_input)
+        npt = 4 * (self.cfg.lookahead + self.cfg.lookbehind)
+        return [("pt_state", o.pt_state, (E, npt), "f8"), ("actions_used", o.actions_used, (E, 2), "f8"),
+                ("mpc_actions", o.mpc_actions, (E, nact), "f8"),
+                ("robot_node", o.robot_node, (E, 2 * LB), "f8"), ("past_robot_vel", o.past_robot_vel, (E, 2 * LB), "f8"),
+                ("percent_episode", o.percent_episode, (E, 1), "f8"),
+                ("spatial_edges", o.spatial_edges, (E, Nh, 2 * H), "f8"), ("human_valid", o.human_valid, (E, Nh), "f8"),
+                ("detected_humans", o.detected_humans, (E,), "f8"), ("rewards", o.rewards, (E, 3), "f8"),
+                ("info", o.info, (E, 8), "f8"), ("done_bits", o.done_bits, (E,), "i4"),
+                ("mpc_status", o.mpc_status, (E, 8), "i4"), ("done_flags", o.done_flags, (E, 16), "u1")]
+
     def _bind_views(self):
         E, Nh, LB, H = self.E, self.Nh, self.LB, self.LB + 1
         d = self.device
-        o = _lib.StepOut()
-        _lib.check(self._L.dre_env_outputs(self._h, ctypes.byref(o)))
-        self._out = o
-        self.slab_bytes = int(o.slab_bytes)
-        nact = 2 * min(self.K, self.cfg.actions_in_input)
-        npt = 4 * (self.cfg.lookahead + self.cfg.lookbehind)
-        self._layout = [("pt_state", o.pt_state, (E, npt), "f8"), ("actions_used", o.actions_used, (E, 2), "f8"),
-                        ("mpc_actions", o.mpc_actions, (E, nact), "f8"),
-                        ("robot_node", o.robot_node, (E, 2 * LB), "f8"), ("past_robot_vel", o.past_robot_vel, (E, 2 * LB), "f8"),
-                        ("percent_episode", o.percent_episode, (E, 1), "f8"),
-                        ("spatial_edges", o.spatial_edges, (E, Nh, 2 * H), "f8"), ("human_valid", o.human_valid, (E, Nh), "f8"),
-                        ("detected_humans", o.detected_humans, (E,), "f8"), ("rewards", o.rewards, (E, 3), "f8"),
-                        ("info", o.info, (E, 8), "f8"), ("done_bits", o.done_bits, (E,), "i4"),
-                        ("mpc_status", o.mpc_status, (E, 8), "i4"), ("done_flags", o.done_flags, (E, 16), "u1")]
-        self.out = {name: _view(ptr, shape, kind, d) for name, ptr, shape, kind in self._layout}
+        own = self._owner
+        # the output slab is double-buffered (step t writes slab t & 1): one set of views per slab
+        self._outs = []
+        for b in (0, 1):
+            o = _lib.StepOut()
+            _lib.check(self._L.dre_env_outputs_at(self._h, b, ctypes.byref(o)))
+            if b == 0:
+                self._out = o
+                self.slab_bytes = int(o.slab_bytes)
+                self._layout = self._slab_layout(o)
+            self._outs.append({name: _view(ptr, shape, kind, d, own) for name, ptr, shape, kind in self._slab_layout(o)})
         s = _lib.EnvStateView()
         _lib.check(self._L.dre_env_state(self._h, ctypes.byref(s)))
+        v = lambda ptr, shape, kind: _view(ptr, shape, kind, d, own)
         self.state = {
-            "hpos": _view(s.hpos, (E, Nh, 2), "f8", d), "hvel": _view(s.hvel, (E, Nh, 2), "f4", d),
-            "hgoal": _view(s.hgoal, (E, Nh, 2), "f8", d), "hstatic": _view(s.hstatic, (E, Nh), "u1", d),
-            "hhist": _view(s.hhist, (E, Nh, H, 2), "f8", d), "hvalid": _view(s.hvalid, (E, Nh), "i4", d),
-            "rpose": _view(s.rpose, (E, 4), "f8", d), "rprev": _view(s.rprev, (E, 4), "f8", d),
-            "rhist": _view(s.rhist, (E, H, 4), "f8", d), "rpastv": _view(s.rpastv, (E, LB, 2), "f8", d),
-            "rvalid": _view(s.rvalid, (E,), "i4", d), "gtime": _view(s.gtime, (E,), "f8", d),
-            "path_idx": _view(s.path_idx, (E,), "i4", d), "loc_to_start": _view(s.loc_to_start, (E,), "u1", d),
-            "step_count": _view(s.step_count, (E,), "i8", d), "sr_state": _view(s.sr_state, (E, 4), "i4", d),
+            "hpos": v(s.hpos, (E, Nh, 2), "f8"), "hvel": v(s.hvel, (E, Nh, 2), "f4"),
+            "hgoal": v(s.hgoal, (E, Nh, 2), "f8"), "hstatic": v(s.hstatic, (E, Nh), "u1"),
+            "hhist": v(s.hhist, (E, Nh, H, 2), "f8"), "hvalid": v(s.hvalid, (E, Nh), "i4"),
+            "rpose": v(s.rpose, (E, 4), "f8"), "rprev": v(s.rprev, (E, 4), "f8"),
+            "rhist": v(s.rhist, (E, H, 4), "f8"), "rpastv": v(s.rpastv, (E, LB, 2), "f8"),
+            "rvalid": v(s.rvalid, (E,), "i4"), "gtime": v(s.gtime, (E,), "f8"),
+            "path_idx": v(s.path_idx, (E,), "i4"), "loc_to_start": v(s.loc_to_start, (E,), "u1"),
+            "step_count": v(s.step_count, (E,), "i8"), "sr_state": v(s.sr_state, (E, 4), "i4"),
         }
+
+    @property
+    def out(self):
+        """Views of the slab holding the LATEST outputs. Views handed out for the previous step stay intact during the next
+        one (double buffering): `S_prime, ... = env.step(a); buf.insert(S, a, S_prime, ...); S = S_prime` needs no clone."""
+        return self._outs[self._L.dre_env_current_slab(self._h)]
 
     def _stream(self):
         import torch
@@ -118,11 +145,20 @@ class BatchedHAAndPTEnv:
                        'detected_human_num': o["detected_humans"], 'human_valid_history': o["human_valid"]}}
 
     # ---- reference interface ----
-    def reset(self, hpos_init=None, hgoal_init=None):
-        """HAAndPTEnv.reset (env.py:243-280). Optional [E,Nh,2] float64 CUDA tensors replace the device-side spawning."""
-        p = ctypes.c_void_p(hpos_init.contiguous().data_ptr()) if hpos_init is not None else None
-        g = ctypes.c_void_p(hgoal_init.contiguous().data_ptr()) if hgoal_init is not None else None
-        _lib.check(self._L.dre_env_reset(self._h, p, g, self._stream()))
+    def _mask(self, env_mask):
+        import torch
+        if env_mask is None:
+            return None
+        return torch.as_tensor(env_mask).to(device=self.device, dtype=torch.uint8).contiguous()
+
+    def reset(self, hpos_init=None, hgoal_init=None, env_mask=None):
+        """HAAndPTEnv.reset (env.py:243-280). Optional [E,Nh,2] tensors replace the device-side spawning; `env_mask` [E]
+        (bool / uint8) resets only the selected envs, the others keep their episode."""
+        import torch
+        conv = lambda t: torch.as_tensor(t).to(device=self.device, dtype=torch.float64).contiguous().reshape(self.E, self.Nh, 2) if t is not None else None
+        hp, hg, m = conv(hpos_init), conv(hgoal_init), self._mask(env_mask)   # held until the launches are queued
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(self._L.dre_env_reset_masked(self._h, ptr(m), ptr(hp), ptr(hg), self._stream()))
         return self._obs()
 
     def step(self, action, update=True, soft_reset=False, model_info=None):
@@ -151,10 +187,28 @@ class BatchedHAAndPTEnv:
                                                                  'safety_corridor_raise', 'actuation_termination'))}
         return self._obs(), reward_return, done_return, info, eps_done_info
 
-    def observe(self, solve_mpc=False):
+    def observe(self, solve_mpc=False, env_mask=None):
         """Regenerate S from the current state (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148)."""
-        _lib.check(self._L.dre_env_observe(self._h, int(solve_mpc), self._stream()))
+        m = self._mask(env_mask)
+        _lib.check(self._L.dre_env_observe_masked(self._h, ctypes.c_void_p(m.data_ptr()) if m is not None else None, int(solve_mpc), self._stream()))
         return self._obs()
+
+    def switch_path(self, env_mask=None):
+        """The path switch of HAAndPTEnv.soft_reset (env.py:130-141): next path, localize_to_start, MPC.reset(), for the
+        selected envs. Follow with observe(solve_mpc=True, env_mask=...) like PT_env.soft_reset / HA_env.soft_reset."""
+        m = self._mask(env_mask)
+        _lib.check(self._L.dre_env_switch_path(self._h, ctypes.c_void_p(m.data_ptr()) if m is not None else None, self._stream()))
+
+    def soft_reset_decide(self, commit=True):
+        """One decision of HAAndPTEnv.soft_reset's loop (env.py:128-238) per env from the latest done word:
+        -> (scripted [E] bool, actions [E,2], stuck [E] bool). For callers that drive the loop themselves."""
+        import torch
+        sc = torch.empty(self.E, dtype=torch.uint8, device=self.device)
+        a = torch.empty((self.E, 2), dtype=torch.float64, device=self.device)
+        st = torch.empty(self.E, dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.dre_env_soft_reset_decide(self._h, int(commit), ctypes.c_void_p(sc.data_ptr()), ctypes.c_void_p(a.data_ptr()),
+                                                     ctypes.c_void_p(st.data_ptr()), self._stream()))
+        return sc.bool(), a, st.bool()
 
     # ---- host-buffer entry point (end-to-end drop-in for a CPU-side caller) ----
     def step_host(self, actions_np):
@@ -203,6 +257,23 @@ class BatchedHAAndPTEnv:
     def set_host_chunks(self, chunks):
         """Number of env chunks step_host pipelines the crowd half and its D2H copies in (1 = no pipelining)."""
         _lib.check(self._L.dre_env_set_host_chunks(self._h, int(chunks)))
+
+    def stats_comm_init(self, rank, world_size, broadcast):
+        """Create the engine's own NCCL communicator for the episode statistics. `broadcast(bytes_or_None) -> bytes` must
+        deliver rank 0's 128-byte id to every rank (e.g. through torch.distributed.broadcast_object_list)."""
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self._L.dre_stats_comm_id(buf))
+        ident = broadcast(bytes(buf.raw) if rank == 0 else None)
+        _lib.check(self._L.dre_env_stats_comm_init(self._h, ctypes.c_char_p(ident), int(rank), int(world_size)))
+
+    def stats_reduce(self, reset=False):
+        """dre_stats_reduce: the statistics of ALL ranks (one ncclAllReduce(sum) pair over NVLink) -> (int64[16], float64[4])."""
+        import torch
+        c = torch.zeros(16, dtype=torch.int64, device=self.device)
+        s = torch.zeros(4, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.dre_stats_reduce(self._h, None, ctypes.c_void_p(c.data_ptr()), ctypes.c_void_p(s.data_ptr()), int(reset), self._stream()))
+        return c, s
 
     def stats(self, reset=False):
         """Episode statistics accumulated on device -> (int64[16], float64[4]) CUDA tensors (feed to all_reduce)."""

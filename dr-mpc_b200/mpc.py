@@ -45,7 +45,14 @@ class BatchedMPC:
     def reset(self, mask=None):
         """MPC.reset (mpc.py:55-56): next act() starts from the iteration0 initial guess. `mask` selects problems."""
         if mask is None:
-            _lib.check(self._L.dre_mpc_reset(self._h, None, None))
+            stream = None
+            try:
+                import torch
+                if torch.cuda.is_available():   # same stream as act(): a reset queued on another stream would race the solve
+                    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            except ImportError:
+                pass
+            _lib.check(self._L.dre_mpc_reset(self._h, None, stream))
         elif _is_torch(mask):
             import torch
             m = mask.to(torch.uint8).contiguous()

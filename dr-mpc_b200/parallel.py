@@ -72,3 +72,18 @@ def stats_dict(counters, sums):
     out = {n: int(c[i]) for i, n in enumerate(STAT_NAMES)}
     out.update({"sum_R": s[0], "sum_R_PT": s[1], "sum_R_HA": s[2]})
     return out
+
+
+def init_stats_comm(env, group=None):
+    """Give `env` the engine's own NCCL communicator for dre_stats_reduce (include/dre.h): rank 0's id travels through
+    torch.distributed (any backend), the all-reduce itself is issued by libdre over NCCL / NVLink."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("init_stats_comm needs an initialised torch.distributed process group")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def bcast(ident):
+        box = [ident]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return box[0]
+    env.stats_comm_init(rank, world, bcast)

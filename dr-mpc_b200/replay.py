@@ -54,6 +54,10 @@ class BatchedReplayBuffer:
         mask [E] bool: rows to keep (e.g. ~info['soft_reset']). Returns the number of transitions stored."""
         import torch
         fS, fSp = _flatten(S), _flatten(S_prime)
+        for k in fS:   # zero-copy views of the same slab: S was overwritten by the step that produced S_prime
+            if fS[k].data_ptr() == fSp[k].data_ptr() and fS[k].numel() > 0:
+                raise ValueError(f"S and S_prime alias the same memory ({'/'.join(k)}): pass the observation returned by the "
+                                 "previous step (the engine double-buffers its output slab), or clone S")
         n_all = A.shape[0]
         if mask is not None:
             rows = torch.nonzero(mask.to(self.device), as_tuple=False).squeeze(1)

@@ -219,7 +219,13 @@ int dre_env_create(const dre_env_config *cfg, dre_env **out);
 int dre_env_destroy(dre_env *h);
 int dre_env_set_paths(dre_env *h, const double *paths_host, int32_t num_paths, int32_t path_stride, const int32_t *lens_host);
 int dre_env_state(dre_env *h, dre_env_state_view *view);
-int dre_env_outputs(dre_env *h, dre_step_out *out);   /* device pointers of the output slab */
+/* Device pointers of the output slab holding the LATEST outputs. The slab is double-buffered: step() number t writes slab
+ * t & 1, so the observation S a caller got from step t-1 is still intact while it holds S' of step t (the reference's
+ * `replay_buffer.insert(S, a, S', ...); S = S'`, online_continuous_task.py:189, works on zero-copy views without a clone).
+ * dre_env_outputs_at(which = 0 | 1) returns either slab, dre_env_current_slab() which one is the latest. */
+int dre_env_outputs(dre_env *h, dre_step_out *out);
+int dre_env_outputs_at(dre_env *h, int32_t which, dre_step_out *out);
+int dre_env_current_slab(dre_env *h);
 dre_mpc *dre_env_mpc(dre_env *h);                     /* the env's MPC instance (warm-start access) */
 /*
  * reset(): robot at (0,-circle_radius, pi) (env.py:286-303), humans spawned by device-side rejection
@@ -228,6 +234,10 @@ dre_mpc *dre_env_mpc(dre_env *h);                     /* the env's MPC instance 
  * they replace the spawning (parity runs upload the oracle's humans).
  */
 int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init, void *stream);
+/* reset() of the envs whose byte in env_mask (dev uint8[E]) is non-zero; the others keep their episode (SURVEY 8(b):
+ * a reset taking `seeds, env_mask` -- the per-env seed is (config seed, global env id, that env's reset epoch), so
+ * no seed array is needed). NULL mask = all envs = dre_env_reset. */
+int dre_env_reset_masked(dre_env *h, const uint8_t *env_mask, const double *hpos_init, const double *hgoal_init, void *stream);
 /* step(): actions dev double[E][2] = ActionRot(v,w) per env; results in the output slab. */
 int dre_env_step(dre_env *h, const double *actions, void *stream);
 /* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab; pinned
@@ -240,6 +250,16 @@ int dre_env_set_host_chunks(dre_env *h, int32_t chunks);
 int dre_env_invalidate_orca_cache(dre_env *h, void *stream);
 /* regenerate observations only (HAEnv.soft_reset / PTEnv.soft_reset, env.py:141-148) */
 int dre_env_observe(dre_env *h, int32_t solve_mpc, void *stream);
+int dre_env_observe_masked(dre_env *h, const uint8_t *env_mask, int32_t solve_mpc, void *stream);   /* only the masked envs */
+/* The path switch of HAAndPTEnv.soft_reset (env.py:130-141) for the masked envs (NULL = all): path_idx <- next path,
+ * localize_to_start <- True, MPC.reset(). Follow with dre_env_observe_masked(mask, 1) = PT_env.soft_reset + HA_env.soft_reset
+ * (env.py:141-148). For callers that keep auto_path_switch = 0 and drive the reference's soft_reset loop themselves. */
+int dre_env_switch_path(dre_env *h, const uint8_t *env_mask, void *stream);
+/* One decision of HAAndPTEnv.soft_reset's loop (env.py:128-238) per env, from the latest step's done word and the loop
+ * variables in sr_state: scripted dev uint8[E] = 1 where the reference would now issue self.step(action, soft_reset=True)
+ * with actions dev double[E][2]; 0 where soft_reset() returns (or was never entered). stuck dev uint8[E] or NULL = the
+ * "Stuck in soft reset" exit (:235-238). commit = 1 advances the loop variables (call once per step); 0 only peeks. */
+int dre_env_soft_reset_decide(dre_env *h, int32_t commit, uint8_t *scripted, double *actions, uint8_t *stuck, void *stream);
 /*
  * CVMM safety filter: HAAndPTEnv.cvmm_diverse_safety_pipeline(action_execute, num_steps, backup_actions)
  * (HA_and_PT env.py:422-513) for every env. actions dev double[E][2] = the policy's (v, w); backup_actions dev
@@ -256,6 +276,13 @@ int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lookahead_ste
  *  safety_corridor_raise, actuation_termination, mpc_retries, mpc_gave_up, orca_lp3, 4 spare} and
  * double[4] {sum R, sum R_PT, sum R_HA, spare}; `reset` clears them. Feed to NCCL all-reduce. */
 int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream);
+/* The ONE collective of the engine: dre_env_stats followed by an in-place ncclAllReduce(sum) of both buffers
+ * over `nccl_comm` (an ncclComm_t; NULL = the communicator made by dre_env_stats_comm_init) on `stream`. libnccl.so.2 is
+ * resolved at run time from the process (torch's copy), it is not a link dependency. Communicator set-up: rank 0 calls
+ * dre_stats_comm_id(id), the host side broadcasts the 128 bytes, every rank calls dre_env_stats_comm_init. */
+int dre_stats_comm_id(char *id128);
+int dre_env_stats_comm_init(dre_env *h, const char *id128, int32_t rank, int32_t world_size);
+int dre_stats_reduce(dre_env *h, void *nccl_comm, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream);
 
 /* Measurement support (bench.py): when profiling is on, step() brackets each of its kernels with CUDA events on the
  * caller's stream; dre_env_kernel_ms() synchronises and returns the summed milliseconds per kernel since the last

@@ -120,7 +120,7 @@ def test_switch_path_and_masked_observe():
     b_env.reset()
     for k in a_env.state:
         b_env.state[k].copy_(a_env.state[k])
-    b_env.MPC.mpc_set_warm(it0=np.ones(E, dtype=np.uint8))
+    b_env.mpc_set_warm(T0, u0, np.ones(E, dtype=np.uint8))   # same stored warm start: a failing first solve retries from it
     Sb = b_env.observe(solve_mpc=True)
     torch.cuda.synchronize()
     assert torch.equal(Sb['PT']['PT_state'][mask], S2['PT']['PT_state'][mask])

@@ -12,4 +12,6 @@ try:
 except ImportError:   # env module not present in minimal builds
     pass
 
-__all__ = ["EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "BatchedReplayBuffer", "paths", "parallel"]
+from . import compat
+
+__all__ = ["compat", "EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "BatchedReplayBuffer", "paths", "parallel"]

@@ -80,6 +80,7 @@ def load():
     L.dre_version.restype = ctypes.c_int
     L.dre_orca_predict.argtypes = [P(OrcaParams), c_i32, c_i32] + [c_vp] * 8
     L.dre_orca_predict_host.argtypes = [P(OrcaParams), c_i32, c_i32] + [c_vp] * 7
+    L.dre_orca_solve_host.argtypes = [P(OrcaParams), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]
     L.dre_mpc_create.argtypes = [P(MpcParams), c_i32, P(c_vp)]
     L.dre_mpc_destroy.argtypes = [c_vp]
     L.dre_mpc_set_paths.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp]
@@ -113,6 +114,8 @@ def load():
         L.dre_env_observe.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
         L.dre_env_cvmm_filter.argtypes = [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]
+        L.dre_env_cvmm_check.argtypes = [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]
+        L.dre_env_set_seed.argtypes = [c_vp, c_u64]
         L.dre_env_set_profiling.argtypes = [c_vp, c_i32]
         L.dre_env_kernel_ms.argtypes = [c_vp, c_vp, c_vp, c_i32]
     L.dre_measure_peak.argtypes = [c_i32, P(c_d)]

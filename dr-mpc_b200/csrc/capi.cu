@@ -122,6 +122,26 @@ extern "C" int dre_orca_predict_host(const dre_orca_params *p, int32_t E, int32_
     return DRE_OK;
 }
 
+extern "C" int dre_orca_solve_host(const dre_orca_params *p, int32_t N, int32_t n_others, const float *self8, const float *others5,
+                                   float *vnew, dre_orca_stats *stats)
+{
+    if (!p || N <= 0 || n_others < 0 || !self8 || (n_others > 0 && !others5) || !vnew) return DRE_ERR_INVALID;
+    DevBuf dself, doth, dv, dstats, dq;
+    const size_t no = (size_t)N * (n_others > 0 ? n_others : 1) * 5 * sizeof(float);
+    if (dself.alloc((size_t)N * 8 * sizeof(float)) || doth.alloc(no) || dv.alloc((size_t)N * 2 * sizeof(float)) || dq.alloc(sizeof(int))) return DRE_ERR_NOMEM;
+    if (stats && dstats.alloc((size_t)N * sizeof(dre_orca_stats))) return DRE_ERR_NOMEM;
+    cudaStream_t s = 0;
+    DRE_CUDA_TRY(cudaMemcpyAsync(dself.p, self8, (size_t)N * 8 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (n_others > 0) DRE_CUDA_TRY(cudaMemcpyAsync(doth.p, others5, no, cudaMemcpyHostToDevice, s));
+    const int rc = dre_orca_joint_launch(*p, N, n_others, (const float *)dself.p, (const float *)doth.p, (float *)dv.p,
+                                         stats ? (dre_orca_stats *)dstats.p : nullptr, (int *)dq.p, s);
+    if (rc) return rc;
+    DRE_CUDA_TRY(cudaMemcpyAsync(vnew, dv.p, (size_t)N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (stats) DRE_CUDA_TRY(cudaMemcpyAsync(stats, dstats.p, (size_t)N * sizeof(dre_orca_stats), cudaMemcpyDeviceToHost, s));
+    DRE_CUDA_TRY(cudaStreamSynchronize(s));
+    return DRE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MPC
 // ------------------------------------------------------------------------------------------------

@@ -386,6 +386,7 @@ extern "C" int dre_env_switch_path(dre_env *h, const uint8_t *env_mask, void *st
 {
     if (!h) return DRE_ERR_INVALID;
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;
     EnvDev D = h->D;
     D.env_mask = env_mask;
     return dre_env_launch_switch_path(D, (cudaStream_t)stream);
@@ -395,6 +396,7 @@ extern "C" int dre_env_soft_reset_decide(dre_env *h, int32_t commit, uint8_t *sc
 {
     if (!h || !scripted || !actions) return DRE_ERR_INVALID;
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;
     return dre_env_launch_sr_decide(h->D, commit, scripted, actions, stuck, (cudaStream_t)stream);
 }
 
@@ -613,6 +615,22 @@ extern "C" int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lo
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
     return dre_env_launch_cvmm(h->D, actions, lookahead_steps, backup_actions, num_backup, safe_actions, info4, candidate_safe,
                                (cudaStream_t)stream);
+}
+
+extern "C" int dre_env_cvmm_check(dre_env *h, const double *actions, int32_t lookahead_steps, uint8_t *safe, double *dist_to_path, void *stream)
+{
+    if (!h || !actions || !safe) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;
+    return dre_env_launch_cvmm_check(h->D, actions, lookahead_steps, safe, dist_to_path, (cudaStream_t)stream);
+}
+
+extern "C" int dre_env_set_seed(dre_env *h, uint64_t seed)
+{
+    if (!h) return DRE_ERR_INVALID;
+    h->cfg.seed = seed;
+    h->D.seed = seed;
+    return DRE_OK;
 }
 
 extern "C" int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream)

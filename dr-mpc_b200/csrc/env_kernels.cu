@@ -858,6 +858,27 @@ __global__ void __launch_bounds__(128) cvmm_filter_kernel(EnvDev D, const double
     }
 }
 
+// HAAndPTEnv.cvmm_safety_check (HA_and_PT env.py:475-513) for one candidate action per env -> (safe, FDE_to_path)
+__global__ void __launch_bounds__(128) cvmm_check_kernel(EnvDev D, const double *__restrict__ actions, int num_steps,
+                                                         uint8_t *__restrict__ safe_out, double *__restrict__ dist_out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D.E) return;
+    const PathView P = path_view(D.paths, D.path_stride, D.path_idx[e], D.lens);
+    double fde = 1e10;
+    const bool safe = cvmm_safety_check(D, e, P, D.loc_to_start[e] != 0, actions[(size_t)e * 2], actions[(size_t)e * 2 + 1], num_steps, fde);
+    safe_out[e] = safe ? 1 : 0;
+    if (dist_out) dist_out[e] = fde;
+}
+
+int dre_env_launch_cvmm_check(const EnvDev &D, const double *actions, int num_steps, uint8_t *safe_out, double *dist_out, cudaStream_t s)
+{
+    if (num_steps < 1) return DRE_ERR_INVALID;
+    cvmm_check_kernel<<<(D.E + 127) / 128, 128, 0, s>>>(D, actions, num_steps, safe_out, dist_out);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
 int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, const double *backup, int A, double *safe_out,
                         int32_t *info, uint8_t *cand_safe, cudaStream_t s)
 {

@@ -20,6 +20,9 @@ int dre_orca_pick_group(const dre_orca_params &p, int Nh);
 int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
                     const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s);
 
+int dre_orca_joint_launch(const dre_orca_params &p, int N, int n_others, const float *self8, const float *others5, float *vnew,
+                          dre_orca_stats *stats, int *queue, cudaStream_t s);
+
 // ---- mpc_kernels.cu ----
 struct MpcDeviceState {
     int N, K;

@@ -231,6 +231,78 @@ static int launch_orca_thread(const dre_orca_params &p, int E, int Nh, const dou
     return DRE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Joint-state solve: ORCA.predict(JointState) (reference scripts/policy/orca.py:64-117) for a batch of INDEPENDENT joint
+// states -- agent 0 = the ego agent (own radius, own max speed, preferred velocity), agents 1..n = the others in the order
+// of state.human_states, each with its own radius -- i.e. exactly what one private rvo2 simulator sees. A lane-group
+// stages its joint state as a private tile and solves agent 0. This is the literal boundary-B entry point; the crowd
+// pass above is the same solve with the tile shared by an env's humans.
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+orca_joint_kernel(dre_orca_params p, int N, int n_others, const float *__restrict__ self8, const float *__restrict__ others5,
+                  float2 *__restrict__ vnew, dre_orca_stats *__restrict__ stats, int *__restrict__ queue)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nA = n_others + 1, nA4 = (nA + 3) & ~3;
+    const int NG = blockDim.x / G, gi = threadIdx.x / G;
+    const size_t per_group = (size_t)2 * nA * sizeof(OLine) + (size_t)(5 * nA4 + nA4) * sizeof(float);
+    unsigned char *base = smem_raw + per_group * gi;
+    OLine *L = reinterpret_cast<OLine *>(base);
+    float *A = reinterpret_cast<float *>(base + (size_t)2 * nA * sizeof(OLine));   // [5][nA4]
+    float *sd = A + 5 * nA4;
+    cg::thread_block blk = cg::this_thread_block();
+    TileGroup<G> g(cg::tiled_partition<G>(blk));
+    const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
+    const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : n_others;
+    (void)NG;
+    for (;;) {
+        int n = 0;
+        if (g.rank() == 0) n = atomicAdd(queue, 1);
+        n = g.bcast(n, 0);
+        if (n >= N) break;
+        const float *S = self8 + (size_t)n * 8;
+        const float *O = others5 + (size_t)n * n_others * 5;
+        for (int a = g.rank(); a < nA; a += G) {
+            float x, y, vx, vy, r;
+            if (a == 0) { x = S[0]; y = S[1]; vx = S[2]; vy = S[3]; r = S[6]; }
+            else { const float *o = O + (size_t)(a - 1) * 5; x = o[0]; y = o[1]; vx = o[2]; vy = o[3]; r = o[4]; }
+            A[a] = x; A[nA4 + a] = y; A[2 * nA4 + a] = vx; A[3 * nA4 + a] = vy; A[4 * nA4 + a] = r;
+        }
+        g.sync();
+        float ox = 0.f, oy = 0.f;
+        orca_solve_group(g, nA, A, A + nA4, A + 2 * nA4, A + 3 * nA4, A + 4 * nA4, 0, S[4], S[5], S[7], p.neighbor_dist, maxNb,
+                         invTH, invDt, sd, L, ox, oy, stats ? &stats[n] : nullptr, false);
+        if (g.rank() == 0) vnew[n] = make_float2(ox, oy);
+        g.sync();
+    }
+}
+
+template <int G>
+static int launch_orca_joint(const dre_orca_params &p, int N, int n_others, const float *self8, const float *others5, float *vnew,
+                             dre_orca_stats *stats, int *queue, cudaStream_t s)
+{
+    const int nA = n_others + 1, nA4 = (nA + 3) & ~3, threads = 128;
+    const size_t bytes = ((size_t)2 * nA * sizeof(OLine) + (size_t)6 * nA4 * sizeof(float)) * (threads / G);
+    if (bytes > 220 * 1024) return DRE_ERR_INVALID;
+    auto kern = orca_joint_kernel<G>;
+    if (bytes > 48 * 1024) DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int blocks = (N + threads / G - 1) / (threads / G);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    DRE_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int), s));
+    kern<<<blocks, threads, bytes, s>>>(p, N, n_others, self8, others5, (float2 *)vnew, stats, queue);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
+int dre_orca_joint_launch(const dre_orca_params &p, int N, int n_others, const float *self8, const float *others5, float *vnew,
+                          dre_orca_stats *stats, int *queue, cudaStream_t s)
+{
+    if (N <= 0 || n_others < 0 || n_others > DRE_MAX_HUMANS) return DRE_ERR_INVALID;
+    if (n_others + 1 <= 8) return launch_orca_joint<4>(p, N, n_others, self8, others5, vnew, stats, queue, s);
+    return launch_orca_joint<8>(p, N, n_others, self8, others5, vnew, stats, queue, s);
+}
+
 int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
     const int gl = p.group_lanes & 0xff;

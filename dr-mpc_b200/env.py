@@ -250,6 +250,21 @@ class BatchedHAAndPTEnv:
             d['candidate_safe'] = cand
         return out, d
 
+    def cvmm_safety_check(self, action_execute, num_steps=8):
+        """HAAndPTEnv.cvmm_safety_check (env.py:475-513) for every env: [E,2] -> (safe [E] bool, FDE_to_path [E])."""
+        import torch
+        a = action_execute.to(device=self.device, dtype=torch.float64).contiguous()
+        safe = torch.empty(self.E, dtype=torch.uint8, device=self.device)
+        dist = torch.empty(self.E, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.dre_env_cvmm_check(self._h, ctypes.c_void_p(a.data_ptr()), int(num_steps), ctypes.c_void_p(safe.data_ptr()),
+                                              ctypes.c_void_p(dist.data_ptr()), self._stream()))
+        return safe.bool(), dist
+
+    def set_seed(self, seed):
+        """Philox key of the spawning / goal resampling from the next reset() on."""
+        self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        _lib.check(self._L.dre_env_set_seed(self._h, ctypes.c_uint64(self.cfg.seed)))
+
     def invalidate_orca_cache(self):
         """orca_dedup: call after writing human / robot state through `self.state` (the cached look-ahead is then stale)."""
         _lib.check(self._L.dre_env_invalidate_orca_cache(self._h, self._stream()))

@@ -70,6 +70,20 @@ int dre_orca_predict_host(const dre_orca_params *p, int32_t num_envs, int32_t nu
                           const double *hpos, const float *hvel, const double *goal, const double *rpos,
                           const uint8_t *is_static, float *vnew, dre_orca_stats *stats);
 
+/*
+ * The literal boundary-B call: ORCA(config).predict(JointState) -> ActionXY (scripts/policy/orca.py:64-117) for N
+ * independent joint states of n_others neighbours each, on HOST buffers (synchronous). What crosses is what the
+ * reference hands to its private rvo2 simulator, already cast to float like the Cython boundary does:
+ *   self8   host float[N][8]           px, py, vx, vy, pref_vx, pref_vy (orca.py:97-100), radius + 0.01 + safety_space
+ *                                      (orca.py:85), max speed = v_pref (orca.py:86)
+ *   others5 host float[N][n_others][5] px, py, vx, vy, radius + 0.01 + safety_space (orca.py:88), in human_states order
+ *   vnew    host float[N][2]  OUT      sim.getAgentVelocity(0) after doStep      stats host dre_orca_stats[N] or NULL
+ * p->neighbor_dist / time_horizon / time_step / max_neighbors (<= 0: n_others, orca.py:77) apply; radius, max_speed_self
+ * and robot_visible of *p are not used (they come per agent).
+ */
+int dre_orca_solve_host(const dre_orca_params *p, int32_t num_states, int32_t n_others, const float *self8,
+                        const float *others5, float *vnew, dre_orca_stats *stats);
+
 /* ---------------------------------------------------------------------------------------------
  * Path-tracking MPC. Replaces MPC(config_master, K, dt, continuous_task, max_v, max_w) /
  * .reset() / .act({'path','interp_index','pose'}) (environment/path_tracking/utils/mpc.py:21,55,58)
@@ -271,6 +285,12 @@ int dre_env_soft_reset_decide(dre_env *h, int32_t commit, uint8_t *scripted, dou
  */
 int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lookahead_steps, const double *backup_actions,
                         int32_t num_backup, double *safe_actions, int32_t *info4, uint8_t *candidate_safe, void *stream);
+/* HAAndPTEnv.cvmm_safety_check(action, num_steps) (env.py:475-513) for one action per env: actions dev double[E][2] ->
+ * safe dev uint8[E], dist_to_path dev double[E] or NULL (FDE_to_path: 1e10 when unsafe). */
+int dre_env_cvmm_check(dre_env *h, const double *actions, int32_t lookahead_steps, uint8_t *safe, double *dist_to_path, void *stream);
+/* Philox key of the device-side spawning / goal resampling from the next reset() on (the reference re-seeds np.random
+ * with the case number at every hard reset, env.py:246-252). */
+int dre_env_set_seed(dre_env *h, uint64_t seed);
 /* episode statistics accumulated on device since the last call: int64[16]
  * {steps, success, collision, safety_human_raise, timeout, deviation_end_of_path, corridor_hit,
  *  safety_corridor_raise, actuation_termination, mpc_retries, mpc_gave_up, orca_lp3, 4 spare} and

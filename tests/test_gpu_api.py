@@ -74,8 +74,9 @@ def test_masked_reset_leaves_the_other_envs_alone():
     assert (st["rpose"][mask][:, 0] == 0).all() and (st["rpose"][mask][:, 1] == -4).all()
     assert (st["step_count"][keep] == 12).all()
     assert (st["hvalid"][mask] == 7).all() and (st["rvalid"][mask] == 7).all()        # the lookback warm-start steps ran
-    # a masked reset from given spawn positions equals a full reset from them (spawning then needs no random draw)
-    hp = before["hpos"].clone(); hg = -hp
+    # a masked reset from given spawn positions equals a full reset from them (spawning then needs no random draw; goals far
+    # away so that none is reached -- and resampled from the epoch-keyed stream -- during the warm-start steps)
+    hp = before["hpos"].clone(); hg = hp + torch.tensor([7.0, 3.0], dtype=torch.float64, device=hp.device)
     ref = _env(E, Nh)
     ref.reset(hp, hg)
     env.reset(hp, hg, env_mask=mask)

@@ -108,6 +108,7 @@ def load():
         L.dre_env_mpc.argtypes = [c_vp]
         L.dre_env_reset.argtypes = [c_vp, c_vp, c_vp, c_vp]
         L.dre_env_step.argtypes = [c_vp, c_vp, c_vp]
+        L.dre_env_crowd_step.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_step_host.argtypes = [c_vp, c_vp, c_vp]
         L.dre_env_set_host_chunks.argtypes = [c_vp, c_i32]
         L.dre_env_invalidate_orca_cache.argtypes = [c_vp, c_vp]

@@ -382,6 +382,14 @@ extern "C" int dre_env_reset(dre_env *h, const double *hpos_init, const double *
     return dre_env_reset_masked(h, nullptr, hpos_init, hgoal_init, stream);
 }
 
+extern "C" int dre_env_crowd_step(dre_env *h, int32_t write_obs, void *stream)
+{
+    if (!h) return DRE_ERR_INVALID;
+    if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;
+    return dre_env_launch_ha(h->D, 1, write_obs ? 1 : 0, (cudaStream_t)stream);
+}
+
 extern "C" int dre_env_switch_path(dre_env *h, const uint8_t *env_mask, void *stream)
 {
     if (!h) return DRE_ERR_INVALID;

@@ -40,7 +40,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     l.off_pos = seg((size_t)EPB * Nh * sizeof(double2));          // new human positions (fp64)
     l.off_pen = seg((size_t)EPB * Nh * 3 * sizeof(double));       // pen_v, pen_th, closest_dist per human
     l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
-    l.off_dist = seg((size_t)NG * ((nA + 3) & ~3) * sizeof(float));
+    l.off_dist = seg((size_t)NG * 2 * ((nA + 3) & ~3) * sizeof(float));   // compacted squared distances + their agent indices
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
     l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
     l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
@@ -55,7 +55,8 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
-    float *sd = dist + (size_t)gi * ((nA + 3) & ~3);
+    const int nA4 = (nA + 3) & ~3;
+    float *sd = dist + (size_t)gi * 2 * nA4;
     const float invTH = 1.0f / D.orca.time_horizon, invDt = 1.0f / D.orca.time_step;
     const int maxNb = D.orca.max_neighbors > 0 ? D.orca.max_neighbors : nA - 1;
     // LP3 (infeasible) solves cost an order of magnitude more than LP2 ones, so the groups of a CTA pull agents from a
@@ -83,7 +84,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
             const float *A = agents + (size_t)el * 5 * nA;
             dre_orca_stats st;
             orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
-                             D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy,
+                             D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              lp3_count ? &st : nullptr);
             if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1ull);
         }

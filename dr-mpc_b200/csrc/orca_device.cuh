@@ -234,52 +234,68 @@ DRE_HD OLine orca_make_line(float px, float py, float vx, float vy, float rs, fl
     return line;
 }
 
-// Neighbour ranking + ORCA lines of agent `self` into L[0..m) (sorted like RVO2's neighbour list). Returns m.
+// Neighbour search + ORCA lines of agent `self` into L[0..m) (sorted like RVO2's neighbour list). Returns m.
+//
+// RVO2 finds the neighbours with a kd-tree range query (Agent::computeNeighbors); an env holds at most 65 agents, all of
+// them in one shared-memory tile, so the query here is a CUT-OFF + COMPACTION instead of a tree or a uniform grid: every
+// lane tests its candidates against neighborDist^2 (strict <, like RVO2), a ballot + prefix count packs the in-range
+// ones -- squared distance into sdist[0..cnt), agent index into sidx[0..cnt) -- and only those are ranked. With the
+// reference's neighbor_dist = 10 everything is in range and the compaction costs a ballot per 8 candidates; with a short
+// range (BASELINE config 4's neighbor_dist = 3: 6 of 50 in range) the ranking works on the 6, not on the 51.
 template <class Grp, class DistT, class LinesT>
 DRE_HD int orca_build_lines(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                             const float *ar, int self, float neighborDist, int maxNeighbors, float invTH, float invDt,
-                            DistT sdist, LinesT L, unsigned &mask)
+                            DistT sdist, DistT sidx, LinesT L, unsigned &mask)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
     const float px = ax[self], py = ay[self], vx = avx[self], vy = avy[self], rs = ar[self];
     const float rangeSq = neighborDist * neighborDist;
-    const int nA4 = (nA + 3) & ~3;
     int cnt = 0;
-    for (int j = lane; j < nA4; j += G) {
-        float d = INFINITY;
+    for (int base = 0; base < nA; base += G) {
+        const int j = base + lane;
+        float d = 0.0f;
+        bool in = false;
         if (j < nA) {
             const float dx = px - ax[j], dy = py - ay[j];
-            const float dd = dx * dx + dy * dy;
-            if (j != self && dd < rangeSq) { d = dd; ++cnt; }
+            d = dx * dx + dy * dy;
+            in = j != self && d < rangeSq;
         }
-        sdist[j] = d;
-    }
-    cnt = g.sum_int(cnt);   // also orders the sdist stores before the ranking reads
-    g.sync();
-    // rank of neighbour j = #{k : (d_k, k) < (d_j, j)} (RVO2 insertNeighbor: ascending distSq, ties by visit order).
-    // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
-    for (int j = lane; j < nA; j += G) {
-        const bool in = sdist[j] < INFINITY;
+        const unsigned b = g.ballot(in);
         if (in) {
-            // (d_k, k) < (d_j, j)  <=>  k < j ? bits_k <= bits_j : bits_k < bits_j. One compare per key: chunks of four
-            // keys below j's own chunk count `<= bits_j` (= `< bits_j + 1`), the others `< bits_j`; the (rare) exact ties
-            // with a smaller index inside j's own chunk are added afterwards from that one chunk.
-            const unsigned uj = dre_f2u(sdist[j]);
-            const int jc = j & ~3;
-            int r = 0;
+            const int pos = cnt + dre_popc(b & ((1u << lane) - 1u));
+            sdist[pos] = d;
+            sidx[pos] = (float)j;            // small integers are exact in fp32
+        }
+        cnt += dre_popc(b);
+    }
+    const int cnt4 = (cnt + 3) & ~3;
+    for (int k = cnt + lane; k < cnt4; k += G) sdist[k] = INFINITY;   // pad the last chunk of four keys
+    g.sync();
+    // rank of neighbour c = #{k : (d_k, k) < (d_c, c)} (RVO2 insertNeighbor: ascending distSq, ties by visit order; the
+    // compaction keeps the agents in index order, so the compact position orders ties like the agent index does).
+    // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
+    for (int c = lane; c < cnt; c += G) {
+        // (d_k, k) < (d_c, c)  <=>  k < c ? bits_k <= bits_c : bits_k < bits_c. One compare per key: chunks of four keys
+        // below c's own chunk count `<= bits_c` (= `< bits_c + 1`), the others `< bits_c`; the (rare) exact ties with a
+        // smaller position inside c's own chunk are added afterwards from that one chunk.
+        const unsigned uc = dre_f2u(sdist[c]);
+        const int cc = c & ~3;
+        int r = 0;
 #pragma unroll 2
-            for (int k = 0; k < nA4; k += 4) {
-                const float4 q = dre_ld4(sdist, k);
-                const unsigned thr = uj + (k < jc ? 1u : 0u);
-                r += (int)(dre_f2u(q.x) < thr) + (int)(dre_f2u(q.y) < thr) + (int)(dre_f2u(q.z) < thr) + (int)(dre_f2u(q.w) < thr);
-            }
-            {
-                const float4 q = dre_ld4(sdist, jc);
-                const int jr = j - jc;   // 0..3: position of j in its chunk
-                r += (int)(jr > 0 && dre_f2u(q.x) == uj) + (int)(jr > 1 && dre_f2u(q.y) == uj) + (int)(jr > 2 && dre_f2u(q.z) == uj);
-            }
-            if (r < maxNeighbors) L[r] = orca_make_line(px, py, vx, vy, rs, ax[j], ay[j], avx[j], avy[j], ar[j], invTH, invDt, mask);
+        for (int k = 0; k < cnt4; k += 4) {
+            const float4 q = dre_ld4(sdist, k);
+            const unsigned thr = uc + (k < cc ? 1u : 0u);
+            r += (int)(dre_f2u(q.x) < thr) + (int)(dre_f2u(q.y) < thr) + (int)(dre_f2u(q.z) < thr) + (int)(dre_f2u(q.w) < thr);
+        }
+        {
+            const float4 q = dre_ld4(sdist, cc);
+            const int cr = c - cc;   // 0..3: position of c in its chunk
+            r += (int)(cr > 0 && dre_f2u(q.x) == uc) + (int)(cr > 1 && dre_f2u(q.y) == uc) + (int)(cr > 2 && dre_f2u(q.z) == uc);
+        }
+        if (r < maxNeighbors) {
+            const int j = (int)sidx[c];
+            L[r] = orca_make_line(px, py, vx, vy, rs, ax[j], ay[j], avx[j], avy[j], ar[j], invTH, invDt, mask);
         }
     }
     const int m = cnt < maxNeighbors ? cnt : maxNeighbors;
@@ -326,7 +342,8 @@ DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine 
 
 // Full solve for agent `self` of a tile of nA agents held in (shared) arrays ax..ar. The other agents are the
 // tile's agents in index order skipping `self` (crowd_sim.py:274-280: other humans in list order, robot last).
-//   sdist : scratch float[round_up(nA,4)], 16 B aligned, private to the group
+//   sdist : scratch float[round_up(nA,4)], 16 B aligned, private to the group (in-range squared distances, compacted)
+//   sidx  : scratch float[round_up(nA,4)] private to the group (their agent indices)
 //   L     : scratch OLine[2*nA] private to the group (ORCA lines, then LP3's projected lines)
 //
 // RVO2's linearProgram2 / linearProgram3 are driven from ONE loop with a single LP2 body: stage 0 runs LP2 on the ORCA
@@ -336,13 +353,13 @@ DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine 
 template <class Grp, class DistT, class LinesT>
 DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
-                             int maxNeighbors, float invTH, float invDt, DistT sdist, LinesT L, float &outx, float &outy,
+                             int maxNeighbors, float invTH, float invDt, DistT sdist, DistT sidx, LinesT L, float &outx, float &outy,
                              dre_orca_stats *st, bool debug_skip_lp3 = false)
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
     unsigned mask = 0;
-    const int m = orca_build_lines(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, L, mask);
+    const int m = orca_build_lines(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, sidx, L, mask);
 
     LinesT P = L + nA;                       // LP3's projected lines
     float rx = 0.0f, ry = 0.0f;

@@ -22,7 +22,7 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
     l.off_lines = 0;
     l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
     l.off_dist = (l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float) + 15) / 16 * 16;
-    l.bytes = (l.off_dist + (size_t)l.NG * ((l.nA + 3) & ~3) * sizeof(float) + 15) / 16 * 16 + 16;   // + work counter
+    l.bytes = (l.off_dist + (size_t)l.NG * 2 * ((l.nA + 3) & ~3) * sizeof(float) + 15) / 16 * 16 + 16;   // distances + indices, + work counter
     return l;
 }
 
@@ -67,7 +67,8 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     TileGroup<G> g(cg::tiled_partition<G>(blk));
     const int gi = threadIdx.x / G;
     OLine *L = lines + (size_t)gi * 2 * nA;
-    float *sd = dist + (size_t)gi * ((nA + 3) & ~3);
+    const int nA4 = (nA + 3) & ~3;
+    float *sd = dist + (size_t)gi * 2 * nA4;
     const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
     const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
 
@@ -96,7 +97,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
             if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
             const float *A = agents + (size_t)el * 5 * nA;
             orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
-                             p.max_speed_self, p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy,
+                             p.max_speed_self, p.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              stats ? &stats[gidx] : nullptr, (p.group_lanes & 0x100) != 0);
         }
         if (g.rank() == 0) vnew[gidx] = make_float2(ox, oy);
@@ -149,8 +150,8 @@ orca_thread_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__r
     const int nA = Nh + (p.robot_visible ? 1 : 0), nA4 = (nA + 3) & ~3;
     OLine *lines = reinterpret_cast<OLine *>(smem_raw);                                   // [nA or 2 nA][threads]
     const size_t nl = (size_t)(P_GLOBAL ? nA : 2 * nA) * DRE_TP_THREADS;
-    float4 *dist = reinterpret_cast<float4 *>(smem_raw + nl * sizeof(OLine));              // [nA4/4][threads]
-    float *agents = reinterpret_cast<float *>(smem_raw + nl * sizeof(OLine) + (size_t)(nA4 / 4) * DRE_TP_THREADS * sizeof(float4));
+    float4 *dist = reinterpret_cast<float4 *>(smem_raw + nl * sizeof(OLine));              // [2][nA4/4][threads]: distances, indices
+    float *agents = reinterpret_cast<float *>(smem_raw + nl * sizeof(OLine) + (size_t)2 * (nA4 / 4) * DRE_TP_THREADS * sizeof(float4));
     const int env0 = blockIdx.x * EPB;
     for (int t = threadIdx.x; t < EPB * nA; t += blockDim.x) {
         const int el = t / nA, a = t - el * nA, e = env0 + el;
@@ -187,17 +188,18 @@ orca_thread_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__r
         const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
         const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
         StridedDist sd = {dist + threadIdx.x, DRE_TP_THREADS};
+        StridedDist si = {dist + (size_t)(nA4 / 4) * DRE_TP_THREADS + threadIdx.x, DRE_TP_THREADS};
         SerialGroup g;
         if (P_GLOBAL) {
             // L in shared memory, P in the global scratch: one accessor type -> generic addressing for both
             TwoSpaceLines L = {lines + threadIdx.x, DRE_TP_THREADS,
                                pscratch + (size_t)blockIdx.x * nA * DRE_TP_THREADS + threadIdx.x, DRE_TP_THREADS, nA, 0};
             orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy, p.max_speed_self,
-                             p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
+                             p.neighbor_dist, maxNb, invTH, invDt, sd, si, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
         } else {
             StridedLines L = {lines + threadIdx.x, DRE_TP_THREADS};
             orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy, p.max_speed_self,
-                             p.neighbor_dist, maxNb, invTH, invDt, sd, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
+                             p.neighbor_dist, maxNb, invTH, invDt, sd, si, L, ox, oy, stats ? &stats[gidx] : nullptr, false);
         }
     }
     vnew[gidx] = make_float2(ox, oy);
@@ -209,7 +211,7 @@ static int launch_orca_thread(const dre_orca_params &p, int E, int Nh, const dou
     const int nA = Nh + (p.robot_visible ? 1 : 0), nA4 = (nA + 3) & ~3;
     int EPB = DRE_TP_THREADS / Nh;
     if (EPB < 1) return DRE_ERR_INVALID;
-    const size_t fixed = (size_t)(nA4 / 4) * DRE_TP_THREADS * sizeof(float4) + (size_t)EPB * 5 * nA * sizeof(float);
+    const size_t fixed = (size_t)2 * (nA4 / 4) * DRE_TP_THREADS * sizeof(float4) + (size_t)EPB * 5 * nA * sizeof(float);
     // large crowds: both line arrays do not fit in shared memory -> projected lines in the global scratch
     const bool pglobal = (p.group_lanes & 0x400) != 0 || (size_t)2 * nA * DRE_TP_THREADS * sizeof(OLine) + fixed > 200 * 1024;
     const size_t bytes = (size_t)(pglobal ? nA : 2 * nA) * DRE_TP_THREADS * sizeof(OLine) + fixed;
@@ -246,7 +248,7 @@ orca_joint_kernel(dre_orca_params p, int N, int n_others, const float *__restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nA = n_others + 1, nA4 = (nA + 3) & ~3;
     const int NG = blockDim.x / G, gi = threadIdx.x / G;
-    const size_t per_group = (size_t)2 * nA * sizeof(OLine) + (size_t)(5 * nA4 + nA4) * sizeof(float);
+    const size_t per_group = (size_t)2 * nA * sizeof(OLine) + (size_t)(5 * nA4 + 2 * nA4) * sizeof(float);
     unsigned char *base = smem_raw + per_group * gi;
     OLine *L = reinterpret_cast<OLine *>(base);
     float *A = reinterpret_cast<float *>(base + (size_t)2 * nA * sizeof(OLine));   // [5][nA4]
@@ -272,7 +274,7 @@ orca_joint_kernel(dre_orca_params p, int N, int n_others, const float *__restric
         g.sync();
         float ox = 0.f, oy = 0.f;
         orca_solve_group(g, nA, A, A + nA4, A + 2 * nA4, A + 3 * nA4, A + 4 * nA4, 0, S[4], S[5], S[7], p.neighbor_dist, maxNb,
-                         invTH, invDt, sd, L, ox, oy, stats ? &stats[n] : nullptr, false);
+                         invTH, invDt, sd, sd + nA4, L, ox, oy, stats ? &stats[n] : nullptr, false);
         if (g.rank() == 0) vnew[n] = make_float2(ox, oy);
         g.sync();
     }
@@ -283,7 +285,7 @@ static int launch_orca_joint(const dre_orca_params &p, int N, int n_others, cons
                              dre_orca_stats *stats, int *queue, cudaStream_t s)
 {
     const int nA = n_others + 1, nA4 = (nA + 3) & ~3, threads = 128;
-    const size_t bytes = ((size_t)2 * nA * sizeof(OLine) + (size_t)6 * nA4 * sizeof(float)) * (threads / G);
+    const size_t bytes = ((size_t)2 * nA * sizeof(OLine) + (size_t)7 * nA4 * sizeof(float)) * (threads / G);
     if (bytes > 220 * 1024) return DRE_ERR_INVALID;
     auto kern = orca_joint_kernel<G>;
     if (bytes > 48 * 1024) DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

@@ -168,6 +168,11 @@ class BatchedHAAndPTEnv:
         _lib.check(self._L.dre_env_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()))
         return self._package()
 
+    def crowd_step(self, write_obs=False):
+        """ORCA-only step: one ORCA pass + the humans' integration, histories and goal resampling, robot frozen
+        (one step of HAEnv.warm_start, human_avoidance_env.py:79-125)."""
+        _lib.check(self._L.dre_env_crowd_step(self._h, int(write_obs), self._stream()))
+
     def _package(self):
         import torch
         o = self.out

@@ -254,6 +254,10 @@ int dre_env_reset(dre_env *h, const double *hpos_init, const double *hgoal_init,
 int dre_env_reset_masked(dre_env *h, const uint8_t *env_mask, const double *hpos_init, const double *hgoal_init, void *stream);
 /* step(): actions dev double[E][2] = ActionRot(v,w) per env; results in the output slab. */
 int dre_env_step(dre_env *h, const double *actions, void *stream);
+/* "ORCA-only" step (BASELINE.json configs[3]): CrowdSim.get_human_actions + the humans' Euler step, histories and goal
+ * resampling with the robot frozen = one step of HAEnv.warm_start (human_avoidance_env.py:79-125). write_obs = 1 also
+ * regenerates the HA observation. */
+int dre_env_crowd_step(dre_env *h, int32_t write_obs, void *stream);
 /* step() on HOST buffers: actions host double[E][2] -> slab_host (slab_bytes, same layout as the device slab; pinned
  * memory lets the copies overlap the kernels). Synchronous: returns when the whole slab has arrived. Runs on the handle's own
  * streams, ordered after earlier reset() / step() / observe() calls whatever stream those were given. */

@@ -526,6 +526,28 @@ void env_ref_step(const env_cfg *c, const env_arrays *A, const double *actions, 
     }
 }
 
+/* "ORCA-only" step (BASELINE config 4): one ORCA pass + integration + histories + goal resampling, robot frozen =
+ * one warm-start step of HAEnv.warm_start (human_avoidance_env.py:79-125) */
+void env_ref_crowd_step(const env_cfg *c, const env_arrays *A, int nthreads, int64_t *lp3_count)
+{
+    int64_t total = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel reduction(+ : total)
+#endif
+    {
+        float *scratch = (float *)malloc(sizeof(float) * (size_t)(4 * c->Nh + 5 * (c->Nh + 1)));
+        int lp3 = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int e = 0; e < c->E; ++e) ha_step(c, A, e, NULL, 1, 0, scratch, &lp3);
+        total += lp3;
+        free(scratch);
+    }
+    if (lp3_count) *lp3_count = total;
+}
+
 void env_ref_observe(const env_cfg *c, const env_arrays *A, int nthreads)
 {
 #ifdef _OPENMP

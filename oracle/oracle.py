@@ -219,6 +219,14 @@ class EnvRef:
         lib().env_ref_reset(ctypes.byref(self.cfg), ctypes.byref(self.A), _p(p), _p(g), nthreads)
         return self.a
 
+    def crowd_step(self, nthreads=0):
+        """ORCA-only step: one pass + integration, robot frozen (BASELINE config 4). Returns (arrays, #LP3 solves)."""
+        L = lib()
+        L.env_ref_crowd_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        n = ctypes.c_int64(0)
+        L.env_ref_crowd_step(ctypes.byref(self.cfg), ctypes.byref(self.A), nthreads, ctypes.byref(n))
+        return self.a, int(n.value)
+
     def step(self, actions, nthreads=0):
         act = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.E, 2)
         lib().env_ref_step(ctypes.byref(self.cfg), ctypes.byref(self.A), _p(act), nthreads)

@@ -31,7 +31,7 @@
 struct HaLayout {
     size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, bytes;
 };
-static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
+static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
 {
     HaLayout l;
     size_t o = 0;
@@ -40,7 +40,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     l.off_pos = seg((size_t)EPB * Nh * sizeof(double2));          // new human positions (fp64)
     l.off_pen = seg((size_t)EPB * Nh * 3 * sizeof(double));       // pen_v, pen_th, closest_dist per human
     l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
-    l.off_dist = seg((size_t)NG * 2 * ((nA + 3) & ~3) * sizeof(float));   // compacted squared distances + their agent indices
+    l.off_dist = seg((size_t)NG * (cutoff ? 2 : 1) * ((nA + 3) & ~3) * sizeof(float));   // squared distances (+ the agent indices of the compacted ones)
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
     l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
     l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
@@ -48,7 +48,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB)
     return l;
 }
 
-template <int G, bool REUSE>
+template <int G, bool REUSE, bool CUTOFF>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
                                bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse, const int *flags)
@@ -56,7 +56,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
     const int nA4 = (nA + 3) & ~3;
-    float *sd = dist + (size_t)gi * 2 * nA4;
+    float *sd = dist + (size_t)gi * (CUTOFF ? 2 : 1) * nA4;
     const float invTH = 1.0f / D.orca.time_horizon, invDt = 1.0f / D.orca.time_step;
     const int maxNb = D.orca.max_neighbors > 0 ? D.orca.max_neighbors : nA - 1;
     // LP3 (infeasible) solves cost an order of magnitude more than LP2 ones, so the groups of a CTA pull agents from a
@@ -83,7 +83,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
             if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
             const float *A = agents + (size_t)el * 5 * nA;
             dre_orca_stats st;
-            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+            orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
                              D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              lp3_count ? &st : nullptr);
             if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1ull);
@@ -113,7 +113,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
 // mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
 // DEDUP: the orca_dedup variant (reuses the previous step's look-ahead pass); a separate instantiation so that the default
 // two-pass kernel carries none of its code
-template <int G, bool DEDUP>
+template <int G, bool DEDUP, bool CUTOFF>
 __global__ void __launch_bounds__(512)
 ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_obs, const __grid_constant__ HaLayout lay)
 {
@@ -175,7 +175,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
         // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
         // instruction cache together)
-        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
+        orca_pass_tile<G, DEDUP, CUTOFF>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
                                  D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0, flags);
         __syncthreads();
 
@@ -333,7 +333,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
 #ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
-        orca_pass_tile<G, DEDUP>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags);
+        orca_pass_tile<G, DEDUP, CUTOFF>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags);
 #endif
         __syncthreads();
         if (DEDUP) {   // keep the look-ahead velocities: they are the next step's movement pass
@@ -924,7 +924,7 @@ int dre_env_ha_envs_per_cta(const EnvDev &D)
     return EPB < 1 ? 1 : EPB;
 }
 
-template <int G, bool DEDUP>
+template <int G, bool DEDUP, bool CUTOFF>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
@@ -933,13 +933,13 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
     // smaller CTAs share an SM)
     const int threads = dre_ha_threads();
     const int EPB = dre_env_ha_envs_per_cta(D);
-    HaLayout lay = ha_layout(Nh, nA, threads / G, EPB);
+    HaLayout lay = ha_layout(Nh, nA, threads / G, EPB, CUTOFF);
     {   // DRE_HA_SMEM_PAD_KB: extra dynamic shared memory per CTA (measurement aid: caps the CTAs per SM)
         static int pad = -1;
         if (pad < 0) { const char *e = getenv("DRE_HA_SMEM_PAD_KB"); pad = e ? atoi(e) : 0; }
         lay.bytes += (size_t)pad * 1024;
     }
-    auto kern = ha_step_kernel<G, DEDUP>;
+    auto kern = ha_step_kernel<G, DEDUP, CUTOFF>;
     if (lay.bytes > 48 * 1024) {
         if (lay.bytes > 220 * 1024) return DRE_ERR_INVALID;
         DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
@@ -952,13 +952,14 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int G = dre_env_pick_group(D);
-#define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true>(D, mode, write_obs, s) : launch_ha<g, false>(D, mode, write_obs, s)
+    const bool cut = dre_orca_use_cutoff(D.orca);   // short neighbour range: cut-off + compaction before the ranking (orca_device.cuh)
+#define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true, false>(D, mode, write_obs, s) : (cut ? launch_ha<g, false, true>(D, mode, write_obs, s) : launch_ha<g, false, false>(D, mode, write_obs, s))
     switch (G) {
     DRE_HA_CASE(2);
     DRE_HA_CASE(4);
     DRE_HA_CASE(8);
     DRE_HA_CASE(16);
-    default: return D.orca_dedup ? launch_ha<32, true>(D, mode, write_obs, s) : launch_ha<32, false>(D, mode, write_obs, s);
+    default: return D.orca_dedup ? launch_ha<32, true, false>(D, mode, write_obs, s) : (cut ? launch_ha<32, false, true>(D, mode, write_obs, s) : launch_ha<32, false, false>(D, mode, write_obs, s));
     }
 #undef DRE_HA_CASE
 }

@@ -17,6 +17,7 @@ void dre_set_error_text(const char *msg);   // what dre_last_cuda_error() report
 
 // ---- orca_kernels.cu ----
 int dre_orca_pick_group(const dre_orca_params &p, int Nh);
+bool dre_orca_use_cutoff(const dre_orca_params &p);
 int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
                     const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s);
 

@@ -234,16 +234,74 @@ DRE_HD OLine orca_make_line(float px, float py, float vx, float vy, float rs, fl
     return line;
 }
 
+// Neighbour ranking + ORCA lines of agent `self` into L[0..m) (sorted like RVO2's neighbour list). Returns m.
+// Variant for ranges that cover (nearly) the whole crowd -- the reference's neighbor_dist = 10: every candidate is ranked
+// against all keys, out-of-range ones carry +inf. See orca_build_lines_cutoff for short ranges.
+template <class Grp, class DistT, class LinesT>
+DRE_HD int orca_build_lines_all(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+                            const float *ar, int self, float neighborDist, int maxNeighbors, float invTH, float invDt,
+                            DistT sdist, LinesT L, unsigned &mask)
+{
+    constexpr int G = Grp::size;
+    const int lane = g.rank();
+    const float px = ax[self], py = ay[self], vx = avx[self], vy = avy[self], rs = ar[self];
+    const float rangeSq = neighborDist * neighborDist;
+    const int nA4 = (nA + 3) & ~3;
+    int cnt = 0;
+    for (int j = lane; j < nA4; j += G) {
+        float d = INFINITY;
+        if (j < nA) {
+            const float dx = px - ax[j], dy = py - ay[j];
+            const float dd = dx * dx + dy * dy;
+            if (j != self && dd < rangeSq) { d = dd; ++cnt; }
+        }
+        sdist[j] = d;
+    }
+    cnt = g.sum_int(cnt);   // also orders the sdist stores before the ranking reads
+    g.sync();
+    // rank of neighbour j = #{k : (d_k, k) < (d_j, j)} (RVO2 insertNeighbor: ascending distSq, ties by visit order).
+    // Squared distances are >= +0, so their bit patterns order like the values: integer compares, 4 keys per load.
+    for (int j = lane; j < nA; j += G) {
+        const bool in = sdist[j] < INFINITY;
+        if (in) {
+            // (d_k, k) < (d_j, j)  <=>  k < j ? bits_k <= bits_j : bits_k < bits_j. One compare per key: chunks of four
+            // keys below j's own chunk count `<= bits_j` (= `< bits_j + 1`), the others `< bits_j`; the (rare) exact ties
+            // with a smaller index inside j's own chunk are added afterwards from that one chunk.
+            const unsigned uj = dre_f2u(sdist[j]);
+            const int jc = j & ~3;
+            int r = 0;
+#pragma unroll 2
+            for (int k = 0; k < nA4; k += 4) {
+                const float4 q = dre_ld4(sdist, k);
+                const unsigned thr = uj + (k < jc ? 1u : 0u);
+                r += (int)(dre_f2u(q.x) < thr) + (int)(dre_f2u(q.y) < thr) + (int)(dre_f2u(q.z) < thr) + (int)(dre_f2u(q.w) < thr);
+            }
+            {
+                const float4 q = dre_ld4(sdist, jc);
+                const int jr = j - jc;   // 0..3: position of j in its chunk
+                r += (int)(jr > 0 && dre_f2u(q.x) == uj) + (int)(jr > 1 && dre_f2u(q.y) == uj) + (int)(jr > 2 && dre_f2u(q.z) == uj);
+            }
+            if (r < maxNeighbors) L[r] = orca_make_line(px, py, vx, vy, rs, ax[j], ay[j], avx[j], avy[j], ar[j], invTH, invDt, mask);
+        }
+    }
+    const int m = cnt < maxNeighbors ? cnt : maxNeighbors;
+    g.sync();
+
+    return m;
+}
+
 // Neighbour search + ORCA lines of agent `self` into L[0..m) (sorted like RVO2's neighbour list). Returns m.
 //
 // RVO2 finds the neighbours with a kd-tree range query (Agent::computeNeighbors); an env holds at most 65 agents, all of
 // them in one shared-memory tile, so the query here is a CUT-OFF + COMPACTION instead of a tree or a uniform grid: every
 // lane tests its candidates against neighborDist^2 (strict <, like RVO2), a ballot + prefix count packs the in-range
 // ones -- squared distance into sdist[0..cnt), agent index into sidx[0..cnt) -- and only those are ranked. With the
-// reference's neighbor_dist = 10 everything is in range and the compaction costs a ballot per 8 candidates; with a short
-// range (BASELINE config 4's neighbor_dist = 3: 6 of 50 in range) the ranking works on the 6, not on the 51.
+// reference's neighbor_dist = 10 everything is in range and the compaction only costs (measured on B200: ha_step 0.608 ->
+// 0.664 ms at 16384 x 20, the ORCA-only step of 8192 x 50 1.53 -> 1.75 ms), so the kernels are instantiated for both and
+// the host picks: cut-off when neighbor_dist is smaller than the crowd's radius (BASELINE config 4's neighbor_dist = 3:
+// 6 of 50 in range, 0.875 -> 0.790 ms), the full ranking otherwise.
 template <class Grp, class DistT, class LinesT>
-DRE_HD int orca_build_lines(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+DRE_HD int orca_build_lines_cutoff(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                             const float *ar, int self, float neighborDist, int maxNeighbors, float invTH, float invDt,
                             DistT sdist, DistT sidx, LinesT L, unsigned &mask)
 {
@@ -350,7 +408,7 @@ DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine 
 // lines with the preferred velocity; if it fails at line `fail`, every later violated line i re-enters the same body
 // with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
 // solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
-template <class Grp, class DistT, class LinesT>
+template <bool CUTOFF = false, class Grp, class DistT, class LinesT>
 DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
                              int maxNeighbors, float invTH, float invDt, DistT sdist, DistT sidx, LinesT L, float &outx, float &outy,
@@ -359,7 +417,8 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
     constexpr int G = Grp::size;
     const int lane = g.rank();
     unsigned mask = 0;
-    const int m = orca_build_lines(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, sidx, L, mask);
+    const int m = CUTOFF ? orca_build_lines_cutoff(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, sidx, L, mask)
+                         : orca_build_lines_all(g, nA, ax, ay, avx, avy, ar, self, neighborDist, maxNeighbors, invTH, invDt, sdist, L, mask);
 
     LinesT P = L + nA;                       // LP3's projected lines
     float rx = 0.0f, ry = 0.0f;

@@ -13,7 +13,7 @@ struct OrcaTileLayout {
     size_t off_lines, off_agents, off_dist, bytes;
 };
 
-static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads, int EPB)
+static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads, int EPB, bool cutoff)
 {
     OrcaTileLayout l;
     l.nA = Nh + (robot_visible ? 1 : 0);
@@ -22,11 +22,11 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
     l.off_lines = 0;
     l.off_agents = (size_t)l.NG * 2 * l.nA * sizeof(OLine);
     l.off_dist = (l.off_agents + (size_t)EPB * 5 * l.nA * sizeof(float) + 15) / 16 * 16;
-    l.bytes = (l.off_dist + (size_t)l.NG * 2 * ((l.nA + 3) & ~3) * sizeof(float) + 15) / 16 * 16 + 16;   // distances + indices, + work counter
+    l.bytes = (l.off_dist + (size_t)l.NG * (cutoff ? 2 : 1) * ((l.nA + 3) & ~3) * sizeof(float) + 15) / 16 * 16 + 16;   // distances (+ indices), + work counter
     return l;
 }
 
-template <int G>
+template <int G, bool CUTOFF>
 __global__ void __launch_bounds__(512)
 orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__restrict__ hpos,
                     const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
@@ -68,7 +68,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     const int gi = threadIdx.x / G;
     OLine *L = lines + (size_t)gi * 2 * nA;
     const int nA4 = (nA + 3) & ~3;
-    float *sd = dist + (size_t)gi * 2 * nA4;
+    float *sd = dist + (size_t)gi * (CUTOFF ? 2 : 1) * nA4;
     const float invTH = 1.0f / p.time_horizon, invDt = 1.0f / p.time_step;
     const int maxNb = p.max_neighbors > 0 ? p.max_neighbors : nA - 1;
 
@@ -96,7 +96,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
             double pvx = dx, pvy = dy;
             if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
             const float *A = agents + (size_t)el * 5 * nA;
-            orca_solve_group(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+            orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
                              p.max_speed_self, p.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              stats ? &stats[gidx] : nullptr, (p.group_lanes & 0x100) != 0);
         }
@@ -105,7 +105,7 @@ orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__
     }
 }
 
-template <int G>
+template <int G, bool CUTOFF>
 static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hpos, const float *hvel, const double *goal,
                        const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
 {
@@ -122,8 +122,8 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
     int EPB = (apg * NGl) / Nh;
     if (EPB > (E + 591) / 592) EPB = (E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
     if (EPB < 1) EPB = 1;
-    const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB);
-    auto kern = orca_predict_kernel<G>;
+    const OrcaTileLayout l = orca_layout(Nh, p.robot_visible, G, threads, EPB, CUTOFF);
+    auto kern = orca_predict_kernel<G, CUTOFF>;
     if (l.bytes > 48 * 1024) {
         if (l.bytes > 220 * 1024) return DRE_ERR_INVALID;
         DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.bytes));
@@ -305,6 +305,15 @@ int dre_orca_joint_launch(const dre_orca_params &p, int N, int n_others, const f
     return launch_orca_joint<8>(p, N, n_others, self8, others5, vnew, stats, queue, s);
 }
 
+// Short neighbour range (below the reference crowd's radius of 5 m): most candidates are out of range, the cut-off +
+// compaction variant of the neighbour search wins; group_lanes bits 0x800 / 0x1000 force it on / off (A/B measurements).
+bool dre_orca_use_cutoff(const dre_orca_params &p)
+{
+    if (p.group_lanes & 0x800) return true;
+    if (p.group_lanes & 0x1000) return false;
+    return p.neighbor_dist < 5.0f;
+}
+
 int dre_orca_pick_group(const dre_orca_params &p, int Nh)
 {
     const int gl = p.group_lanes & 0xff;
@@ -319,12 +328,13 @@ int dre_orca_launch(const dre_orca_params &p, int E, int Nh, const double *hpos,
                     const double *rpos, const uint8_t *is_static, float *vnew, dre_orca_stats *stats, cudaStream_t s)
 {
     if (E <= 0 || Nh <= 0 || Nh > DRE_MAX_HUMANS) return DRE_ERR_INVALID;
+    const bool cut = dre_orca_use_cutoff(p);
     switch (dre_orca_pick_group(p, Nh)) {
     case 1: return launch_orca_thread(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
-    case 2: return launch_orca<2>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
-    case 4: return launch_orca<4>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
-    case 8: return launch_orca<8>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
-    case 16: return launch_orca<16>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
-    default: return launch_orca<32>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 2: return cut ? launch_orca<2, true>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s) : launch_orca<2, false>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 4: return cut ? launch_orca<4, true>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s) : launch_orca<4, false>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 8: return cut ? launch_orca<8, true>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s) : launch_orca<8, false>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    case 16: return cut ? launch_orca<16, true>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s) : launch_orca<16, false>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
+    default: return cut ? launch_orca<32, true>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s) : launch_orca<32, false>(p, E, Nh, hpos, hvel, goal, rpos, is_static, vnew, stats, s);
     }
 }

@@ -111,6 +111,8 @@ def load():
         L.dre_env_crowd_step.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_step_host.argtypes = [c_vp, c_vp, c_vp]
         L.dre_env_set_host_chunks.argtypes = [c_vp, c_i32]
+        L.dre_env_set_host_outputs.argtypes = [c_vp, c_i32]
+        L.dre_env_d2h_probe.argtypes = [c_vp, c_vp, c_i32, P(c_d)]
         L.dre_env_invalidate_orca_cache.argtypes = [c_vp, c_vp]
         L.dre_env_observe.argtypes = [c_vp, c_i32, c_vp]
         L.dre_env_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]

@@ -82,6 +82,8 @@ struct dre_env {
     int *d_chunk_count = nullptr;  // device [MAX_CHUNKS]
     int step_seq = 0;
     int host_chunks = 8;
+    int host_mode = 0;             // dre_env_set_host_outputs: 0 whole float64 slab, 1 observations as float32, 2 control fields only
+    float *d_stage32 = nullptr;    // mode 1: float32 images of the observation fields, at the fields' own byte offsets
     bool was_reset = false;
     void *stats_comm = nullptr;    // ncclComm_t of dre_env_stats_comm_init (the only collective of the engine)
     // per-kernel timing (bench.py's roofline leg)
@@ -186,6 +188,16 @@ void use_slab(dre_env *h, int b)
     h->D.prev_done_bits = h->outdev[b ^ 1].done_bits;
 }
 
+// The copy stream also runs the float32 conversion kernels of host-output mode 1: highest priority, so that their few
+// CTAs take the next CTA slot that frees up instead of queueing behind the crowd half's pending CTAs.
+cudaError_t create_copy_stream(cudaStream_t *st)
+{
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
+}
+
 int n_mpc_actions(const dre_env_config &c)
 {
     const int a = c.mpc_actions_in_input > 0 ? c.mpc_actions_in_input : 4;
@@ -238,7 +250,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
         (e = cudaMalloc(&h->slabs[1], obytes)) != cudaSuccess || (e = cudaMemset(h->slabs[1], 0, obytes)) != cudaSuccess ||
         (e = cudaMalloc(&h->d_actions, (size_t)D.E * 2 * sizeof(double))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = create_copy_stream(&h->copy_stream)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_pt, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
@@ -270,7 +282,7 @@ extern "C" int dre_env_destroy(dre_env *h)
     cudaDeviceSynchronize();
     dre_mpc_destroy(h->mpc);
     if (h->profiling) dre_env_set_profiling(h, 0);
-    cudaFree(h->state_block); cudaFree(h->slabs[0]); cudaFree(h->slabs[1]); cudaFree(h->d_actions);
+    cudaFree(h->state_block); cudaFree(h->slabs[0]); cudaFree(h->slabs[1]); cudaFree(h->d_actions); cudaFree(h->d_stage32);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
@@ -519,19 +531,38 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     EnvDev D = h->D;
     D.actions = h->d_actions;
     char *dev = (char *)h->slab, *host = (char *)slab_host;
-    auto d2h = [&](const void *field, size_t per_env, int e0, int e1) -> cudaError_t {
-        const size_t off = (const char *)field - dev + (size_t)e0 * per_env;
-        return cudaMemcpyAsync(host + off, dev + off, (size_t)(e1 - e0) * per_env, cudaMemcpyDeviceToHost, c);
+    const int mode = h->host_mode;
+    if (mode == 1 && !h->d_stage32) DRE_CUDA_TRY(cudaMalloc(&h->d_stage32, h->slab_bytes));
+    // elements [first, first + count) of one float64 field of the slab to the host: as they are, or (mode 1, observation
+    // fields) rounded once to float32 by a small kernel on the copy stream; the float32 image of a field starts at the
+    // field's own byte offset of the host slab. `raw` runs (several control fields + padding) are copied byte for byte.
+    auto send_field = [&](const double *field, size_t first, size_t count, bool is_obs) -> int {
+        if (count == 0) return DRE_OK;
+        const size_t foff = (const char *)field - dev;
+        if (mode == 1 && is_obs) {
+            float *st = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_stage32) + foff) + first;
+            const int r = dre_env_launch_cvt32(field + first, st, count, c);
+            if (r) return r;
+            DRE_CUDA_TRY(cudaMemcpyAsync(host + foff + first * sizeof(float), st, count * sizeof(float), cudaMemcpyDeviceToHost, c));
+        } else {
+            DRE_CUDA_TRY(cudaMemcpyAsync(host + foff + first * sizeof(double), field + first, count * sizeof(double), cudaMemcpyDeviceToHost, c));
+        }
+        return DRE_OK;
     };
+    auto send_raw = [&](const void *p0, const void *p1) -> int {
+        const size_t off = (const char *)p0 - dev, nb = (const char *)p1 - (const char *)p0;
+        if (nb) DRE_CUDA_TRY(cudaMemcpyAsync(host + off, dev + off, nb, cudaMemcpyDeviceToHost, c));
+        return DRE_OK;
+    };
+    const size_t LB = h->D.LB, NPT = 4 * (size_t)(h->D.lookahead + h->D.lookbehind);
     int rc = dre_env_launch_pt(D, 0, s);
     if (rc) return rc;
     // the PT state (the second largest output) and the executed actions are final after pt_step
     DRE_CUDA_TRY(cudaEventRecord(h->ev_pt, s));
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_pt, 0));
-    {   // pt_state and actions_used are adjacent at the head of the slab
-        const size_t head = (const char *)h->out.mpc_actions - dev;
-        DRE_CUDA_TRY(cudaMemcpyAsync(host, dev, head, cudaMemcpyDeviceToHost, c));
-    }
+    if (mode != 2) { rc = send_field(h->out.pt_state, 0, (size_t)E * NPT, true); if (rc) return rc; }
+    rc = send_raw(h->out.actions_used, h->out.mpc_actions);
+    if (rc) return rc;
     // crowd half BEFORE the MPC solve on this path: it produces 3/4 of the bytes, so its copies get the MPC solve's
     // duration as additional cover (neither half reads the other's outputs; the merge only needs pt_step's)
     const int epb = dre_env_ha_envs_per_cta(D);
@@ -540,55 +571,68 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
     int per = ((E + chunks - 1) / chunks + epb - 1) / epb * epb;
     chunks = (E + per - 1) / per;
     h->step_seq = h->step_seq == 0x7fffffff ? 1 : h->step_seq + 1;
-    D.chunk_flags = h->d_flags; D.chunk_count = h->d_chunk_count; D.chunk_envs = per; D.step_seq = h->step_seq;
+    if (mode != 2) { D.chunk_flags = h->d_flags; D.chunk_count = h->d_chunk_count; D.chunk_envs = per; D.step_seq = h->step_seq; }
     rc = dre_env_launch_ha(D, 0, 1, s);
     if (rc) return rc;
     DRE_CUDA_TRY(cudaEventRecord(h->ev_front, s));     // crowd half done
     // The solve stays BEHIND the crowd half here, not next to it as in dre_env_step: this path is bound by the copies, and
     // a solve that shares the SMs delays the chunk flags (measured p50 1.19 ms serial vs 1.27 ms concurrent, also with the
     // solve on a lowest-priority stream: priorities do not stop its persistent CTAs from taking freed slots early).
-    rc = env_solve_mpc(h, D, s);
-    if (rc) return rc;
+    if (mode == 2) {   // nothing big travels: the solve runs NEXT to the crowd half, as in dre_env_step
+        DRE_CUDA_TRY(cudaStreamWaitEvent(h->mpc_stream, h->ev_pt, 0));
+        rc = env_solve_mpc(h, D, h->mpc_stream);
+        if (rc) return rc;
+        DRE_CUDA_TRY(cudaEventRecord(h->ev_join, h->mpc_stream));
+        DRE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+    } else {
+        rc = env_solve_mpc(h, D, s);
+        if (rc) return rc;
+    }
     DRE_CUDA_TRY(cudaEventRecord(h->ev_done, s));      // step done
     if (tr) t_enq = now_us();
-    volatile int *flags = h->h_flags;
-    for (int i = 0; i < chunks; ++i) {
-        const int e0 = i * per, e1 = e0 + per < E ? e0 + per : E;
-        for (unsigned spin = 0; flags[i] != h->step_seq; ++spin) {
-            if ((spin & 0x3ff) == 0x3ff) {   // the launch may have failed or finished without us seeing the flag yet
-                const cudaError_t q = cudaEventQuery(h->ev_front);
-                if (q == cudaSuccess) { if (flags[i] != h->step_seq) { h->h_flags[i] = h->step_seq; } break; }
-                if (q != cudaErrorNotReady) { dre_set_cuda_error(q, __FILE__, __LINE__); return DRE_ERR_CUDA; }
-            }
+    if (mode != 2) {
+        volatile int *flags = h->h_flags;
+        const size_t per_env = (size_t)Nh * 2 * H;
+        for (int i = 0; i < chunks; ++i) {
+            const int e0 = i * per, e1 = e0 + per < E ? e0 + per : E;
+            for (unsigned spin = 0; flags[i] != h->step_seq; ++spin) {
+                if ((spin & 0x3ff) == 0x3ff) {   // the launch may have failed or finished without us seeing the flag yet
+                    const cudaError_t q = cudaEventQuery(h->ev_front);
+                    if (q == cudaSuccess) { if (flags[i] != h->step_seq) { h->h_flags[i] = h->step_seq; } break; }
+                    if (q != cudaErrorNotReady) { dre_set_cuda_error(q, __FILE__, __LINE__); return DRE_ERR_CUDA; }
+                }
 #if defined(__x86_64__)
-            __builtin_ia32_pause();
+                __builtin_ia32_pause();
 #endif
+            }
+            if (tr) t_flag[i] = now_us();
+            // the pair history of the crowd is 3/4 of the crowd half's bytes: one copy per chunk
+            rc = send_field(h->out.spatial_edges, (size_t)e0 * per_env, (size_t)(e1 - e0) * per_env, true);
+            if (rc) return rc;
         }
-        if (tr) t_flag[i] = now_us();
-        // the pair history of the crowd is 3/4 of the crowd half's bytes: one copy per chunk
-        DRE_CUDA_TRY(d2h(h->out.spatial_edges, (size_t)Nh * 2 * H * sizeof(double), e0, e1));
-    }
-    // every CTA has written its observation: the small observation arrays go as two contiguous runs of the slab
-    // (robot_node .. percent_episode, human_valid .. detected_humans) while the last CTAs finish their look-ahead pass
-    {
-        const size_t a0 = (const char *)h->out.robot_node - dev, a1 = (const char *)h->out.spatial_edges - dev;
-        const size_t b0 = (const char *)h->out.human_valid - dev, b1 = (const char *)h->out.rewards - dev;
-        DRE_CUDA_TRY(cudaMemcpyAsync(host + a0, dev + a0, a1 - a0, cudaMemcpyDeviceToHost, c));
-        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
+        // every CTA has written its observation: the small observation arrays go as two contiguous runs of the slab
+        // (robot_node .. percent_episode, human_valid .. detected_humans) while the last CTAs finish their look-ahead pass
+        if (mode == 0) {
+            rc = send_raw(h->out.robot_node, h->out.spatial_edges);
+            if (rc) return rc;
+            rc = send_raw(h->out.human_valid, h->out.rewards);
+            if (rc) return rc;
+        } else {
+            if ((rc = send_field(h->out.robot_node, 0, (size_t)E * 2 * LB, true)) || (rc = send_field(h->out.past_robot_vel, 0, (size_t)E * 2 * LB, true)) ||
+                (rc = send_field(h->out.percent_episode, 0, (size_t)E, true)) || (rc = send_field(h->out.human_valid, 0, (size_t)E * Nh, true)) ||
+                (rc = send_field(h->out.detected_humans, 0, (size_t)E, true))) return rc;
+        }
     }
     // rewards, info, done bits once the crowd half is complete; MPC actions, MPC status and the done flags (which sit
     // behind the status in the slab) once the solve is
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_front, 0));
-    {
-        const size_t b0 = (const char *)h->out.rewards - dev, b1 = (const char *)h->out.mpc_status - dev;
-        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
-    }
+    rc = send_raw(h->out.rewards, h->out.mpc_status);
+    if (rc) return rc;
     DRE_CUDA_TRY(cudaStreamWaitEvent(c, h->ev_done, 0));
-    {
-        const size_t b0 = (const char *)h->out.mpc_status - dev, b1 = h->slab_bytes;
-        DRE_CUDA_TRY(d2h(h->out.mpc_actions, (size_t)n_mpc_actions(h->cfg) * sizeof(double), 0, E));
-        DRE_CUDA_TRY(cudaMemcpyAsync(host + b0, dev + b0, b1 - b0, cudaMemcpyDeviceToHost, c));
-    }
+    rc = send_raw(h->out.mpc_actions, h->out.robot_node);
+    if (rc) return rc;
+    rc = send_raw(h->out.mpc_status, dev + h->slab_bytes);
+    if (rc) return rc;
     if (tr) {
         cudaEventSynchronize(h->ev_done);
         const double t_done = now_us();
@@ -599,6 +643,33 @@ extern "C" int dre_env_step_host(dre_env *h, const double *actions_host, void *s
         fprintf(stderr, ", step (crowd half, then MPC) done %.0f, copies done %.0f us\n", t_done - t_start, t_end - t_start);
     }
     DRE_CUDA_TRY(cudaStreamSynchronize(c));
+    return DRE_OK;
+}
+
+extern "C" int dre_env_set_host_outputs(dre_env *h, int32_t mode)
+{
+    if (!h || mode < 0 || mode > 2) return DRE_ERR_INVALID;
+    h->host_mode = mode;
+    return DRE_OK;
+}
+
+// the D2H floor of this box for one step's slab: plain pinned copies, nothing else on the GPU
+extern "C" int dre_env_d2h_probe(dre_env *h, void *slab_host, int32_t reps, double *ms_per_slab)
+{
+    if (!h || !slab_host || reps < 1 || !ms_per_slab) return DRE_ERR_INVALID;
+    cudaEvent_t e0, e1;
+    DRE_CUDA_TRY(cudaEventCreate(&e0));
+    DRE_CUDA_TRY(cudaEventCreate(&e1));
+    DRE_CUDA_TRY(cudaDeviceSynchronize());
+    DRE_CUDA_TRY(cudaMemcpyAsync(slab_host, h->slab, h->slab_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    DRE_CUDA_TRY(cudaEventRecord(e0, h->copy_stream));
+    for (int i = 0; i < reps; ++i) DRE_CUDA_TRY(cudaMemcpyAsync(slab_host, h->slab, h->slab_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    DRE_CUDA_TRY(cudaEventRecord(e1, h->copy_stream));
+    DRE_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DRE_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_slab = (double)ms / reps;
     return DRE_OK;
 }
 

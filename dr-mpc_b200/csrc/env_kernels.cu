@@ -964,6 +964,25 @@ int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 #undef DRE_HA_CASE
 }
 
+// float64 -> float32, one rounding (the opt-in float32 observation output of the host path)
+__global__ void cvt32_kernel(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + i);
+        *reinterpret_cast<float2 *>(dst + i) = make_float2((float)v.x, (float)v.y);
+    } else if (i < n) dst[i] = (float)src[i];
+}
+
+int dre_env_launch_cvt32(const double *src, float *dst, size_t n, cudaStream_t s)
+{
+    if (n == 0) return DRE_OK;
+    const size_t pairs = (n + 1) / 2;
+    cvt32_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(src, dst, n);
+    DRE_CUDA_TRY(cudaGetLastError());
+    return DRE_OK;
+}
+
 int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s)
 {
     const int threads = 128, envs_per_block = threads / 8;   // PT_LANES lanes per env

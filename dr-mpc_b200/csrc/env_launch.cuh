@@ -71,6 +71,7 @@ int dre_env_launch_pt(const EnvDev &D, int mode, cudaStream_t s);
 int dre_env_launch_mpc_stats(const EnvDev &D, cudaStream_t s);
 int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, const double *backup, int A, double *safe_out,
                         int32_t *info, uint8_t *cand_safe, cudaStream_t s);
+int dre_env_launch_cvt32(const double *src, float *dst, size_t n, cudaStream_t s);
 int dre_env_launch_cvmm_check(const EnvDev &D, const double *actions, int num_steps, uint8_t *safe_out, double *dist_out, cudaStream_t s);
 int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double *hgoal_init, cudaStream_t s);
 int dre_env_launch_switch_path(const EnvDev &D, cudaStream_t s);

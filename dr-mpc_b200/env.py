@@ -216,18 +216,47 @@ class BatchedHAAndPTEnv:
         return sc.bool(), a, st.bool()
 
     # ---- host-buffer entry point (end-to-end drop-in for a CPU-side caller) ----
-    def step_host(self, actions_np):
-        """actions: numpy [E,2] float64 (pinned for best speed) -> dict of numpy views into one pinned host slab."""
+    OBS_FIELDS = ("pt_state", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
+    CONTROL_FIELDS = ("actions_used", "mpc_actions", "rewards", "info", "done_bits", "mpc_status", "done_flags")
+
+    def _make_host_views(self):
         import torch
         if self._host_slab is None:
             self._host_slab = torch.empty(self.slab_bytes, dtype=torch.uint8).pin_memory()
-            base = self._host_slab.numpy()
-            self._host_views = {}
-            for name, ptr, shape, kind in self._layout:
-                off = int(ptr) - int(self._out.slab)
-                n = int(np.prod(shape))
-                dt = np.dtype(_TYPESTR[kind])
-                self._host_views[name] = base[off:off + n * dt.itemsize].view(dt).reshape(shape)
+        base = self._host_slab.numpy()
+        mode = getattr(self, "_host_mode", 0)
+        self._host_views = {}
+        self.host_bytes_per_step = 0
+        for name, ptr, shape, kind in self._layout:
+            if mode == 2 and name in self.OBS_FIELDS:
+                continue
+            off = int(ptr) - int(self._out.slab)
+            n = int(np.prod(shape))
+            dt = np.dtype("<f4") if (mode == 1 and name in self.OBS_FIELDS) else np.dtype(_TYPESTR[kind])
+            self._host_views[name] = base[off:off + n * dt.itemsize].view(dt).reshape(shape)
+            self.host_bytes_per_step += n * dt.itemsize
+
+    def configure_host_outputs(self, out_dtype="float64", outputs="all"):
+        """What step_host brings back each step: out_dtype 'float32' = the observation fields rounded once to float32 on the
+        device (half the bytes); outputs 'control' = only actions / rewards / info / done words / MPC status (the observations
+        stay in HBM for a GPU-side consumer). Default: the whole float64 slab, like the reference's loop receives."""
+        mode = 2 if outputs == "control" else (1 if out_dtype in ("float32", "f32") else 0)
+        _lib.check(self._L.dre_env_set_host_outputs(self._h, mode))
+        self._host_mode = mode
+        self._host_views = None
+
+    def d2h_ceiling_ms(self, reps=20):
+        """Milliseconds of one plain pinned D2H copy of the slab (the floor of a step_host that returns everything)."""
+        if self._host_slab is None:
+            self._make_host_views()
+        ms = _lib.c_d()
+        _lib.check(self._L.dre_env_d2h_probe(self._h, ctypes.c_void_p(self._host_slab.data_ptr()), int(reps), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def step_host(self, actions_np):
+        """actions: numpy [E,2] float64 (pinned for best speed) -> dict of numpy views into one pinned host slab."""
+        if self._host_slab is None or getattr(self, "_host_views", None) is None:
+            self._make_host_views()
         a = np.ascontiguousarray(actions_np, dtype=np.float64)
         _lib.check(self._L.dre_env_step_host(self._h, a.ctypes.data_as(ctypes.c_void_p),
                                              ctypes.c_void_p(self._host_slab.data_ptr())))

@@ -262,6 +262,16 @@ int dre_env_crowd_step(dre_env *h, int32_t write_obs, void *stream);
  * memory lets the copies overlap the kernels). Synchronous: returns when the whole slab has arrived. Runs on the handle's own
  * streams, ordered after earlier reset() / step() / observe() calls whatever stream those were given. */
 int dre_env_step_host(dre_env *h, const double *actions_host, void *slab_host);
+/* What dre_env_step_host returns to the host each step (the device slab always holds everything in float64):
+ *   0  the whole float64 slab (default; what the reference's loop receives: float64 numpy arrays)
+ *   1  observation fields (pt_state, robot_node, past_robot_vel, percent_episode, spatial_edges, human_valid,
+ *      detected_humans) as float32 -- each float64 result rounded ONCE on the device -- stored at the field's own byte
+ *      offset of slab_host (first half of its region); the control fields below stay float64
+ *   2  control fields only: actions_used, mpc_actions, rewards, info, done_bits, mpc_status, done_flags -- for a caller whose
+ *      networks consume the observations on the GPU (the reference moves S to cuda:0 anyway, scripts/utils/misc.py:7-21) */
+int dre_env_set_host_outputs(dre_env *h, int32_t mode);
+/* measurement aid: milliseconds of one plain pinned D2H copy of slab_bytes on this handle's copy stream (mean of reps) */
+int dre_env_d2h_probe(dre_env *h, void *slab_host, int32_t reps, double *ms_per_slab);
 /* number of env chunks whose observation copies dre_env_step_host overlaps with the crowd half (1..32, default 8) */
 int dre_env_set_host_chunks(dre_env *h, int32_t chunks);
 /* orca_dedup: forget the cached look-ahead velocities (call after writing human / robot state through dre_env_state) */

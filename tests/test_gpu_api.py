@@ -147,3 +147,31 @@ def test_soft_reset_decide_predicts_the_device_machine():
         assert not bool(stuck.any())
         seen += int(scripted.sum())
     assert seen > 100
+
+
+def test_host_output_modes():
+    """dre_env_set_host_outputs: float32 observations are the float64 results rounded once (bit-equal to numpy's cast of
+    the full slab); 'control' brings back only the control fields, identical to the full slab's."""
+    import torch
+    import dr_mpc_b200 as d
+    E, Nh = 1000 + 13, 10
+    envs = {m: d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E) for m in ("full", "f32", "ctl")}
+    envs["f32"].configure_host_outputs(out_dtype="float32")
+    envs["ctl"].configure_host_outputs(outputs="control")
+    for e in envs.values():
+        e.reset()
+    act = envs["full"].out["mpc_actions"][:, :2].cpu().numpy().copy()
+    for t in range(5):
+        v = {m: e.step_host(act) for m, e in envs.items()}
+        for name in d.BatchedHAAndPTEnv.OBS_FIELDS:
+            assert v["f32"][name].dtype == np.float32 and name not in v["ctl"]
+            assert np.array_equal(v["f32"][name], v["full"][name].astype(np.float32)), (t, name)
+        for name in d.BatchedHAAndPTEnv.CONTROL_FIELDS:
+            for m in ("f32", "ctl"):
+                assert np.array_equal(np.asarray(v[m][name]).view(np.uint8), np.asarray(v["full"][name]).view(np.uint8)), (t, m, name)
+        # the device slab stays float64 and complete in every mode
+        for m in ("f32", "ctl"):
+            assert torch.equal(envs[m].out["spatial_edges"], envs["full"].out["spatial_edges"])
+        act = v["full"]["mpc_actions"][:, :2].copy()
+    assert envs["f32"].host_bytes_per_step < 0.65 * envs["full"].host_bytes_per_step and envs["ctl"].host_bytes_per_step < 0.05 * envs["full"].host_bytes_per_step
+    assert envs["full"].d2h_ceiling_ms(reps=3) > 0

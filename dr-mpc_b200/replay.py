@@ -81,12 +81,20 @@ class BatchedReplayBuffer:
         self.valid_entries = min(self.buffer_size, self.valid_entries + n)
         return n
 
+    def physical_index(self, chronological):
+        """Ring slot of the `chronological`-th oldest valid entry. The reference keeps its tensors in insertion order (it rolls
+        everything by one when full, storage.py:56-75): its index j is this buffer's slot (head + j) % size once full."""
+        if self.valid_entries < self.buffer_size:
+            return chronological
+        return (chronological + self._head) % self.buffer_size
+
     def sample_from_buffer(self, batch_size, indices_to_sample=None):
-        """Same return as storage.py:101-133: (S, actions, S_prime, rewards, done) gathered at random valid indices."""
+        """Same return as storage.py:101-133: (S, actions, S_prime, rewards, done) gathered at random valid indices;
+        `indices_to_sample` are chronological (0 = oldest), like the reference's."""
         import torch
         if indices_to_sample is None:
             indices_to_sample = torch.randint(0, max(self.valid_entries, 1), (batch_size,), device=self.device)
-        idx = indices_to_sample.to(self.device)
+        idx = self.physical_index(indices_to_sample.to(self.device))
         rb = self.replay_buffer
         return (_nest({k: v[idx] for k, v in self._S.items()}), rb['actions'][idx], _nest({k: v[idx] for k, v in self._Sp.items()}),
                 rb['rewards'][idx], rb['done'][idx])

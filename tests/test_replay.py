@@ -52,3 +52,54 @@ def test_oversized_batch_keeps_the_newest_rows():
     R = torch.arange(8, dtype=torch.float64)
     rb.insert(_obs(8, 1), torch.zeros(8, 2), _obs(8, 2), R, torch.zeros(8))
     assert sorted(rb.replay_buffer['rewards'][:, 0].tolist()) == [3.0, 4.0, 5.0, 6.0, 7.0]
+
+
+def test_matches_reference_replay_buffer_on_the_same_trace():
+    """The reference's own ReplayBuffer (scripts/utils/storage.py:6-133, imported unmodified; torch only) and
+    BatchedReplayBuffer fed the same transitions -- one by one there, in masked batches here, through two overflows of the
+    buffer -- hold the same entries in the same chronological order and return the same samples for the same indices."""
+    import os
+    import sys
+    import types
+    import torch
+    ref_root = os.environ.get("DRE_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "scripts")):
+        pytest.skip("the reference tree is only in the build container")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_storage", os.path.join(ref_root, "scripts", "utils", "storage.py"))
+    ref_storage = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_storage)
+    import dr_mpc_b200 as d
+    E, Nh, size = 7, 3, 40
+    gen = torch.Generator().manual_seed(3)
+
+    def obs(n):
+        return {'PT': {'PT_state': torch.randn(n, 100, generator=gen, dtype=torch.float64), 'MPC_actions': torch.randn(n, 8, generator=gen, dtype=torch.float64)},
+                'HA': {'spatial_edges': torch.randn(n, Nh, 14, generator=gen, dtype=torch.float64), 'robot_node': torch.randn(n, 12, generator=gen, dtype=torch.float64),
+                       'detected_human_num': torch.full((n,), float(Nh), dtype=torch.float64)}}
+    cm = types.SimpleNamespace(config_general=types.SimpleNamespace(device='cpu'))
+    take = lambda S, i: {k: {kk: vv[i:i + 1] for kk, vv in v.items()} for k, v in S.items()}
+    ref = ref_storage.ReplayBuffer(take(obs(1), 0), cm, size)
+    ours = d.BatchedReplayBuffer(obs(E), buffer_size=size, device='cpu')
+    for t in range(16):                                           # 16 x ~5 kept rows: the buffer overflows twice
+        S, Sp = obs(E), obs(E)
+        A = torch.randn(E, 2, generator=gen, dtype=torch.float64); R = torch.randn(E, generator=gen, dtype=torch.float64)
+        done = (torch.rand(E, generator=gen) < 0.2)
+        mask = torch.rand(E, generator=gen) < 0.75
+        ours.insert(S, A, Sp, R, done, mask=mask)
+        for i in torch.nonzero(mask).flatten().tolist():          # the reference inserts one transition per call
+            ref.insert(take(S, i), A[i:i + 1], take(Sp, i), R[i].item(), float(done[i]))
+    assert ref.valid_entries == ours.valid_entries == size and ours.full() and ref.full()
+    order = ours.physical_index(torch.arange(size))
+    for grp in ('S', 'S_prime'):
+        for k, v in ref.replay_buffer[grp].items():
+            for kk, vv in v.items():
+                assert torch.equal(vv, ours.replay_buffer[grp][k][kk][order]), (grp, k, kk)
+    for k in ('rewards', 'actions', 'done'):
+        assert torch.equal(ref.replay_buffer[k], ours.replay_buffer[k][order]), k
+    idx = torch.randint(0, size, (25,), generator=gen)
+    a, b = ref.sample_from_buffer(25, idx), ours.sample_from_buffer(25, idx)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    for k in a[0]:
+        for kk in a[0][k]:
+            assert torch.equal(a[0][k][kk], b[0][k][kk]) and torch.equal(a[2][k][kk], b[2][k][kk])

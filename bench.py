@@ -465,6 +465,8 @@ def run_env(a):
     else:
         cnt, sums = env.stats()
     cnt = cnt.cpu().numpy(); sums = sums.cpu().numpy()
+    if int(cnt[0]) != world * E * a.steps:
+        raise SystemExit(f"episode statistics do not add up: {int(cnt[0])} env-steps counted, {world * E * a.steps} timed ({stats_via})")
 
     # ---------------- per-kernel durations (same loop, events around every kernel) ----------------
     env.set_profiling(True)

@@ -518,9 +518,8 @@ def run_env(a):
 
     # ---------------- de-duplicated variant, reported separately: the look-ahead ORCA pass of step t IS the
     # movement pass of step t+1 unless a goal was resampled in between; bit-identical results, one pass per step ----------------
-    dedup = None
-    if not a.no_dedup:
-        env2 = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, horizon=K, env_id_offset=rank * E, orca_dedup=True, soft_reset_on_device=a.soft_reset), num_envs=E, device=dev)
+    def variant(**kw):
+        env2 = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, horizon=K, env_id_offset=rank * E, soft_reset_on_device=a.soft_reset, **kw), num_envs=E, device=dev)
         env2.reset()
         act2 = env2.out["mpc_actions"][:, :2].clone()
         tk = [0]
@@ -534,10 +533,18 @@ def run_env(a):
         for _ in range(max(a.warmup, 3)):
             step2(); flush.zero_()
         ms2, _, _ = _timed(step2, a.steps, flush, barrier, max_over_ranks, rank, local, sample_clocks=False)
-        dedup = {"value": world * E * a.steps / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2 / a.steps,
-                 "what": "EngineConfig(orca_dedup=True): same steps, same policy, same results bit for bit (tests/test_gpu_env.py::"
-                         "test_orca_dedup_is_bit_identical); NOT the headline, which keeps the reference's two ORCA passes per step"}
         del env2
+        return {"value": world * E * a.steps / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2 / a.steps}
+
+    dedup = pruned = None
+    if not a.no_dedup:
+        dedup = variant(orca_dedup=True)
+        dedup["what"] = ("EngineConfig(orca_dedup=True): same steps, same policy, same results bit for bit (tests/test_gpu_env.py::"
+                         "test_orca_dedup_is_bit_identical); NOT the headline, which keeps the reference's two ORCA passes per step")
+        pruned = variant(orca_lookahead_prune=True)
+        pruned["what"] = ("EngineConfig(orca_lookahead_prune=True): the look-ahead pass solves only the humans whose future velocity the "
+                          "disturbance reward reads (within 1.5 m of the robot); same results bit for bit (tests/test_gpu_env.py::"
+                          "test_lookahead_prune_is_bit_identical); NOT the headline, which keeps the reference's two full ORCA passes per step")
 
     # ---------------- end to end through the host-buffer C-ABI call (closed loop through host memory) ----------------
     noise_h = noise[:8].cpu().numpy()
@@ -605,7 +612,7 @@ def run_env(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": DTYPE, "data": "synthetic", "config": workload_config(a), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "parity": parity, "roofline": roofline, "roofline_compute": roofline_compute,
-                "kernels_ms": kavg, "dedup_variant": dedup, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
+                "kernels_ms": kavg, "dedup_variant": dedup, "lookahead_prune_variant": pruned, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
                 "episode_stats": {n: int(cnt[i]) for i, n in enumerate(d.env.STAT_NAMES)}, "episode_stats_via": stats_via,
                 "reward_sums": [float(x) for x in sums[:3]]}
         _emit(line)

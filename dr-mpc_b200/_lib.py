@@ -47,7 +47,7 @@ class EnvConfig(ctypes.Structure):
                 ("corridor_penalty", c_d), ("corridor_max_dev", c_d), ("end_of_path_penalty", c_d),
                 ("safety_corridor_penalty", c_d), ("safety_corridor_max_dev", c_d),
                 ("lookahead", c_i32), ("lookbehind", c_i32), ("mpc_actions_in_input", c_i32), ("auto_path_switch", c_i32),
-                ("soft_reset_on_device", c_i32), ("orca_dedup", c_i32), ("sensor_restriction", c_i32), ("sensor_range", c_d), ("num_static_humans", c_i32), ("static_pos", c_d * 8), ("seed", c_u64), ("env_id_offset", c_i64)]
+                ("soft_reset_on_device", c_i32), ("orca_dedup", c_i32), ("orca_lookahead_prune", c_i32), ("sensor_restriction", c_i32), ("sensor_range", c_d), ("num_static_humans", c_i32), ("static_pos", c_d * 8), ("seed", c_u64), ("env_id_offset", c_i64)]
 
 
 class EnvStateView(ctypes.Structure):

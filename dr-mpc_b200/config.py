@@ -65,6 +65,7 @@ class EngineConfig:
     auto_path_switch: bool = True
     soft_reset_on_device: bool = False   # run HAAndPTEnv.soft_reset as a per-env state machine inside step()
     orca_dedup: bool = False             # reuse step t's look-ahead ORCA pass as step t+1's movement pass (bit-identical)
+    orca_lookahead_prune: bool = False   # look-ahead pass only for the humans the disturbance reward reads (bit-identical)
     robot_sensor_restriction: bool = False   # config_HA.robot.sensor_restriction ("TODO: if True, verify correctness" upstream)
     robot_sensor_range: float = 4.0          # config_HA.robot.sensor_range
     static_humans: tuple = ()            # ((x, y), ...) static obstacles = the LAST len(static_humans) of num_humans
@@ -130,7 +131,7 @@ class EngineConfig:
             self.path_advancement_scaling, self.deviation_xy, self.deviation_th, self.deviation_scale,
             self.corridor_penalty, self.corridor_max_dev, self.end_of_path_penalty, self.safety_corridor_penalty,
             self.safety_corridor_max_dev, self.lookahead, self.lookbehind, self.actions_in_input,
-            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), int(self.robot_sensor_restriction), float(self.robot_sensor_range),
+            int(self.auto_path_switch), int(self.soft_reset_on_device), int(self.orca_dedup), int(self.orca_lookahead_prune), int(self.robot_sensor_restriction), float(self.robot_sensor_range),
             len(self.static_humans),
             (ctypes.c_double * 8)(*([float(v) for xy in self.static_humans for v in xy] + [0.0] * (8 - 2 * len(self.static_humans)))),
             self.seed, self.env_id_offset)

@@ -232,7 +232,7 @@ extern "C" int dre_env_create(const dre_env_config *cfg, dre_env **out)
     D.corridor_max_dev = cfg->corridor_max_dev; D.eop_penalty = cfg->end_of_path_penalty;
     D.safety_corridor_penalty = cfg->safety_corridor_penalty; D.safety_corridor_max_dev = cfg->safety_corridor_max_dev;
     D.lookahead = cfg->lookahead; D.lookbehind = cfg->lookbehind; D.auto_path_switch = cfg->auto_path_switch;
-    D.soft_reset = cfg->soft_reset_on_device; D.orca_dedup = cfg->orca_dedup;
+    D.soft_reset = cfg->soft_reset_on_device; D.orca_dedup = cfg->orca_dedup; D.lookahead_prune = cfg->orca_lookahead_prune;
     D.sensor_restriction = cfg->sensor_restriction; D.sensor_range = cfg->sensor_range;
     D.num_static = cfg->num_static_humans;
     for (int i = 0; i < 8; ++i) D.static_pos[i] = cfg->static_pos[i];

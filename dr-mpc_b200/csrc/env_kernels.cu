@@ -48,10 +48,11 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
     return l;
 }
 
-template <int G, bool REUSE, bool CUTOFF>
+template <int G, bool REUSE, bool CUTOFF, bool PRUNE>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
-                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse, const int *flags)
+                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse, const int *flags,
+                               bool prune)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
@@ -70,6 +71,15 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
         if (flags[el * 4 + 2] == 0) continue;
         const size_t gidx = (size_t)e * Nh + i;
         float ox = 0.f, oy = 0.f;
+        if (PRUNE && prune) {
+            // look-ahead pass with lookahead_prune: the disturbance reward (human_avoidance_env.py:247-273) reads the future
+            // velocity only of humans within its radius of the robot; every other look-ahead solve is dead work (each ORCA
+            // solve is a pure function of the crowd state). Same expression as the reward loop below -> same decision.
+            const double2 P = posd[el * Nh + i];
+            const double ddx = P.x - D.rpose[(size_t)e * 4], ddy = P.y - D.rpose[(size_t)e * 4 + 1];
+            const double closest = sqrt(ddx * ddx + ddy * ddy) - D.human_radius - D.robot_radius;
+            if (closest > D.dist_radius || closest <= 0.0) { g.sync(); continue; }
+        }
         if (REUSE && reuse && D.cache_valid[e] && !D.goal_changed[gidx]) {
             // orca_dedup: this solve was done as the look-ahead pass of the previous step, on this very state
             const float2 c = D.hvel_next[gidx];
@@ -113,7 +123,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
 // mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
 // DEDUP: the orca_dedup variant (reuses the previous step's look-ahead pass); a separate instantiation so that the default
 // two-pass kernel carries none of its code
-template <int G, bool DEDUP, bool CUTOFF>
+template <int G, bool DEDUP, bool CUTOFF, bool PRUNE>
 __global__ void __launch_bounds__(512)
 ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_obs, const __grid_constant__ HaLayout lay)
 {
@@ -175,8 +185,8 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
         // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
         // instruction cache together)
-        orca_pass_tile<G, DEDUP, CUTOFF>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
-                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0, flags);
+        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
+                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0, flags, false);
         __syncthreads();
 
         DRE_HA_T(12);   // stage + pass 1
@@ -333,7 +343,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
 #ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
-        orca_pass_tile<G, DEDUP, CUTOFF>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags);
+        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags, PRUNE);
 #endif
         __syncthreads();
         if (DEDUP) {   // keep the look-ahead velocities: they are the next step's movement pass
@@ -924,7 +934,7 @@ int dre_env_ha_envs_per_cta(const EnvDev &D)
     return EPB < 1 ? 1 : EPB;
 }
 
-template <int G, bool DEDUP, bool CUTOFF>
+template <int G, bool DEDUP, bool CUTOFF, bool PRUNE>
 static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int Nh = D.Nh, nA = Nh + (D.orca.robot_visible ? 1 : 0);
@@ -939,7 +949,7 @@ static int launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
         if (pad < 0) { const char *e = getenv("DRE_HA_SMEM_PAD_KB"); pad = e ? atoi(e) : 0; }
         lay.bytes += (size_t)pad * 1024;
     }
-    auto kern = ha_step_kernel<G, DEDUP, CUTOFF>;
+    auto kern = ha_step_kernel<G, DEDUP, CUTOFF, PRUNE>;
     if (lay.bytes > 48 * 1024) {
         if (lay.bytes > 220 * 1024) return DRE_ERR_INVALID;
         DRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
@@ -953,13 +963,18 @@ int dre_env_launch_ha(const EnvDev &D, int mode, int write_obs, cudaStream_t s)
 {
     const int G = dre_env_pick_group(D);
     const bool cut = dre_orca_use_cutoff(D.orca);   // short neighbour range: cut-off + compaction before the ranking (orca_device.cuh)
-#define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true, false>(D, mode, write_obs, s) : (cut ? launch_ha<g, false, true>(D, mode, write_obs, s) : launch_ha<g, false, false>(D, mode, write_obs, s))
+    // kernel variants (one instantiation each, so the default two-pass kernel carries none of the others' code):
+    // dedup | look-ahead pruning (+ cut-off) | cut-off | default
+#define DRE_HA_CASE(g) case g: return D.orca_dedup ? launch_ha<g, true, false, false>(D, mode, write_obs, s) \
+                                   : D.lookahead_prune ? (cut ? launch_ha<g, false, true, true>(D, mode, write_obs, s) : launch_ha<g, false, false, true>(D, mode, write_obs, s)) \
+                                   : (cut ? launch_ha<g, false, true, false>(D, mode, write_obs, s) : launch_ha<g, false, false, false>(D, mode, write_obs, s))
     switch (G) {
     DRE_HA_CASE(2);
     DRE_HA_CASE(4);
     DRE_HA_CASE(8);
     DRE_HA_CASE(16);
-    default: return D.orca_dedup ? launch_ha<32, true, false>(D, mode, write_obs, s) : (cut ? launch_ha<32, false, true>(D, mode, write_obs, s) : launch_ha<32, false, false>(D, mode, write_obs, s));
+    default:
+    DRE_HA_CASE(32);
     }
 #undef DRE_HA_CASE
 }

@@ -22,7 +22,7 @@ struct EnvDev {
     double collision_penalty, safety_dist, safety_penalty, dist_radius, dist_factor_v, dist_factor_th, act_min_vel, act_penalty;
     double pt_overall_scaling, goal_radius, goal_angle, goal_reward, path_adv_scaling, dev_xy, dev_th, dev_scale;
     double corridor_penalty, corridor_max_dev, eop_penalty, safety_corridor_penalty, safety_corridor_max_dev;
-    int lookahead, lookbehind, auto_path_switch, soft_reset, orca_dedup;
+    int lookahead, lookbehind, auto_path_switch, soft_reset, orca_dedup, lookahead_prune;
     int sensor_restriction;
     double sensor_range;
     int num_static;

@@ -167,6 +167,11 @@ typedef struct dre_env_config {
                                                     (:181-184); those humans are solved again. Bit-identical results, one
                                                     ORCA pass per step instead of two. Writers of the state views must call
                                                     dre_env_invalidate_orca_cache(). Default 0 = two passes like the reference */
+    int32_t orca_lookahead_prune;                /* 1: the look-ahead ORCA pass (human_avoidance_env.py:245) solves only the humans whose
+                                                    future velocity the disturbance reward reads (:247-252: within its radius of
+                                                    the robot, not colliding); the other look-ahead solves are dead work. Bit-
+                                                    identical results. Ignored with orca_dedup (which needs the whole pass).
+                                                    Default 0 = the whole second pass like the reference */
     int32_t sensor_restriction;                  /* config_HA.robot.sensor_restriction (False): humans farther than sensor_range
                                                     from the robot lose their history (human_avoidance_env.py:102-105,161-164,
                                                     331-334) and the observation lists the visible ones first (:53-72)     */

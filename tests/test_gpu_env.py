@@ -316,3 +316,26 @@ def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
             checked += E; lp_div += int((~same).sum())
     print(f"E={E} Nh={Nh}: {checked} transitions vs oracle, LM-branch divergences {lp_div}, goals resampled {resampled}")
     assert lp_div <= 0.02 * checked and (resampled > 0 or variant.get("end_goal_changing") is False)
+
+
+def test_lookahead_prune_is_bit_identical():
+    """orca_lookahead_prune solves, in the look-ahead ORCA pass (human_avoidance_env.py:245), only the humans whose future
+    velocity the disturbance reward reads (:247-252); every state array and every output of a free-running batch must equal
+    the two-full-pass engine's bit for bit, dense start and goal resamplings included."""
+    import torch
+    import dr_mpc_b200 as d
+    E, Nh = 2048, 20
+    a_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E)
+    b_env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, orca_lookahead_prune=True), num_envs=E)
+    Sa = a_env.reset(); Sb = b_env.reset()
+    disturbed = 0
+    for t in range(60):
+        act = Sa['PT']['MPC_actions'][:, :2].clone()
+        Sa, Ra, *_ = a_env.step(act)
+        Sb, Rb, *_ = b_env.step(act)
+        for k in a_env.out:
+            assert torch.equal(a_env.out[k], b_env.out[k]), (t, k)
+        for k in ("hpos", "hvel", "hgoal", "hhist", "rpose", "path_idx"):
+            assert torch.equal(a_env.state[k], b_env.state[k]), (t, k)
+        disturbed += int((a_env.out["info"][:, 0] != 0).sum())
+    assert disturbed > 1000          # the disturbance reward was exercised

@@ -17,7 +17,7 @@ out = {"tag": tag}
 
 
 def make():
-    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh), num_envs=E)
+    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, group_lanes=int(os.environ.get('PROBE_G', 0)), orca_lookahead_prune=bool(int(os.environ.get('PROBE_PRUNE', 0))), orca_dedup=bool(int(os.environ.get('PROBE_DEDUP', 0)))), num_envs=E)
     env.reset()
     return env, env.out["mpc_actions"][:, :2].clone(), [0]
 
@@ -44,6 +44,8 @@ for rep in range(3):
 out["driver_window_ms"] = vals
 print(tag, "driver window (5+20 steps after reset) ms/step:", ["%.4f" % v for v in vals], "-> %.2f M env-steps/s" % (E / min(vals) * 1e-3), flush=True)
 
+if os.environ.get('PROBE_ONLY_WINDOW'):
+    sys.exit(0)
 # (2) per-kernel windows
 env, act, t = make()
 env.set_profiling(True)

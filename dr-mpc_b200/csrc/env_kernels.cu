@@ -123,8 +123,16 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
 // mode: 0 = full step, 1 = warm-start step (robot frozen, no rewards, no second pass), 2 = observation only
 // DEDUP: the orca_dedup variant (reuses the previous step's look-ahead pass); a separate instantiation so that the default
 // two-pass kernel carries none of its code
+// 128-thread CTAs, register target for 9 resident CTAs per SM (56 registers, 24 B of spills). Measured on B200 at 16384 x 20
+// (driver window / sparse-crowd ha_step): 7 CTAs 72 regs 1.047 / 0.587 ms, 8 CTAs 64 regs 1.045 / 0.582, 9 CTAs 56 regs
+// 1.016 / 0.572, 10 CTAs 48 regs 1.016 / 0.569 (but the 50-human ORCA-only step 1.58 vs 1.49 ms); the unconstrained
+// __launch_bounds__(512) this kernel had before also landed on 64 registers, with spills: 1.057 / 0.592.
+#ifndef DRE_HA_MINB
+#define DRE_HA_MINB 9
+#endif
+#define DRE_HA_BOUNDS 128, DRE_HA_MINB
 template <int G, bool DEDUP, bool CUTOFF, bool PRUNE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(DRE_HA_BOUNDS)
 ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_obs, const __grid_constant__ HaLayout lay)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -907,7 +915,7 @@ int dre_env_launch_cvmm(const EnvDev &D, const double *actions, int num_steps, c
 static int dre_ha_threads()
 {
     static int v = 0;
-    if (v == 0) { const char *e = getenv("DRE_HA_THREADS"); v = e ? atoi(e) : 128; if (v != 64 && v != 128 && v != 256 && v != 512) v = 128; }
+    if (v == 0) { const char *e = getenv("DRE_HA_THREADS"); v = e ? atoi(e) : 128; if (v != 64 && v != 128) v = 128; }   // the kernel is bounded to 128 threads
     return v;
 }
 static int dre_ha_agents_per_group()

@@ -27,7 +27,7 @@ static OrcaTileLayout orca_layout(int Nh, int robot_visible, int G, int threads,
 }
 
 template <int G, bool CUTOFF>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(128, 9)
 orca_predict_kernel(dre_orca_params p, int E, int Nh, int EPB, const double2 *__restrict__ hpos,
                     const float2 *__restrict__ hvel, const double2 *__restrict__ goal,
                     const double2 *__restrict__ rpos, const uint8_t *__restrict__ is_static,
@@ -114,7 +114,7 @@ static int launch_orca(const dre_orca_params &p, int E, int Nh, const double *hp
     static int threads = 0, apg = 0;
     if (threads == 0) {
         const char *e = getenv("DRE_ORCA_THREADS"); threads = e ? atoi(e) : 128;
-        if (threads != 64 && threads != 128 && threads != 256 && threads != 512) threads = 128;
+        if (threads != 64 && threads != 128) threads = 128;   // the kernel is bounded to 128 threads
         e = getenv("DRE_ORCA_AGENTS_PER_GROUP"); apg = e ? atoi(e) : 8;
         if (apg < 1 || apg > 64) apg = 8;
     }

@@ -173,5 +173,5 @@ def test_host_output_modes():
         for m in ("f32", "ctl"):
             assert torch.equal(envs[m].out["spatial_edges"], envs["full"].out["spatial_edges"])
         act = v["full"]["mpc_actions"][:, :2].copy()
-    assert envs["f32"].host_bytes_per_step < 0.65 * envs["full"].host_bytes_per_step and envs["ctl"].host_bytes_per_step < 0.05 * envs["full"].host_bytes_per_step
+    assert envs["f32"].host_bytes_per_step < 0.65 * envs["full"].host_bytes_per_step and envs["ctl"].host_bytes_per_step < 0.15 * envs["full"].host_bytes_per_step
     assert envs["full"].d2h_ceiling_ms(reps=3) > 0

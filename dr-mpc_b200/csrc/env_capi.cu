@@ -150,6 +150,7 @@ void carve_state(EnvDev &D, void *base, size_t &bytes)
     D.hvel_next = c.take<float2>(E * Nh);
     D.goal_changed = c.take<uint8_t>(E * Nh);
     D.cache_valid = c.take<uint8_t>(E);
+    D.lp_class = c.take<uint8_t>(E * Nh);
     D.stat_counters = c.take<unsigned long long>(16);
     D.stat_sums = c.take<double>(4);
     bytes = (c.off + 255) / 256 * 256;

@@ -29,7 +29,7 @@
 // shared-memory layout of ha_step_kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct HaLayout {
-    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, bytes;
+    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, off_order, bytes;
 };
 static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
 {
@@ -42,8 +42,9 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
     l.off_agents = seg((size_t)EPB * 5 * nA * sizeof(float));
     l.off_dist = seg((size_t)NG * (cutoff ? 2 : 1) * ((nA + 3) & ~3) * sizeof(float));   // squared distances (+ the agent indices of the compacted ones)
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
-    l.off_flags = seg((size_t)(EPB * 4 + 2) * sizeof(int));   // per-env flags + the two ORCA work counters
+    l.off_flags = seg((size_t)(EPB * 4 + 3) * sizeof(int));   // per-env flags + the two ORCA work counters + the CTA's LP3 count
     l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
+    l.off_order = seg((size_t)EPB * Nh * (sizeof(uint16_t) + 1) + 2 * sizeof(int));   // agent queue order, solve classes, 2 fill counters
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -51,8 +52,8 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
 template <int G, bool REUSE, bool CUTOFF, bool PRUNE>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
-                               bool pos_from_smem, unsigned long long *lp3_count, int *work_counter, bool reuse, const int *flags,
-                               bool prune)
+                               bool pos_from_smem, int *lp3_count, int *work_counter, bool reuse, const int *flags,
+                               bool prune, const uint16_t *order, uint8_t *cls_out)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
@@ -67,6 +68,7 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
         if (g.rank() == 0) ag = atomicAdd(work_counter, 1);
         ag = g.bcast(ag, 0);
         if (ag >= EPB * Nh) break;
+        ag = order[ag];                 // expensive (LP3) solves first: see ha_build_order
         const int el = ag / Nh, i = ag - el * Nh, e = env0 + el;
         if (flags[el * 4 + 2] == 0) continue;
         const size_t gidx = (size_t)e * Nh + i;
@@ -93,14 +95,30 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
             if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
             const float *A = agents + (size_t)el * 5 * nA;
             dre_orca_stats st;
-            orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+            const bool hard = orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
                              D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              lp3_count ? &st : nullptr);
-            if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1ull);
+            if (g.rank() == 0) cls_out[ag] = hard ? 1 : 0;
+            if (lp3_count && g.rank() == 0 && hard) atomicAdd(lp3_count, 1);   // shared memory; one global atomic per CTA
         }
         if (g.rank() == 0) vout[el * Nh + i] = make_float2(ox, oy);
         g.sync();
     }
+}
+
+// Queue order of a pass: the agents whose last solve needed linearProgram3 (2-3x the cost of an LP2-only solve) go first,
+// the cheap ones fill the tail (longest-processing-time-first), and the lane-groups of a warp tend to be on the same class
+// of solve at the same time. The class of an agent's previous solve predicts the next one almost always (the look-ahead
+// pass of step t-1 and the movement pass of step t see the same crowd). Order only: results do not depend on it.
+__device__ __forceinline__ void ha_build_order(uint16_t *order, const uint8_t *cls, int n, int *fill /*[2], zeroed here*/)
+{
+    if (threadIdx.x < 2) fill[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int pos = cls[t] ? atomicAdd(&fill[0], 1) : n - 1 - atomicAdd(&fill[1], 1);
+        order[pos] = (uint16_t)t;
+    }
+    __syncthreads();
 }
 
 // -DDRE_HA_TRACE: thread 0 of every CTA adds the cycles it spent in each phase to stat_counters[12..15] + stat_sums
@@ -145,6 +163,9 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     float *dist = reinterpret_cast<float *>(smem_raw + lay.off_dist);
     float2 *vnew = reinterpret_cast<float2 *>(smem_raw + lay.off_vnew);
     int *flags = reinterpret_cast<int *>(smem_raw + lay.off_flags);
+    uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + lay.off_order);
+    int *fill = reinterpret_cast<int *>(smem_raw + lay.off_order + (((size_t)EPB * D.Nh * sizeof(uint16_t) + 3) & ~(size_t)3));
+    uint8_t *cls = reinterpret_cast<uint8_t *>(fill + 2);
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(smem_raw + lay.off_stats);   // [9]
     double *s_sum = reinterpret_cast<double *>(s_cnt + 9);                                            // [3]
     const int env0 = blockIdx.x * EPB;
@@ -159,7 +180,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
 
     // per-env flags: [0] a goal was reached, [1] visible humans (sensor restriction), [2] the env takes part in this launch
     // (in range and selected by the mask of a masked reset / observe), [3] spare; then the two ORCA work counters
-    for (int t = threadIdx.x; t < EPB * 4 + 2; t += blockDim.x) {
+    for (int t = threadIdx.x; t < EPB * 4 + 3; t += blockDim.x) {
         int v = 0;
         if (t < EPB * 4 && (t & 3) == 2) { const int e = env0 + (t >> 2); v = e < D.E && (D.env_mask == nullptr || D.env_mask[e] != 0); }
         flags[t] = v;
@@ -190,12 +211,23 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         }
         __syncthreads();
 
+        // the previous solve's class of every agent of this CTA (global state) -> queue order of pass 1
+        for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
+            const int e = env0 + t / Nh;
+            cls[t] = e < D.E ? D.lp_class[(size_t)env0 * Nh + t] : 0;
+        }
+        __syncthreads();
+        ha_build_order(order, cls, EPB * Nh, fill);
         // ---- ORCA pass 1: the humans' actions (human_avoidance_env.py:129 / :84) ----
         // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
         // instruction cache together)
         orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
-                                 D.stat_counters ? D.stat_counters + 11 : nullptr, &flags[EPB * 4], mode == 0, flags, false);
+                                 D.stat_counters ? &flags[EPB * 4 + 2] : nullptr, &flags[EPB * 4], mode == 0, flags, false, order, cls);
         __syncthreads();
+        if (threadIdx.x == 0 && D.stat_counters && flags[EPB * 4 + 2]) atomicAdd(D.stat_counters + 11, (unsigned long long)flags[EPB * 4 + 2]);
+        if (mode == 1)   // no look-ahead pass in a warm-start step: these classes order the next pass
+            for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x)
+                if (env0 + t / Nh < D.E) D.lp_class[(size_t)env0 * Nh + t] = cls[t];
 
         DRE_HA_T(12);   // stage + pass 1
         // ---- integrate: robot (unicycle, agent.py:169-176) and humans (Euler, agent.py:164-168); histories ----
@@ -350,10 +382,13 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     if (mode == 0) {
         // ---- ORCA pass 2 on the moved crowd: what the humans will do next (human_avoidance_env.py:245) ----
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
+        ha_build_order(order, cls, EPB * Nh, fill);   // from the classes pass 1 has just produced
 #ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
-        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags, PRUNE);
+        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags, PRUNE, order, cls);
 #endif
         __syncthreads();
+        for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x)   // the classes of the latest solves order the next step's pass 1
+            if (env0 + t / Nh < D.E) D.lp_class[(size_t)env0 * Nh + t] = cls[t];
         if (DEDUP) {   // keep the look-ahead velocities: they are the next step's movement pass
             for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
                 const int el = t / Nh, i = t - el * Nh, e = env0 + el;
@@ -781,6 +816,7 @@ __global__ void __launch_bounds__(128) env_reset_kernel(EnvDev D, const double2 
         D.hgoal[gidx] = make_double2(gx, gy);
         D.hvel[gidx] = make_float2(0.f, 0.f);
         D.hstatic[gidx] = si >= 0 ? 1 : 0;
+        D.lp_class[gidx] = 0;
         int v0 = 1;
         if (D.sensor_restriction) {   // human_avoidance_env.py:331-334
             double st, ct;

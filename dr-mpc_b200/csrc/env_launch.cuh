@@ -52,6 +52,7 @@ struct EnvDev {
     float2 *hvel_next;      // [E][Nh] orca_dedup: look-ahead velocities of the last step (= next step's movement pass)
     uint8_t *goal_changed;  // [E][Nh] orca_dedup: goal resampled since hvel_next was computed
     uint8_t *cache_valid;   // [E]     orca_dedup: hvel_next belongs to the current state
+    uint8_t *lp_class;      // [E][Nh] 1 = the human's latest ORCA solve needed linearProgram3 (queue order of the next pass)
     // ---- paths ----
     const double *paths;
     const int32_t *lens;

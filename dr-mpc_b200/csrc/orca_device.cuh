@@ -411,7 +411,7 @@ DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine 
 // with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
 // solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
 template <bool CUTOFF = false, class Grp, class DistT, class LinesT>
-DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+DRE_HD bool orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
                              int maxNeighbors, float invTH, float invDt, DistT sdist, DistT sidx, LinesT L, float &outx, float &outy,
                              dre_orca_stats *st, bool debug_skip_lp3 = false)
@@ -475,6 +475,7 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
         cl = P; cm = pc; cox = -li3.dy; coy = li3.dx; dirOpt = true;
     }
     outx = rx; outy = ry;
+    const bool needed_lp3 = fail < m;
     if (st) {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) mask |= g.shfl_xor(mask, o);
@@ -483,4 +484,5 @@ DRE_HD void orca_solve_group(const Grp &g, int nA, const float *ax, const float 
             st->branch_mask = mask; st->n_lp3_proj = nproj;
         }
     }
+    return needed_lp3;   // linearProgram2 failed and linearProgram3 ran: the expensive class of solves
 }

@@ -44,7 +44,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
     l.off_vnew = seg((size_t)EPB * Nh * sizeof(float2));
     l.off_flags = seg((size_t)(EPB * 4 + 3) * sizeof(int));   // per-env flags + the two ORCA work counters + the CTA's LP3 count
     l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
-    l.off_order = seg((size_t)EPB * Nh * (sizeof(uint16_t) + 1) + 2 * sizeof(int));   // agent queue order, solve classes, 2 fill counters
+    l.off_order = seg((size_t)EPB * Nh * (sizeof(uint16_t) + 1) + 16 * sizeof(int) + 4);   // agent queue order, solve classes, sort counters
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -95,29 +95,34 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
             if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
             const float *A = agents + (size_t)el * 5 * nA;
             dre_orca_stats st;
-            const bool hard = orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
+            const int hard = orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
                              D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
                              lp3_count ? &st : nullptr);
-            if (g.rank() == 0) cls_out[ag] = hard ? 1 : 0;
-            if (lp3_count && g.rank() == 0 && hard) atomicAdd(lp3_count, 1);   // shared memory; one global atomic per CTA
+            if (g.rank() == 0) cls_out[ag] = (uint8_t)hard;
+            if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1);   // shared memory; one global atomic per CTA
         }
         if (g.rank() == 0) vout[el * Nh + i] = make_float2(ox, oy);
         g.sync();
     }
 }
 
-// Queue order of a pass: the agents whose last solve needed linearProgram3 (2-3x the cost of an LP2-only solve) go first,
-// the cheap ones fill the tail (longest-processing-time-first), and the lane-groups of a warp tend to be on the same class
-// of solve at the same time. The class of an agent's previous solve predicts the next one almost always (the look-ahead
+// Queue order of a pass: agents sorted by the cost class of their previous solve, most expensive first (a solve that needs
+// linearProgram3 costs 2-3x an LP2-only one): the cheap ones fill the tail (longest-processing-time-first) and the
+// lane-groups of a warp tend to be on the same class of solve at the same time. The class of an agent's previous solve predicts the next one almost always (the look-ahead
 // pass of step t-1 and the movement pass of step t see the same crowd). Order only: results do not depend on it.
-__device__ __forceinline__ void ha_build_order(uint16_t *order, const uint8_t *cls, int n, int *fill /*[2], zeroed here*/)
+__device__ __forceinline__ void ha_build_order(uint16_t *order, const uint8_t *cls, int n, int *fill /*[16]*/)
 {
-    if (threadIdx.x < 2) fill[threadIdx.x] = 0;
+    // counting sort by descending class (8 classes): count, prefix, place
+    if (threadIdx.x < 16) fill[threadIdx.x] = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int pos = cls[t] ? atomicAdd(&fill[0], 1) : n - 1 - atomicAdd(&fill[1], 1);
-        order[pos] = (uint16_t)t;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) atomicAdd(&fill[cls[t] & 7], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int base = 0;
+        for (int c = 7; c >= 0; --c) { fill[8 + c] = base; base += fill[c]; }
     }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) order[atomicAdd(&fill[8 + (cls[t] & 7)], 1)] = (uint16_t)t;
     __syncthreads();
 }
 
@@ -165,7 +170,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     int *flags = reinterpret_cast<int *>(smem_raw + lay.off_flags);
     uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + lay.off_order);
     int *fill = reinterpret_cast<int *>(smem_raw + lay.off_order + (((size_t)EPB * D.Nh * sizeof(uint16_t) + 3) & ~(size_t)3));
-    uint8_t *cls = reinterpret_cast<uint8_t *>(fill + 2);
+    uint8_t *cls = reinterpret_cast<uint8_t *>(fill + 16);
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(smem_raw + lay.off_stats);   // [9]
     double *s_sum = reinterpret_cast<double *>(s_cnt + 9);                                            // [3]
     const int env0 = blockIdx.x * EPB;

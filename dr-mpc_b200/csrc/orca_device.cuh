@@ -411,7 +411,7 @@ DRE_HD int orca_project_lines(const Grp &g, const LinesT &L, int i, const OLine 
 // with the lines projected onto line i and the direction objective (linearProgram3). One copy of LP2/LP1 keeps the
 // solve inside the instruction cache (the two-copy version stalled 23 % of its cycles on instruction fetch).
 template <bool CUTOFF = false, class Grp, class DistT, class LinesT>
-DRE_HD bool orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
+DRE_HD int orca_solve_group(const Grp &g, int nA, const float *ax, const float *ay, const float *avx, const float *avy,
                              const float *ar, int self, float prefx, float prefy, float maxSpeed, float neighborDist,
                              int maxNeighbors, float invTH, float invDt, DistT sdist, DistT sidx, LinesT L, float &outx, float &outy,
                              dre_orca_stats *st, bool debug_skip_lp3 = false)
@@ -475,7 +475,11 @@ DRE_HD bool orca_solve_group(const Grp &g, int nA, const float *ax, const float 
         cl = P; cm = pc; cox = -li3.dy; coy = li3.dx; dirOpt = true;
     }
     outx = rx; outy = ry;
-    const bool needed_lp3 = fail < m;
+    // cost class of this solve (0..7) for the queue order of the next pass: 0..3 = linearProgram2 sufficed, by the number of
+    // linearProgram1 calls (0-1, 2-3, 4-5, 6+); 4..7 = linearProgram3 ran, by its number of projections (1, 2, 3, 4+).
+    // (Measured on B200, dense post-reset window of 16384 x 20: 2 classes 0.945 ms, 4 classes 0.926, these 8 0.903; a
+    // 16-class running work estimate updated inside the LP loops 0.927: the bookkeeping costs more than it orders.)
+    const int cost_class = fail < m ? 4 + (nproj > 4 ? 3 : nproj - 1) : (n_lp1 > 7 ? 3 : n_lp1 >> 1);
     if (st) {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) mask |= g.shfl_xor(mask, o);
@@ -484,5 +488,5 @@ DRE_HD bool orca_solve_group(const Grp &g, int nA, const float *ax, const float 
             st->branch_mask = mask; st->n_lp3_proj = nproj;
         }
     }
-    return needed_lp3;   // linearProgram2 failed and linearProgram3 ran: the expensive class of solves
+    return cost_class;
 }

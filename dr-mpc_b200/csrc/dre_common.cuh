@@ -12,6 +12,12 @@
 #define DRE_D inline
 #endif
 
+#if defined(__CUDACC__)
+#define DRE_ALIGN16 __align__(16)
+#else
+#define DRE_ALIGN16 alignas(16)
+#endif
+
 #define DRE_RVO_EPSILON 0.00001f
 #define DRE_PI 3.14159265358979323846
 

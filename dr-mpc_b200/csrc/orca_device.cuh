@@ -73,7 +73,9 @@ struct SerialGroup {
                            // Measured on B200 at 16384 x 20: 4 -> 1 takes ha_step from 0.607 to 0.592 ms (sparse crowd) and the step
                            // of the dense first 25 steps after a reset from 1.091 to 1.057 ms; 0 and 2 are in between, 8 is slower
 #endif
-struct OLine { float px, py, dx, dy; };   // point, direction (16 B, float4-compatible)
+struct DRE_ALIGN16 OLine { float px, py, dx, dy; };   // point, direction: 16 B, 16 B-aligned so that a line moves as ONE 128-bit
+                                                      // shared-memory access (a quarter-warp = one lane-group of 8 then touches 128 contiguous bytes: no bank conflicts;
+                                                      // as two 64-bit halves the groups of a warp collided: 44 M excess wavefronts per launch, ncu r2)
 
 // Scratch accessors. The lane-group kernels give every group contiguous arrays (plain pointers); the thread-per-agent
 // kernel interleaves its threads' arrays (element i of thread t at base[i * stride + t]: conflict-free 16 B accesses).

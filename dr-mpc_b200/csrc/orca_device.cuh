@@ -25,6 +25,7 @@ struct TileGroup {
     __device__ unsigned ballot(bool p) const { return t.ballot(p); }
     __device__ bool any(bool p) const { return t.any(p); }
     __device__ float shfl_xor(float v, int m) const { return t.shfl_xor(v, m); }
+    __device__ int shfl_xor(int v, int m) const { return t.shfl_xor(v, m); }
     __device__ unsigned shfl_xor(unsigned v, int m) const { return t.shfl_xor(v, m); }
     __device__ int bcast(int v, int src) const { return t.shfl(v, src); }
     __device__ void sync() const { t.sync(); }
@@ -35,8 +36,22 @@ struct TileGroup {
     }
     // group-wide reductions in one REDUX instruction (sm_100a has the fp32 min/max forms; min/max are exact, so the
     // result equals the sequential scan bit for bit)
-    __device__ int min_int(int v) const { return __reduce_min_sync(lane_mask(), v); }
-    __device__ int sum_int(int v) const { return __reduce_add_sync(lane_mask(), v); }
+    // Integer min / sum over the group: log2(G) butterfly shuffles. (REDUX.MIN / REDUX.ADD with a sub-warp member mask take a
+    // slow path when the warp's groups are on different iterations -- 9 % of ha_step's stall samples sat on them, half
+    // branch_resolving; measured on B200: shuffles take the dense-window step from 0.888 to 0.854 ms.) The fp32 min / max
+    // of linearProgram1 stay on redux.sync.{min,max}.f32: shuffles measured the same there.
+    __device__ int min_int(int v) const
+    {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) { const int w = t.shfl_xor(v, o); v = w < v ? w : v; }
+        return v;
+    }
+    __device__ int sum_int(int v) const
+    {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += t.shfl_xor(v, o);
+        return v;
+    }
     __device__ float min_f32(float v) const
     {
         float r;

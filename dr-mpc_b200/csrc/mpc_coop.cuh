@@ -27,7 +27,9 @@
 
 #if defined(__CUDACC__)
 
+#ifndef DRE_MPC_CTA
 #define DRE_MPC_CTA 128   // threads per CTA of the cooperative kernel (shared-memory columns are strided by this)
+#endif
 
 template <int G>
 struct LaneGroup {

@@ -15,7 +15,7 @@
 // MINB = minimum resident CTAs per SM the register allocation is capped for. The linearisation lives in shared memory
 // (mpc_coop.cuh), which lets 3 CTAs = 12 warps per SM hide the fp64 dependency chains without spills.
 template <int G, int MINB, bool TRACE = false>
-__global__ void __launch_bounds__(128, MINB)
+__global__ void __launch_bounds__(DRE_MPC_CTA, MINB * (128 / DRE_MPC_CTA))
 mpc_coop_kernel(dre_mpc_params prm, CoopBatch B)
 {
     extern __shared__ __align__(16) double coop_smem[];   // CS_SLOTS columns of DRE_MPC_CTA doubles

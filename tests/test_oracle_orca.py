@@ -59,3 +59,36 @@ def test_lp3_overshoot_is_reference_behaviour(oracle):
 def test_single_agent_moves_to_goal(oracle):
     v, st = oracle.orca_solve([0, 0, 0, 0, 0.6, 0.8, 0.485, 1.0], np.zeros((0, 5)))
     assert np.allclose(v, [0.6, 0.8]) and st["n_lines"] == 0
+
+
+def test_instrumented_oracle_counts_and_agrees(oracle, golden_orca):
+    """oracle/opcount: the flat oracle compiled UNCHANGED with instrumented scalar types (the source of bench.py's
+    algorithmic flop figures, profiles/roofline.json). The instrumentation must not change a bit of the results, and the
+    count per ORCA solve must sit where the survey's formula 53 n + sum(10 i + 20) puts it."""
+    import ctypes
+    import os
+    import subprocess
+    from conftest import REPO
+    d = os.path.join(REPO, "oracle", "opcount")
+    subprocess.check_call(["make", "-C", d, "-B", "libopcount.so"], stdout=subprocess.DEVNULL)
+    cnt = ctypes.CDLL(os.path.join(d, "libopcount.so"))
+    key = "n20_s5.0"
+    hpos, hvel, goal, rpos, vnew = (golden_orca[f"{key}_{k}"] for k in ("hpos", "hvel", "goal", "rpos", "vnew"))
+    fast = oracle.lib()
+    try:
+        oracle._lib = cnt
+        cnt.opcount_reset()
+        v, st = oracle.orca_crowd_pass(hpos, hvel, goal, rpos, nthreads=1, want_stats=True)
+        ops = (ctypes.c_uint64 * 8)()
+        cnt.opcount_get(ops)
+    finally:
+        oracle._lib = fast
+    assert np.array_equal(v.view(np.uint32), vnew.view(np.uint32))
+    n = hpos.shape[0] * hpos.shape[1]
+    flops = sum(list(ops)[:6]) / n
+    formula = 53.0 * 20 + 10.0 * st["lp1_work"].mean() + 20.0 * st["n_lp1"].mean()
+    print(f"counted {flops:.0f} flops per solve, survey formula {formula:.0f}")
+    assert 0.7 * formula < flops < 1.5 * formula
+    import json
+    rj = json.load(open(os.path.join(REPO, "profiles", "roofline.json")))
+    assert {"n6", "n10", "n20", "n50"} <= set(rj["orca"]) and {"K4", "K10", "K20", "K30", "K40"} <= set(rj["mpc"])

@@ -263,7 +263,9 @@ def test_training_loop_skeleton_with_replay_soft_reset_and_cvmm():
 @pytest.mark.parametrize("E,Nh,variant", [(2048, 20, {}), (1024, 10, {}), (256, 50, {}),
                                           (512, 12, {"robot_visible": False}), (512, 8, {"end_goal_changing": False}),
                                           (512, 8, {"auto_path_switch": False}), (384, 16, {"neighbor_dist": 3.0}),
-                                          (256, 6, {"horizon": 10}), (192, 6, {"horizon": 40})])
+                                          (256, 6, {"horizon": 10}), (192, 6, {"horizon": 40}),
+                                          (1024, 10, {"soft_reset_on_device": True}), (1024, 6, {"soft_reset_on_device": True, "static_humans": ((-4.0, 0.0), (0.0, 0.0))}),
+                                          (512, 10, {"robot_sensor_restriction": True}), (512, 8, {"static_humans": ((-4.0, 0.0), (0.0, 0.0))})])
 def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
     """CUDA env step vs the CPU oracle (oracle/env_ref.c) on thousands of states the free-running engine itself reaches
     (dense and sparse crowds, goal resampling by the shared Philox streams, path switches): the device state is copied into
@@ -276,20 +278,24 @@ def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
     env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, **variant), num_envs=E)
     S = env.reset()
     ov = dict(variant)
-    ref_kw = {k: ov.pop(k) for k in ("auto_path_switch", "end_goal_changing", "neighbor_dist") if k in ov}
+    ref_kw = {k: ov.pop(k) for k in ("auto_path_switch", "end_goal_changing", "neighbor_dist", "static_humans") if k in ov}
     if "horizon" in ov: ref_kw["K"] = ov.pop("horizon")
+    if "soft_reset_on_device" in ov: ref_kw["soft_reset"] = ov.pop("soft_reset_on_device")     # HAAndPTEnv.soft_reset inside step()
+    if "robot_sensor_restriction" in ov: ref_kw["sensor_restriction"] = ov.pop("robot_sensor_restriction")
     ref = oracle.EnvRef(E, Nh, tab, lens, **ref_kw, **{k: int(v) for k, v in ov.items()})
     ref.reset()
     gen = torch.Generator(device=env.device).manual_seed(7)
-    checked = lp_div = resampled = 0
-    for t in range(60):
+    checked = lp_div = resampled = scripted = 0
+    steps = 120 if variant.get("soft_reset_on_device") else 60     # recoveries (waits, back-ups, turns) need a while to show up
+    for t in range(steps):
         a = S['PT']['MPC_actions'][:, :2] + torch.randn((E, 2), generator=gen, device=env.device, dtype=torch.float64) * 0.15
         a[:, 0].clamp_(0, 1); a[:, 1].clamp_(-1, 1)
         if t % 6 == 3:
             torch.cuda.synchronize()
             for k in ("hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime",
-                      "path_idx", "loc_to_start", "step_count"):
+                      "path_idx", "loc_to_start", "step_count", "sr_state"):
                 ref.a[k][...] = env.state[k].cpu().numpy().reshape(ref.a[k].shape)
+            ref.a["done_bits"][...] = env.out["done_bits"].cpu().numpy().view(np.uint32)   # the previous step's done word drives the soft-reset machine
             ref.a["reset_epoch"][...] = 1
             pre_goal = ref.a["hgoal"].copy()
             T, u, it0 = env.mpc_get_warm()
@@ -306,6 +312,11 @@ def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
             resampled += int((r["hgoal"] != pre_goal).any(-1).sum())
             assert np.abs(st["rpose"][:, :3] - r["rpose"][:, :3]).max() <= 1e-12 and np.array_equal(st["path_idx"], r["path_idx"])
             assert np.array_equal(o["done_bits"].view(np.uint32), r["done_bits"])
+            assert np.array_equal(o["actions_used"], r["actions_used"]), t                     # the caller's action, or the scripted one
+            if variant.get("soft_reset_on_device"):
+                assert np.array_equal(o["done_flags"][:, 12], r["soft_flags"][:, 0]) and np.array_equal(st["sr_state"], r["sr_state"]), t
+                scripted += int(r["soft_flags"][:, 0].sum())
+            assert np.array_equal(st["hvalid"], r["hvalid"]) and np.array_equal(o["detected_humans"], r["detected_humans"]), t
             assert np.abs(o["rewards"] - r["rewards"]).max() <= 1e-9
             for name in ("pt_state", "robot_node", "past_robot_vel", "spatial_edges", "human_valid"):
                 assert np.abs(o[name] - r[name].reshape(o[name].shape)).max() <= 1e-9, (t, name)
@@ -314,8 +325,10 @@ def test_step_matches_oracle_at_scale(oracle, golden_mpc, E, Nh, variant):
             du = np.abs(o["mpc_actions"] - r["mpc_actions"]).max(1)
             assert du[same].max() <= 1e-6
             checked += E; lp_div += int((~same).sum())
-    print(f"E={E} Nh={Nh}: {checked} transitions vs oracle, LM-branch divergences {lp_div}, goals resampled {resampled}")
+    print(f"E={E} Nh={Nh} {variant}: {checked} transitions vs oracle, LM-branch divergences {lp_div}, goals resampled {resampled}, scripted soft-reset steps {scripted}")
     assert lp_div <= 0.02 * checked and (resampled > 0 or variant.get("end_goal_changing") is False)
+    if variant.get("soft_reset_on_device"):
+        assert scripted > 50
 
 
 def test_lookahead_prune_is_bit_identical():

@@ -29,7 +29,7 @@
 // shared-memory layout of ha_step_kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct HaLayout {
-    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, off_order, bytes;
+    size_t off_lines, off_agents, off_dist, off_vnew, off_pos, off_pen, off_flags, off_stats, off_order, off_pref, bytes;
 };
 static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
 {
@@ -45,6 +45,7 @@ static HaLayout ha_layout(int Nh, int nA, int NG, int EPB, bool cutoff)
     l.off_flags = seg((size_t)(EPB * 4 + 3) * sizeof(int));   // per-env flags + the two ORCA work counters + the CTA's LP3 count
     l.off_stats = seg(12 * sizeof(unsigned long long));        // CTA-level episode statistics: 9 counters + 3 reward sums
     l.off_order = seg((size_t)EPB * Nh * (sizeof(uint16_t) + 1) + 16 * sizeof(int) + 4);   // agent queue order, solve classes, sort counters
+    l.off_pref = seg((size_t)EPB * Nh * (sizeof(float2) + 1));   // preferred velocities (fp32, like the Cython boundary) + static flags
     l.bytes = (o + 15) / 16 * 16;
     return l;
 }
@@ -53,7 +54,7 @@ template <int G, bool REUSE, bool CUTOFF, bool PRUNE>
 __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, int gi, int NG, int EPB, int env0, int nA,
                                const float *agents, OLine *lines, float *dist, float2 *vout, const double2 *posd,
                                bool pos_from_smem, int *lp3_count, int *work_counter, bool reuse, const int *flags,
-                               bool prune, const uint16_t *order, uint8_t *cls_out)
+                               bool prune, const uint16_t *order, uint8_t *cls_out, const float2 *pref, const uint8_t *sstat)
 {
     const int Nh = D.Nh;
     OLine *L = lines + (size_t)gi * 2 * nA;
@@ -86,24 +87,28 @@ __device__ __noinline__ void orca_pass_tile(const EnvDev &D, TileGroup<G> &g, in
             // orca_dedup: this solve was done as the look-ahead pass of the previous step, on this very state
             const float2 c = D.hvel_next[gidx];
             ox = c.x; oy = c.y;
-        } else if (!D.hstatic[gidx]) {
-            const double2 P = pos_from_smem ? posd[el * Nh + i] : D.hpos[gidx];
-            const double2 Gl = D.hgoal[gidx];
-            const double dx = Gl.x - P.x, dy = Gl.y - P.y;
-            const double speed = sqrt(dx * dx + dy * dy);
-            double pvx = dx, pvy = dy;
-            if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
+        } else if (!sstat[ag]) {
+            const float2 pv = pref[ag];   // computed for the whole tile at once (ha_pref_velocity), not per lane-group here
             const float *A = agents + (size_t)el * 5 * nA;
-            dre_orca_stats st;
-            const int hard = orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, (float)pvx, (float)pvy,
-                             D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy,
-                             lp3_count ? &st : nullptr);
+            const int hard = orca_solve_group<CUTOFF>(g, nA, A, A + nA, A + 2 * nA, A + 3 * nA, A + 4 * nA, i, pv.x, pv.y,
+                             D.orca.max_speed_self, D.orca.neighbor_dist, maxNb, invTH, invDt, sd, sd + nA4, L, ox, oy, nullptr);
             if (g.rank() == 0) cls_out[ag] = (uint8_t)hard;
-            if (lp3_count && g.rank() == 0 && st.lp2_fail < st.n_lines) atomicAdd(lp3_count, 1);   // shared memory; one global atomic per CTA
+            if (lp3_count && g.rank() == 0 && hard >= 4) atomicAdd(lp3_count, 1);   // shared memory; one global atomic per CTA
         }
         if (g.rank() == 0) vout[el * Nh + i] = make_float2(ox, oy);
         g.sync();
     }
+}
+
+// Preferred velocity of a human (orca.py:97-100): towards the goal, normalised only beyond 1 m; computed in fp64 like the
+// reference's numpy, then cast to fp32 like its Cython boundary.
+__device__ __forceinline__ float2 ha_pref_velocity(double2 P, double2 Gl)
+{
+    const double dx = Gl.x - P.x, dy = Gl.y - P.y;
+    const double speed = sqrt(dx * dx + dy * dy);
+    double pvx = dx, pvy = dy;
+    if (speed > 1.0) { pvx = dx / speed; pvy = dy / speed; }
+    return make_float2((float)pvx, (float)pvy);
 }
 
 // Queue order of a pass: agents sorted by the cost class of their previous solve, most expensive first (a solve that needs
@@ -168,6 +173,8 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
     float *dist = reinterpret_cast<float *>(smem_raw + lay.off_dist);
     float2 *vnew = reinterpret_cast<float2 *>(smem_raw + lay.off_vnew);
     int *flags = reinterpret_cast<int *>(smem_raw + lay.off_flags);
+    float2 *pref = reinterpret_cast<float2 *>(smem_raw + lay.off_pref);
+    uint8_t *sstat = reinterpret_cast<uint8_t *>(pref + (size_t)EPB * D.Nh);
     uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + lay.off_order);
     int *fill = reinterpret_cast<int *>(smem_raw + lay.off_order + (((size_t)EPB * D.Nh * sizeof(uint16_t) + 3) & ~(size_t)3));
     uint8_t *cls = reinterpret_cast<uint8_t *>(fill + 16);
@@ -219,7 +226,11 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // the previous solve's class of every agent of this CTA (global state) -> queue order of pass 1
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x) {
             const int e = env0 + t / Nh;
-            cls[t] = e < D.E ? D.lp_class[(size_t)env0 * Nh + t] : 0;
+            const size_t gidx = (size_t)env0 * Nh + t;
+            const bool on = e < D.E;
+            cls[t] = on ? D.lp_class[gidx] : 0;
+            sstat[t] = on ? D.hstatic[gidx] : 1;
+            pref[t] = on ? ha_pref_velocity(D.hpos[gidx], D.hgoal[gidx]) : make_float2(0.f, 0.f);   // pass 1: the humans where they are
         }
         __syncthreads();
         ha_build_order(order, cls, EPB * Nh, fill);
@@ -227,7 +238,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         // (the DEDUP kernel uses ONE instantiation of the pass for both passes: two copies of the solve do not fit the
         // instruction cache together)
         orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnew, posd, false,
-                                 D.stat_counters ? &flags[EPB * 4 + 2] : nullptr, &flags[EPB * 4], mode == 0, flags, false, order, cls);
+                                 D.stat_counters ? &flags[EPB * 4 + 2] : nullptr, &flags[EPB * 4], mode == 0, flags, false, order, cls, pref, sstat);
         __syncthreads();
         if (threadIdx.x == 0 && D.stat_counters && flags[EPB * 4 + 2]) atomicAdd(D.stat_counters + 11, (unsigned long long)flags[EPB * 4 + 2]);
         if (mode == 1)   // no look-ahead pass in a warm-start step: these classes order the next pass
@@ -249,6 +260,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
                 D.hpos[gidx] = np_;
                 D.hvel[gidx] = v;
                 posd[el * Nh + a] = np_;
+                pref[el * Nh + a] = ha_pref_velocity(np_, D.hgoal[gidx]);   // pass 2: from the moved position
                 float *A = agents + (size_t)el * 5 * nA;
                 A[a] = (float)np_.x; A[nA + a] = (float)np_.y; A[2 * nA + a] = v.x; A[3 * nA + a] = v.y;
                 // history roll (human_avoidance_env.py:149-158 / :92-100)
@@ -389,7 +401,7 @@ ha_step_kernel(const __grid_constant__ EnvDev D, int EPB, int mode, int write_ob
         float2 *vnext = vnew;   // pass-1 velocities now live in the tile / hvel
         ha_build_order(order, cls, EPB * Nh, fill);   // from the classes pass 1 has just produced
 #ifndef DRE_HA_SKIP_PASS2   // measurement builds only: what does the kernel cost without the look-ahead pass?
-        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags, PRUNE, order, cls);
+        orca_pass_tile<G, DEDUP, CUTOFF, PRUNE>(D, g, gi, NG, EPB, env0, nA, agents, lines, dist, vnext, posd, true, nullptr, &flags[EPB * 4 + 1], false, flags, PRUNE, order, cls, pref, sstat);
 #endif
         __syncthreads();
         for (int t = threadIdx.x; t < EPB * Nh; t += blockDim.x)   // the classes of the latest solves order the next step's pass 1

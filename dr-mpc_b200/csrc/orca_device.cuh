@@ -36,10 +36,11 @@ struct TileGroup {
     }
     // group-wide reductions in one REDUX instruction (sm_100a has the fp32 min/max forms; min/max are exact, so the
     // result equals the sequential scan bit for bit)
-    // Integer min / sum over the group: log2(G) butterfly shuffles. (REDUX.MIN / REDUX.ADD with a sub-warp member mask take a
-    // slow path when the warp's groups are on different iterations -- 9 % of ha_step's stall samples sat on them, half
-    // branch_resolving; measured on B200: shuffles take the dense-window step from 0.888 to 0.854 ms.) The fp32 min / max
-    // of linearProgram1 stay on redux.sync.{min,max}.f32: shuffles measured the same there.
+    // Group-wide min / max / sum: log2(G) butterfly shuffles (min and max are exact, so linearProgram1's reductions equal the
+    // sequential scan bit for bit). REDUX with a sub-warp member mask takes a slow path when the warp's groups are on different
+    // iterations -- 9 % of ha_step's stall samples sat on REDUX.MIN, half of them branch_resolving; measured on B200: shuffles
+    // take the dense-window step from 0.888 to 0.854 ms for the integer ones, the fp32 ones (redux.sync.{min,max}.f32 on
+    // sm_100a) another 0.4 %.
     __device__ int min_int(int v) const
     {
 #pragma unroll
@@ -54,15 +55,15 @@ struct TileGroup {
     }
     __device__ float min_f32(float v) const
     {
-        float r;
-        asm volatile("redux.sync.min.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(lane_mask()));
-        return r;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, t.shfl_xor(v, o));
+        return v;
     }
     __device__ float max_f32(float v) const
     {
-        float r;
-        asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(lane_mask()));
-        return r;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, t.shfl_xor(v, o));
+        return v;
     }
 };
 #endif
@@ -147,10 +148,11 @@ DRE_HD int orca_first_violated(const Grp &g, const LinesT &L, int m, int cursor,
     const int lane = g.rank();
     int best = m;
 #pragma unroll 1
-    for (int i = (cursor / G) * G + lane; i < m; i += G) {
+    for (int i = cursor + lane; i < m; i += G) {       // from the cursor, not from its 8-aligned base (no wasted tests, -1.7 %);
+                                                       // a lane's indices grow, so its first hit is its smallest
         const OLine l = L[i];
         const bool v = (l.dx * (l.py - ry) - l.dy * (l.px - rx)) > thresh;
-        if (v && i >= cursor && i < best) best = i;
+        if (v && best == m) best = i;
     }
     return g.min_int(best);
 }

@@ -6,7 +6,7 @@ from .orca import BatchedORCA
 from .mpc import BatchedMPC
 from . import paths
 from . import parallel
-from .replay import BatchedReplayBuffer
+from .replay import BatchedReplayBuffer, DeviceReplayBuffer
 try:
     from .env import BatchedHAAndPTEnv
 except ImportError:   # env module not present in minimal builds
@@ -14,4 +14,4 @@ except ImportError:   # env module not present in minimal builds
 
 from . import compat
 
-__all__ = ["compat", "EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "BatchedReplayBuffer", "paths", "parallel"]
+__all__ = ["compat", "EngineConfig", "BatchedORCA", "BatchedMPC", "BatchedHAAndPTEnv", "BatchedReplayBuffer", "DeviceReplayBuffer", "paths", "parallel"]

@@ -61,6 +61,19 @@ class StepOut(ctypes.Structure):
                                     "mpc_status", "done_flags", "slab")] + [("slab_bytes", ctypes.c_size_t)]
 
 
+_REPLAY_KEYS = ("pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid",
+                "detected_humans")
+
+
+class ReplayFields(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in _REPLAY_KEYS]
+
+
+class ReplayView(ctypes.Structure):
+    _fields_ = [("S", ReplayFields), ("S_prime", ReplayFields), ("rewards", c_vp), ("actions", c_vp), ("done", c_vp),
+                ("rows", c_i64), ("dtype", c_i32)]
+
+
 _lib = None
 
 
@@ -119,6 +132,13 @@ def load():
         L.dre_env_cvmm_filter.argtypes = [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]
         L.dre_env_cvmm_check.argtypes = [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]
         L.dre_env_set_seed.argtypes = [c_vp, c_u64]
+        L.dre_replay_create.argtypes = [c_vp, c_i64, c_i32, P(c_vp)]
+        L.dre_replay_destroy.argtypes = [c_vp]
+        L.dre_replay_storage.argtypes = [c_vp, P(ReplayView), P(c_i32), P(ctypes.c_size_t)]
+        L.dre_replay_insert.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
+        L.dre_replay_count.argtypes = [c_vp, P(c_i64), P(c_i64), P(c_i64), c_vp]
+        L.dre_replay_clear.argtypes = [c_vp, c_vp]
+        L.dre_replay_sample.argtypes = [c_vp, c_vp, c_i64, c_i32, P(ReplayView), c_vp]
         L.dre_env_set_profiling.argtypes = [c_vp, c_i32]
         L.dre_env_kernel_ms.argtypes = [c_vp, c_vp, c_vp, c_i32]
     L.dre_measure_peak.argtypes = [c_i32, P(c_d)]

@@ -22,6 +22,7 @@ UNITS = [
     ("env_kernels.cu", ["-fmad=false"]),
     ("capi.cu", []),
     ("env_capi.cu", []),
+    ("replay_capi.cu", []),
 ]
 
 

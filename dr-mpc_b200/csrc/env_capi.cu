@@ -339,6 +339,9 @@ extern "C" int dre_env_current_slab(dre_env *h) { return h ? h->cur : DRE_ERR_IN
 
 extern "C" dre_mpc *dre_env_mpc(dre_env *h) { return h ? h->mpc : nullptr; }
 
+const dre_env_config &dre_env_config_of(const dre_env *h) { return h->cfg; }
+int dre_env_mpc_actions_width(const dre_env *h) { return n_mpc_actions(h->cfg); }
+
 static int env_solve_mpc(dre_env *h, const EnvDev &D, cudaStream_t s)
 {
     const int nact = n_mpc_actions(h->cfg);

@@ -78,6 +78,11 @@ int dre_env_launch_reset(const EnvDev &D, const double *hpos_init, const double 
 int dre_env_launch_switch_path(const EnvDev &D, cudaStream_t s);
 int dre_env_launch_sr_decide(const EnvDev &D, int commit, uint8_t *scripted, double *actions, uint8_t *stuck, cudaStream_t s);
 
+// env_capi.cu accessors (replay_capi.cu)
+struct dre_env;
+const dre_env_config &dre_env_config_of(const dre_env *h);
+int dre_env_mpc_actions_width(const dre_env *h);   // doubles per env in dre_step_out.mpc_actions
+
 // capi.cu accessors
 struct dre_mpc;
 const dre_mpc_params &dre_mpc_params_of(const dre_mpc *h);

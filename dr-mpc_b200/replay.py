@@ -98,3 +98,156 @@ class BatchedReplayBuffer:
         rb = self.replay_buffer
         return (_nest({k: v[idx] for k, v in self._S.items()}), rb['actions'][idx], _nest({k: v[idx] for k, v in self._Sp.items()}),
                 rb['rewards'][idx], rb['done'][idx])
+
+
+class _ReplayHandle:
+    """Owns the dre_replay handle (and keeps the env handle it reads from alive)."""
+
+    def __init__(self, L, h, env_owner):
+        self.L, self.h, self.env_owner = L, h, env_owner
+
+    def __del__(self):
+        if self.h is not None and self.L is not None:
+            self.L.dre_replay_destroy(self.h)
+            self.h = None
+
+
+class DeviceReplayBuffer:
+    """The reference ReplayBuffer (scripts/utils/storage.py:6-133) as a ring in HBM owned by libdre and fed by one gather
+    kernel per step from the env's double-buffered output slab (include/dre.h: dre_replay_*): no torch indexing, no host
+    round trip, no clone of S. `replay_buffer` has the reference's nesting and keys (zero-copy views of the ring).
+
+        rb = DeviceReplayBuffer(env, buffer_size)
+        S = env.reset()
+        loop:  a = policy(S); S, R, done, info, _ = env.step(a); rb.insert(a)        # S / S_prime come from the two slabs
+               Sb, Ab, Spb, Rb, Db = rb.sample_from_buffer(256)
+
+    dtype torch.float64 keeps the reference's storage type; torch.float32 halves the ring (one rounding of each float64)."""
+
+    _OBS_KEYS = (('PT', 'PT_state', 'pt_state'), ('PT', 'MPC_actions', 'mpc_actions'), ('HA', 'robot_node', 'robot_node'),
+                 ('HA', 'past_robot_velocities', 'past_robot_vel'), ('HA', 'percent_episode', 'percent_episode'),
+                 ('HA', 'spatial_edges', 'spatial_edges'), ('HA', 'human_valid_history', 'human_valid'),
+                 ('HA', 'detected_human_num', 'detected_humans'))
+
+    def __init__(self, env, buffer_size, dtype=None):
+        import ctypes
+        import torch
+        from . import _lib
+        from .env import _view
+        self.env = env
+        self.device = env.device
+        self.dtype = dtype or torch.float64
+        if self.dtype not in (torch.float64, torch.float32):
+            raise ValueError("DeviceReplayBuffer stores float64 or float32")
+        self._code = 0 if self.dtype == torch.float64 else 1
+        self.buffer_size = int(buffer_size)
+        self._L = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self._L.dre_replay_create(env._h, self.buffer_size, self._code, ctypes.byref(h)))
+        self._h = h
+        self._owner = _ReplayHandle(self._L, h, env._owner)
+        view = _lib.ReplayView()
+        widths = (ctypes.c_int32 * 8)()
+        nbytes = ctypes.c_size_t()
+        _lib.check(self._L.dre_replay_storage(self._h, ctypes.byref(view), widths, ctypes.byref(nbytes)))
+        self.storage_bytes = int(nbytes.value)
+        self._widths = list(widths)
+        self._shapes = self._row_shapes(env)
+        kind = "f8" if self._code == 0 else "f4"
+        mk = lambda ptr, shape: _view(ptr, (self.buffer_size,) + shape, kind, self.device, self._owner)
+        self.replay_buffer = {'S': {'PT': {}, 'HA': {}}, 'S_prime': {'PT': {}, 'HA': {}},
+                              'rewards': mk(view.rewards, (1,)), 'actions': mk(view.actions, (2,)), 'done': mk(view.done, (1,))}
+        for grp, fields in (('S', view.S), ('S_prime', view.S_prime)):
+            for top, key, name in self._OBS_KEYS:
+                self.replay_buffer[grp][top][key] = mk(getattr(fields, name), self._shapes[name])
+
+    def _row_shapes(self, env):
+        shapes = {name: tuple(env.out[name].shape[1:]) for _, _, name in self._OBS_KEYS}
+        for (_, _, name), w in zip(self._OBS_KEYS, self._widths):
+            n = 1
+            for s in shapes[name]:
+                n *= s
+            assert n == w, (name, shapes[name], w)
+        return shapes
+
+    def _stream(self):
+        import ctypes
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _count(self):
+        import ctypes
+        from . import _lib
+        v, hd, last = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._L.dre_replay_count(self._h, ctypes.byref(v), ctypes.byref(hd), ctypes.byref(last), self._stream()))
+        return int(v.value), int(hd.value), int(last.value)
+
+    @property
+    def valid_entries(self):
+        """storage.py:13. Reads the device-side counter (synchronises the current stream)."""
+        return self._count()[0]
+
+    @property
+    def last_inserted(self):
+        return self._count()[2]
+
+    def full(self):
+        return self.valid_entries == self.buffer_size
+
+    def clear(self):
+        from . import _lib
+        _lib.check(self._L.dre_replay_clear(self._h, self._stream()))
+
+    def insert(self, actions=None, mask=None, skip_scripted=True):
+        """storage.py:54-98 / online_continuous_task.py:189 for all envs of the latest step: (S = previous slab, A,
+        S_prime = latest slab, R['R'], done_for_replay). `actions` [E,2] float64 = the policy's action_model (None: the
+        executed actions); `mask` [E] bool keeps a subset; skip_scripted leaves the soft-reset steps out. Asynchronous."""
+        import ctypes
+        import torch
+        from . import _lib
+        a = None
+        if actions is not None:
+            a = torch.as_tensor(actions).to(device=self.device, dtype=torch.float64).contiguous()
+            if tuple(a.shape) != (self.env.E, 2):
+                raise ValueError(f"actions must be [{self.env.E}, 2]")
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+            if m.numel() != self.env.E:
+                raise ValueError(f"mask must have {self.env.E} entries")
+        _lib.check(self._L.dre_replay_insert(self._h, ctypes.c_void_p(a.data_ptr()) if a is not None else None,
+                                             ctypes.c_void_p(m.data_ptr()) if m is not None else None, int(bool(skip_scripted)),
+                                             self._stream()))
+
+    def physical_index(self, chronological):
+        valid, head, _ = self._count()
+        return chronological if valid < self.buffer_size else (chronological + head) % self.buffer_size
+
+    def sample_from_buffer(self, batch_size, indices_to_sample=None, dtype=None):
+        """storage.py:101-133: (S, actions, S_prime, rewards, done) at random valid rows, or at the given chronological
+        indices (0 = oldest). dtype torch.float32 hands the batch out in the networks' precision in the same pass."""
+        import ctypes
+        import torch
+        from . import _lib
+        out_dtype = dtype or self.dtype
+        code = 0 if out_dtype == torch.float64 else 1
+        if indices_to_sample is None:
+            valid = self.valid_entries
+            if valid < batch_size:      # storage.py:103-106 only warns
+                print(f"Not enough entries in buffer to sample from. Only {valid} entries in buffer")
+            indices_to_sample = torch.randint(0, max(valid, 1), (batch_size,), device=self.device)
+        idx = torch.as_tensor(indices_to_sample).to(device=self.device, dtype=torch.int64).contiguous()
+        n = int(idx.numel())
+        batch = _lib.ReplayView()
+        mk = lambda shape: torch.empty((n,) + shape, dtype=out_dtype, device=self.device)
+        S, Sp = {'PT': {}, 'HA': {}}, {'PT': {}, 'HA': {}}
+        for grp, fields in ((S, batch.S), (Sp, batch.S_prime)):
+            for top, key, name in self._OBS_KEYS:
+                t = mk(self._shapes[name])
+                grp[top][key] = t
+                setattr(fields, name, t.data_ptr())
+        A, R, D = mk((2,)), mk((1,)), mk((1,))
+        batch.actions, batch.rewards, batch.done = A.data_ptr(), R.data_ptr(), D.data_ptr()
+        batch.rows, batch.dtype = n, code
+        _lib.check(self._L.dre_replay_sample(self._h, ctypes.c_void_p(idx.data_ptr()), n, code, ctypes.byref(batch), self._stream()))
+        return S, A, Sp, R, D

@@ -323,6 +323,56 @@ int dre_stats_comm_id(char *id128);
 int dre_env_stats_comm_init(dre_env *h, const char *id128, int32_t rank, int32_t world_size);
 int dre_stats_reduce(dre_env *h, void *nccl_comm, int64_t *counters_dev16, double *sums_dev4, int32_t reset, void *stream);
 
+/*
+ * Replay ring in device memory, fed straight from the env's double-buffered output slab.
+ * Replaces ReplayBuffer (reference scripts/utils/storage.py:6-133) together with the numpy -> torch -> cuda conversion in
+ * front of it (scripts/online_continuous_task.py:136,148,187; scripts/utils/misc.py:7-21) for E envs at once.
+ * Storage = the reference's (storage.py:21-35): one array [capacity][...] per observation key for 'S' and for 'S_prime',
+ * 'rewards' [N][1], 'actions' [N][2], 'done' [N][1]; element type float64 (the reference's) or float32 (each float64 result
+ * rounded once). It is a ring: a full buffer overwrites its oldest rows where the reference rolls every tensor by one
+ * (storage.py:56-75), so the reference's row j (chronological, 0 = oldest) is slot (head + j) % capacity once full.
+ */
+#define DRE_REPLAY_F64 0
+#define DRE_REPLAY_F32 1
+typedef struct dre_replay dre_replay;
+typedef struct dre_replay_fields {   /* dev pointers, [rows][...] each; same keys as dre_step_out's observation part */
+    void *pt_state;        /* S['PT']['PT_state']   [rows][4*(lookahead+lookbehind)] */
+    void *mpc_actions;     /* S['PT']['MPC_actions'] [rows][2*min(K,A)]              */
+    void *robot_node;      /* [rows][2*LB]          */
+    void *past_robot_vel;  /* [rows][2*LB]          */
+    void *percent_episode; /* [rows]                */
+    void *spatial_edges;   /* [rows][Nh][2*(LB+1)]  */
+    void *human_valid;     /* [rows][Nh]            */
+    void *detected_humans; /* [rows]                */
+} dre_replay_fields;
+typedef struct dre_replay_view {
+    dre_replay_fields S, S_prime;
+    void *rewards;         /* [rows][1] */
+    void *actions;         /* [rows][2] */
+    void *done;            /* [rows][1] */
+    int64_t rows;
+    int32_t dtype;         /* DRE_REPLAY_F64 | DRE_REPLAY_F32 */
+} dre_replay_view;
+/* ReplayBuffer.__init__ (storage.py:8-35): capacity = buffer_size rows of the env's observation shapes. */
+int dre_replay_create(dre_env *env, int64_t capacity, int32_t dtype, dre_replay **out);
+int dre_replay_destroy(dre_replay *rb);
+/* the ring's arrays (zero-copy access for the learner), the 8 row widths in dre_replay_fields order, the bytes allocated */
+int dre_replay_storage(dre_replay *rb, dre_replay_view *view, int32_t *widths8, size_t *bytes);
+/* ReplayBuffer.insert(S, A, S_prime, R, done) (storage.py:54-98; call site online_continuous_task.py:189) for every env of
+ * the latest step at once: S = the observation of the PREVIOUS slab (what the action was chosen on), S_prime = the latest
+ * slab, R = rewards[e][2] ('R'), done = done_for_replay; A = actions dev double[E][2] (the policy's action_model), NULL =
+ * the executed actions. keep_mask dev uint8[E] or NULL selects envs; skip_scripted = 1 also leaves out the envs whose step
+ * ran a scripted soft-reset action (the reference's soft_reset=True steps never reach insert, :143,189). Asynchronous: the
+ * row count stays on the device (dre_replay_count synchronises). */
+int dre_replay_insert(dre_replay *rb, const double *actions, const uint8_t *keep_mask, int32_t skip_scripted, void *stream);
+/* valid_entries (storage.py:13), the ring head, and the rows stored by the latest insert; any pointer may be NULL */
+int dre_replay_count(dre_replay *rb, int64_t *valid, int64_t *head, int64_t *last_inserted, void *stream);
+int dre_replay_clear(dre_replay *rb, void *stream);
+/* ReplayBuffer.sample_from_buffer (storage.py:101-133): gather the rows with CHRONOLOGICAL indices (dev int64[n], 0 = oldest
+ * valid row, like the reference's indices_to_sample) into the caller's arrays `batch` ([n][...] each, element type
+ * out_dtype; a float64 ring can hand out float32 batches -- the cast model.py applies -- in the same pass). */
+int dre_replay_sample(dre_replay *rb, const int64_t *indices, int64_t n, int32_t out_dtype, const dre_replay_view *batch, void *stream);
+
 /* Measurement support (bench.py): when profiling is on, step() brackets each of its kernels with CUDA events on the
  * caller's stream; dre_env_kernel_ms() synchronises and returns the summed milliseconds per kernel since the last
  * reset, order {ha_step, pt_step, mpc_solve, mpc_stats}, and the number of profiled steps. */

@@ -546,6 +546,33 @@ def run_env(a):
                           "disturbance reward reads (within 1.5 m of the robot); same results bit for bit (tests/test_gpu_env.py::"
                           "test_lookahead_prune_is_bit_identical); NOT the headline, which keeps the reference's two full ORCA passes per step")
 
+    # ---------------- the data-collection loop's other half, reported separately: every step followed by the replay insert
+    # (online_continuous_task.py:185-189) into the device-resident ring (dre_replay_insert: select + gather, HBM-bound) ----------------
+    replay = None
+    if not a.no_dedup:
+        try:
+            rb = d.DeviceReplayBuffer(env, 262144)
+
+            def step_insert():
+                rb.insert(step())
+
+            for _ in range(3):
+                step_insert(); flush.zero_()
+            ms3, _, _ = _timed(step_insert, a.steps, flush, barrier, max_over_ranks, rank, local, sample_clocks=False)
+            ms_ins, _, _ = _timed(lambda: rb.insert(act), min(a.steps, 20), flush, barrier, max_over_ranks, rank, local, sample_clocks=False)
+            ms_ins /= min(a.steps, 20)
+            W = sum(rb._widths)
+            ins_bytes = E * (2 * W * 8 + 29) + E * (2 * W + 4) * 8
+            replay = {"value": world * E * a.steps / (ms3 * 1e-3), "unit": unit, "ms_per_step": ms3 / a.steps, "insert_ms": ms_ins,
+                      "insert_algorithmic_bytes": ins_bytes, "insert_GBps": ins_bytes / (ms_ins * 1e-3) * 1e-9,
+                      "insert_frac_of_hbm_peak": ins_bytes / (ms_ins * 1e-3) * 1e-9 / hbm_peak, "ring_rows": rb.buffer_size,
+                      "ring_bytes": rb.storage_bytes, "valid_entries": rb.valid_entries,
+                      "what": "every step followed by dre_replay_insert of all E transitions (S from the previous slab, S' from the latest, "
+                              "float64 ring with the reference ReplayBuffer's layout); NOT the headline, which times the env step alone"}
+            del rb
+        except Exception as ex:   # noqa: BLE001 -- an extra; never lose the bench line over it
+            replay = {"error": repr(ex)}
+
     # ---------------- end to end through the host-buffer C-ABI call (closed loop through host memory) ----------------
     noise_h = noise[:8].cpu().numpy()
     a_host = torch.empty((E, 2), dtype=torch.float64).pin_memory().numpy()
@@ -612,7 +639,7 @@ def run_env(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": DTYPE, "data": "synthetic", "config": workload_config(a), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "parity": parity, "roofline": roofline, "roofline_compute": roofline_compute,
-                "kernels_ms": kavg, "dedup_variant": dedup, "lookahead_prune_variant": pruned, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
+                "kernels_ms": kavg, "dedup_variant": dedup, "lookahead_prune_variant": pruned, "replay_variant": replay, "cpu_baseline": cpu_baseline, "wall_ms_per_step_incl_flush": t_wall / a.steps * 1e3,
                 "episode_stats": {n: int(cnt[i]) for i, n in enumerate(d.env.STAT_NAMES)}, "episode_stats_via": stats_via,
                 "reward_sums": [float(x) for x in sums[:3]]}
         _emit(line)

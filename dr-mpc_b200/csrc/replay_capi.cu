@@ -14,7 +14,7 @@
 #include "env_launch.cuh"
 
 namespace {
-enum { RP_OBS = 8, RP_FIELDS = RP_OBS * 2 + 3, RP_THREADS = 256, RP_UNROLL = 4, RP_SEL_PER = 16 };
+enum { RP_OBS = 8, RP_FIELDS = RP_OBS * 2 + 3, RP_THREADS = 256, RP_UNROLL = 2, RP_ROWS = 4, RP_SEL = 1024 };
 
 struct RingState {          // device-resident bookkeeping: an insert never synchronises with the host
     long long head;         // slot the next row goes to
@@ -23,41 +23,49 @@ struct RingState {          // device-resident bookkeeping: an insert never sync
     int n_last;             // rows selected by the latest insert
     int first_last;         // rank of the first selected row that fits (n_last > capacity keeps the newest)
     long long base_last;    // head before the latest insert
+    unsigned arrived;       // CTAs of the running selection that have published their keep words
 };
 
-// one copy job per field: dst[(dst_row) * w + k] = src[(src_row) * w + k], k < w
+// one copy job per field: dst[dst_row * w + k] = src[src_row * w + k], k < w. A row is cut into UNITS: pairs of elements
+// (one 16-byte access for float64) in the fields of even width, single elements in the others.
 struct FieldTable {
     const void *src[RP_FIELDS];
     void *dst[RP_FIELDS];
     int w[RP_FIELDS];
-    int off[RP_FIELDS + 1];  // prefix sums of w: element j of a row belongs to field f with off[f] <= j < off[f+1]
+    int uoff[RP_FIELDS + 1];  // prefix sums of the units per field: unit j belongs to field f with uoff[f] <= j < uoff[f+1]
     int nf;
 };
 
 // keep[e] = (mask == nullptr || mask[e]) && !(skip_scripted && done_flags[e][12]); rows[] = the kept envs in env order.
-// One CTA (E is 10^4..10^6 bytes of input): every thread loads RP_SEL_PER consecutive envs' bytes first (independent
-// loads, one memory latency per pass of 16384 envs), then one block-wide exclusive scan of the per-thread counts.
-__global__ void __launch_bounds__(1024) replay_select_kernel(int E, long long capacity, const uint8_t *mask, const uint8_t *done_flags,
-                                                             int skip_scripted, int *rows, RingState *st)
+// Every CTA publishes the keep bits of its 1024 envs as 32 ballot words; the LAST CTA to arrive scans the words (2 KB for
+// 16384 envs instead of 256 KB of strided flag bytes), writes rows[] and advances the ring.
+__global__ void __launch_bounds__(RP_SEL) replay_select_kernel(int E, long long capacity, const uint8_t *mask, const uint8_t *done_flags,
+                                                               int skip_scripted, unsigned *words, int *rows, RingState *st)
 {
     __shared__ int warp_sum[32];
     __shared__ int running;
+    __shared__ bool last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int e = blockIdx.x * RP_SEL + tid;
+    bool keep = e < E;
+    if (keep && mask) keep = mask[e] != 0;
+    if (keep && skip_scripted) keep = done_flags[(size_t)e * 16 + 12] == 0;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) words[e >> 5] = b;
+    __syncthreads();
+    if (tid == 0) {                       // one cumulative fence per CTA (the barrier ordered the CTA's word stores before it)
+        __threadfence();
+        last = atomicAdd(&st->arrived, 1u) == gridDim.x - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (!last) return;
     if (tid == 0) running = 0;
     __syncthreads();
-    for (int base = 0; base < E; base += 1024 * RP_SEL_PER) {
-        const int e0 = base + tid * RP_SEL_PER;
-        unsigned bits = 0;
-        uint8_t m[RP_SEL_PER], s[RP_SEL_PER];
-#pragma unroll
-        for (int q = 0; q < RP_SEL_PER; ++q) {
-            const bool in = e0 + q < E;
-            m[q] = (in && mask) ? mask[e0 + q] : (uint8_t)(in ? 1 : 0);
-            s[q] = (in && skip_scripted) ? done_flags[(size_t)(e0 + q) * 16 + 12] : (uint8_t)0;
-        }
-#pragma unroll
-        for (int q = 0; q < RP_SEL_PER; ++q) bits |= (m[q] != 0 && s[q] == 0) ? (1u << q) : 0u;
-        const int mine = __popc(bits);
+    const int nwords = gridDim.x * 32;
+    for (int wbase = 0; wbase < nwords; wbase += RP_SEL) {
+        unsigned w = wbase + tid < nwords ? __ldcg(&words[wbase + tid]) : 0u;
+        const int mine = __popc(w);
         int incl = mine;                                       // inclusive scan over the warp
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -67,12 +75,14 @@ __global__ void __launch_bounds__(1024) replay_select_kernel(int E, long long ca
         if (lane == 31) warp_sum[wid] = incl;
         __syncthreads();
         int before = running + incl - mine;
-        for (int w = 0; w < wid; ++w) before += warp_sum[w];
-#pragma unroll
-        for (int q = 0; q < RP_SEL_PER; ++q)
-            if (bits & (1u << q)) rows[before++] = e0 + q;
+        for (int q = 0; q < wid; ++q) before += warp_sum[q];
+        const int e0 = (wbase + tid) * 32;
+        while (w) {
+            rows[before++] = e0 + __ffs(w) - 1;
+            w &= w - 1;
+        }
         __syncthreads();
-        if (tid == 1023) running = before;                     // the last thread's end = everything kept so far
+        if (tid == RP_SEL - 1) running = before;               // the last thread's end = everything kept so far
         __syncthreads();
     }
     if (tid == 0) {
@@ -85,24 +95,26 @@ __global__ void __launch_bounds__(1024) replay_select_kernel(int E, long long ca
         st->head = (st->head + m) % capacity;
         st->valid = st->valid + m > capacity ? capacity : st->valid + m;
         st->total += m;
+        st->arrived = 0;
     }
 }
 
-template <class Tsrc, class Tdst> __device__ __forceinline__ Tdst rp_cvt(Tsrc v) { return (Tdst)v; }
+template <class T> struct alignas(2 * sizeof(T)) RpPair { T x, y; };
 
 // MODE 0 (insert): row r < n_last - first_last: src row = rows[first_last + r], dst row = (base_last + r) mod capacity;
 //                  the three transition scalars come from their own source layouts.
 // MODE 1 (sample): row r < n: src row = ring slot of chronological index idx[r], dst row = r.
-// Element j of a row (all fields of S and S' laid end to end, W elements) is copied by thread j mod 256 for EVERY row: the
-// (field, offset) of a thread's RP_UNROLL elements is looked up once per tile of 1024 elements, outside the row loop, and
-// each row then costs RP_UNROLL independent loads followed by RP_UNROLL stores.
+// Unit j of a row (all fields of S and S' laid end to end) is copied by thread j mod 256 for EVERY row: the (field, offset)
+// of a thread's RP_UNROLL units is looked up once per tile, outside the row loop; one trip then issues
+// RP_ROWS * RP_UNROLL independent 16-byte loads per thread before the first store -- the copy is bound by memory latency
+// x bytes in flight, not by instructions.
 template <class Tsrc, class Tdst, int MODE>
-__global__ void __launch_bounds__(RP_THREADS, 4) replay_gather_kernel(const __grid_constant__ FieldTable T, long long capacity,
-                                                                   const RingState *st, const int *rows, const long long *idx,
-                                                                   long long n_rows, const double *act_src, const double *rew_src,
-                                                                   const uint8_t *done_src, Tdst *act_dst, Tdst *rew_dst, Tdst *done_dst)
+__global__ void __launch_bounds__(RP_THREADS, 3) replay_gather_kernel(const __grid_constant__ FieldTable T, long long capacity,
+                                                                      const RingState *st, const int *rows, const long long *idx,
+                                                                      long long n_rows, const double *act_src, const double *rew_src,
+                                                                      const uint8_t *done_src, Tdst *act_dst, Tdst *rew_dst, Tdst *done_dst)
 {
-    const int nf = T.nf, W = T.off[nf];
+    const int nf = T.nf, U = T.uoff[nf];
     long long n = n_rows, head = 0, valid = 0, base = 0;
     int first = 0;
     if (MODE == 0) {
@@ -114,34 +126,32 @@ __global__ void __launch_bounds__(RP_THREADS, 4) replay_gather_kernel(const __gr
         valid = st->valid;
     }
     constexpr int TILE = RP_UNROLL * RP_THREADS;
-    for (int t0 = 0; t0 < W; t0 += TILE) {
+    for (int t0 = 0; t0 < U; t0 += TILE) {
         const Tsrc *sp[RP_UNROLL];
         Tdst *dp[RP_UNROLL];
-        long long w[RP_UNROLL];
+        int w[RP_UNROLL];       // field width; 0 = no unit; negative = a single-element unit
 #pragma unroll
         for (int u = 0; u < RP_UNROLL; ++u) {
             const int j = t0 + u * RP_THREADS + (int)threadIdx.x;
             sp[u] = nullptr; dp[u] = nullptr; w[u] = 0;
-            if (j < W) {
+            if (j < U) {
                 int f = 0;
-                for (int q = 1; q < nf; ++q) f += j >= T.off[q] ? 1 : 0;
-                const int k = j - T.off[f];
+                for (int q = 1; q < nf; ++q) f += j >= T.uoff[q] ? 1 : 0;
+                const int wf = T.w[f];
+                const bool pair = (wf & 1) == 0;
+                const int k = (j - T.uoff[f]) * (pair ? 2 : 1);
                 sp[u] = (const Tsrc *)T.src[f] + k;
                 dp[u] = (Tdst *)T.dst[f] + k;
-                w[u] = T.w[f];
+                w[u] = pair ? wf : -wf;
             }
         }
-        // two rows per trip: 2 * RP_UNROLL independent loads in flight per thread (the copy is bound by memory latency x
-        // bytes in flight, not by instructions)
-        for (long long r0 = blockIdx.x; r0 < n; r0 += 2 * (long long)gridDim.x) {
-            long long srow[2], drow[2];
-            bool on[2];
+        for (long long r0 = blockIdx.x; r0 < n; r0 += RP_ROWS * (long long)gridDim.x) {
+            long long srow[RP_ROWS], drow[RP_ROWS];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < RP_ROWS; ++h) {
                 const long long r = r0 + h * (long long)gridDim.x;
-                on[h] = r < n;
-                srow[h] = 0; drow[h] = 0;
-                if (!on[h]) continue;
+                srow[h] = -1; drow[h] = 0;
+                if (r >= n) continue;
                 if (MODE == 0) {
                     srow[h] = rows[first + r];
                     drow[h] = base + r;                     // base < capacity and r < capacity
@@ -155,24 +165,36 @@ __global__ void __launch_bounds__(RP_THREADS, 4) replay_gather_kernel(const __gr
                     drow[h] = r;
                 }
             }
-            Tsrc v[2][RP_UNROLL];
+            RpPair<Tsrc> v[RP_ROWS][RP_UNROLL];
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < RP_ROWS; ++h)
 #pragma unroll
-                for (int u = 0; u < RP_UNROLL; ++u)
-                    if (on[h] && sp[u]) v[h][u] = sp[u][srow[h] * w[u]];
+                for (int u = 0; u < RP_UNROLL; ++u) {
+                    if (srow[h] < 0 || w[u] == 0) continue;
+                    if (w[u] > 0) v[h][u] = *(const RpPair<Tsrc> *)(sp[u] + srow[h] * w[u]);
+                    else v[h][u].x = sp[u][srow[h] * -w[u]];
+                }
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < RP_ROWS; ++h)
 #pragma unroll
-                for (int u = 0; u < RP_UNROLL; ++u)
-                    if (on[h] && dp[u]) dp[u][drow[h] * w[u]] = rp_cvt<Tsrc, Tdst>(v[h][u]);
-            if (MODE == 0 && t0 == 0 && threadIdx.x >= RP_THREADS - 8) {
+                for (int u = 0; u < RP_UNROLL; ++u) {
+                    if (srow[h] < 0 || w[u] == 0) continue;
+                    if (w[u] > 0) {
+                        RpPair<Tdst> o;
+                        o.x = (Tdst)v[h][u].x; o.y = (Tdst)v[h][u].y;
+                        *(RpPair<Tdst> *)(dp[u] + drow[h] * w[u]) = o;
+                    } else {
+                        dp[u][drow[h] * -w[u]] = (Tdst)v[h][u].x;
+                    }
+                }
+            if (MODE == 0 && t0 == 0 && threadIdx.x >= RP_THREADS - 4 * RP_ROWS) {
                 // A [E][2], R = rewards[e][2] (HA_and_PT env.py:413), done_for_replay = flags[e][3]
-                const int t = (threadIdx.x - (RP_THREADS - 8)) & 3;
-                const bool second = threadIdx.x >= RP_THREADS - 4;
-                const bool o = second ? on[1] : on[0];
-                const long long sr = second ? srow[1] : srow[0], dr = second ? drow[1] : drow[0];
-                if (o) {
+                const int q = threadIdx.x - (RP_THREADS - 4 * RP_ROWS), t = q & 3, hh = q >> 2;
+                long long sr = -1, dr = 0;
+#pragma unroll
+                for (int h = 0; h < RP_ROWS; ++h)
+                    if (h == hh) { sr = srow[h]; dr = drow[h]; }
+                if (sr >= 0) {
                     if (t < 2) act_dst[dr * 2 + t] = (Tdst)act_src[sr * 2 + t];
                     else if (t == 2) rew_dst[dr] = (Tdst)rew_src[sr * 3 + 2];
                     else done_dst[dr] = (Tdst)(done_src[sr * 16 + 3] ? 1.0 : 0.0);
@@ -198,6 +220,7 @@ struct dre_replay {
     dre_replay_view ring;
     RingState *st = nullptr;        // device
     int *rows = nullptr;            // device [E]
+    unsigned *words = nullptr;      // device [ceil(E / 1024) * 32] keep bits of the running selection
 };
 
 namespace {
@@ -233,6 +256,18 @@ void carve_view(char *base, size_t &off, long long rows, size_t es, const ObsWid
     v.actions = take((size_t)rows * 2);
     v.done = take((size_t)rows);
     off = (off + 255) / 256 * 256;
+}
+
+// units per field + alignment of the paired (even-width) fields: base pointers on 16 bytes (row strides then are too)
+bool finish_table(FieldTable &T)
+{
+    T.uoff[0] = 0;
+    for (int f = 0; f < RP_FIELDS; ++f) {
+        const bool pair = (T.w[f] & 1) == 0;
+        T.uoff[f + 1] = T.uoff[f] + (f < T.nf ? (pair ? T.w[f] / 2 : T.w[f]) : 0);
+        if (f < T.nf && pair && T.w[f] > 0 && ((((uintptr_t)T.src[f]) | ((uintptr_t)T.dst[f])) & 15)) return false;
+    }
+    return true;
 }
 
 template <int MODE, class Tsrc, class Tdst>
@@ -271,7 +306,8 @@ extern "C" int dre_replay_create(dre_env *env, int64_t capacity, int32_t dtype, 
     cudaError_t e;
     if ((e = cudaMalloc(&rb->block, bytes)) != cudaSuccess || (e = cudaMemset(rb->block, 0, bytes)) != cudaSuccess ||
         (e = cudaMalloc((void **)&rb->st, sizeof(RingState))) != cudaSuccess || (e = cudaMemset(rb->st, 0, sizeof(RingState))) != cudaSuccess ||
-        (e = cudaMalloc((void **)&rb->rows, (size_t)rb->E * sizeof(int))) != cudaSuccess) {
+        (e = cudaMalloc((void **)&rb->rows, (size_t)rb->E * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&rb->words, (size_t)((rb->E + RP_SEL - 1) / RP_SEL) * 32 * sizeof(unsigned))) != cudaSuccess) {
         dre_set_cuda_error(e, __FILE__, __LINE__);
         dre_replay_destroy(rb);
         return e == cudaErrorMemoryAllocation ? DRE_ERR_NOMEM : DRE_ERR_CUDA;
@@ -288,7 +324,7 @@ extern "C" int dre_replay_destroy(dre_replay *rb)
 {
     if (!rb) return DRE_OK;
     cudaDeviceSynchronize();
-    cudaFree(rb->block); cudaFree(rb->st); cudaFree(rb->rows);
+    cudaFree(rb->block); cudaFree(rb->st); cudaFree(rb->rows); cudaFree(rb->words);
     delete rb;
     return DRE_OK;
 }
@@ -311,20 +347,20 @@ extern "C" int dre_replay_insert(dre_replay *rb, const double *actions, const ui
     int rc = dre_env_outputs_at(rb->env, cur, &now);
     if (rc) return rc;
     if ((rc = dre_env_outputs_at(rb->env, cur ^ 1, &before))) return rc;
-    replay_select_kernel<<<1, 1024, 0, s>>>(rb->E, rb->capacity, keep_mask, now.done_flags, skip_scripted ? 1 : 0, rb->rows, rb->st);
+    replay_select_kernel<<<(rb->E + RP_SEL - 1) / RP_SEL, RP_SEL, 0, s>>>(rb->E, rb->capacity, keep_mask, now.done_flags, skip_scripted ? 1 : 0,
+                                                                        rb->words, rb->rows, rb->st);
     DRE_CUDA_TRY(cudaGetLastError());
     FieldTable T;
     const void *ps[RP_OBS], *pn[RP_OBS];
     slab_obs(before, ps);   // S  = the observation the action was chosen on: the previous step's slab
     slab_obs(now, pn);      // S' = the latest outputs
     T.nf = 2 * RP_OBS;
-    T.off[0] = 0;
     for (int f = 0; f < RP_OBS; ++f) {
         T.src[f] = ps[f]; T.dst[f] = obs_ptrs(rb->ring.S)[f]; T.w[f] = rb->ow.w[f];
         T.src[RP_OBS + f] = pn[f]; T.dst[RP_OBS + f] = obs_ptrs(rb->ring.S_prime)[f]; T.w[RP_OBS + f] = rb->ow.w[f];
     }
-    for (int f = 0; f < T.nf; ++f) T.off[f + 1] = T.off[f] + T.w[f];
-    for (int f = T.nf; f < RP_FIELDS; ++f) { T.src[f] = nullptr; T.dst[f] = nullptr; T.w[f] = 0; T.off[f + 1] = T.off[T.nf]; }
+    for (int f = T.nf; f < RP_FIELDS; ++f) { T.src[f] = nullptr; T.dst[f] = nullptr; T.w[f] = 0; }
+    if (!finish_table(T)) return DRE_ERR_INVALID;
     const double *act = actions ? actions : now.actions_used;
     const long long n_max = rb->E < rb->capacity ? rb->E : rb->capacity;
     if (rb->dtype == DRE_REPLAY_F32)
@@ -361,7 +397,6 @@ extern "C" int dre_replay_sample(dre_replay *rb, const int64_t *indices, int64_t
     if (n == 0) return DRE_OK;
     FieldTable T;
     T.nf = RP_FIELDS;
-    T.off[0] = 0;
     for (int f = 0; f < RP_OBS; ++f) {
         T.src[f] = obs_ptrs(rb->ring.S)[f]; T.dst[f] = obs_ptrs(batch->S)[f]; T.w[f] = rb->ow.w[f];
         T.src[RP_OBS + f] = obs_ptrs(rb->ring.S_prime)[f]; T.dst[RP_OBS + f] = obs_ptrs(batch->S_prime)[f]; T.w[RP_OBS + f] = rb->ow.w[f];
@@ -370,10 +405,9 @@ extern "C" int dre_replay_sample(dre_replay *rb, const int64_t *indices, int64_t
     T.src[a] = rb->ring.rewards; T.dst[a] = batch->rewards; T.w[a] = 1;
     T.src[a + 1] = rb->ring.actions; T.dst[a + 1] = batch->actions; T.w[a + 1] = 2;
     T.src[a + 2] = rb->ring.done; T.dst[a + 2] = batch->done; T.w[a + 2] = 1;
-    for (int f = 0; f < T.nf; ++f) {
+    for (int f = 0; f < T.nf; ++f)
         if (!T.dst[f]) return DRE_ERR_INVALID;
-        T.off[f + 1] = T.off[f] + T.w[f];
-    }
+    if (!finish_table(T)) return DRE_ERR_INVALID;   // the paired fields of `batch` must be 16-byte aligned
     cudaStream_t s = (cudaStream_t)stream;
     const long long *idx = (const long long *)indices;
     if (rb->dtype == DRE_REPLAY_F32) return launch_gather<1, float, float>(T, rb, idx, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s);

@@ -84,6 +84,9 @@ struct SerialGroup {
     DRE_HD float max_f32(float v) const { return v; }
 };
 
+#ifndef DRE_SCAN_BALLOT
+#define DRE_SCAN_BALLOT 0
+#endif
 #ifndef DRE_LP1_SERIAL
 #define DRE_LP1_SERIAL 1   // LP1 scans over at most this many earlier lines run redundantly on every lane (no group reduction).
                            // Measured on B200 at 16384 x 20: 4 -> 1 takes ha_step from 0.607 to 0.592 ms (sparse crowd) and the step
@@ -146,6 +149,21 @@ DRE_HD int orca_first_violated(const Grp &g, const LinesT &L, int m, int cursor,
 {
     constexpr int G = Grp::size;
     const int lane = g.rank();
+#if DRE_SCAN_BALLOT
+    // one vote per chunk of G lines, leaving at the first chunk that holds a violated line
+#pragma unroll 1
+    for (int base = cursor; base < m; base += G) {
+        const int i = base + lane;
+        bool v = false;
+        if (i < m) {
+            const OLine l = L[i];
+            v = (l.dx * (l.py - ry) - l.dy * (l.px - rx)) > thresh;
+        }
+        const unsigned b = g.ballot(v);
+        if (b) return base + dre_ffs(b) - 1;
+    }
+    return m;
+#endif
     int best = m;
 #pragma unroll 1
     for (int i = cursor + lane; i < m; i += G) {       // from the cursor, not from its 8-aligned base (no wasted tests, -1.7 %);

@@ -568,7 +568,8 @@ def run_env(a):
                       "insert_frac_of_hbm_peak": ins_bytes / (ms_ins * 1e-3) * 1e-9 / hbm_peak, "ring_rows": rb.buffer_size,
                       "ring_bytes": rb.storage_bytes, "valid_entries": rb.valid_entries,
                       "what": "every step followed by dre_replay_insert of all E transitions (S from the previous slab, S' from the latest, "
-                              "float64 ring with the reference ReplayBuffer's layout); NOT the headline, which times the env step alone"}
+                              "float64 ring with the reference ReplayBuffer's layout); NOT the headline, which times the env step alone. Timed later in "
+                              "the episode than the headline window (sparser crowd, faster steps): compare insert_ms, not ms_per_step"}
             del rb
         except Exception as ex:   # noqa: BLE001 -- an extra; never lose the bench line over it
             replay = {"error": repr(ex)}

@@ -23,14 +23,15 @@ def _rollout(env, steps, on_step):
         S = S_prime
 
 
-@pytest.mark.parametrize("capacity", [1500, 20000])
-def test_device_ring_equals_torch_ring(capacity):
+@pytest.mark.parametrize("E,Nh,capacity", [(512, 6, 1500), (512, 6, 20000), (128, 50, 700), (200, 7, 333), (1100, 3, 5000)])
+def test_device_ring_equals_torch_ring(E, Nh, capacity):
     """Masked inserts over 30 steps with the soft-reset machine on (scripted steps stay out), through several wrap-arounds
-    of the small ring: every stored tensor, the counters and chronological sampling agree with BatchedReplayBuffer."""
+    of the small ring: every stored tensor, the counters and chronological sampling agree with BatchedReplayBuffer. 50 humans =
+    a row longer than one tile of copy units; 7 and 3 humans = odd-width fields (single-element units); 1100 envs = two
+    selection CTAs, the second one partly empty."""
     import torch
     import dr_mpc_b200 as d
-    E = 512
-    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=6, soft_reset_on_device=True), num_envs=E)
+    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=Nh, soft_reset_on_device=True), num_envs=E)
     S0 = env.reset()
     ref = d.BatchedReplayBuffer(S0, buffer_size=capacity)
     ours = d.DeviceReplayBuffer(env, capacity)
@@ -44,7 +45,7 @@ def test_device_ring_equals_torch_ring(capacity):
         stored[1] += ours.last_inserted
     _rollout(env, 30, on_step)
     torch.cuda.synchronize()
-    assert stored[0] == stored[1] > capacity // 2
+    assert stored[0] == stored[1] > min(capacity // 2, 20 * E)
     assert ours.valid_entries == ref.valid_entries == min(stored[0], capacity)
     assert ours.physical_index(0) == ref.physical_index(0)
     fr, fo = ref.replay_buffer, ours.replay_buffer
@@ -55,7 +56,9 @@ def test_device_ring_equals_torch_ring(capacity):
             assert torch.equal(t_our, t_ref), (grp, key)
     for key in ('rewards', 'actions', 'done'):
         assert torch.equal(fo[key], fr[key]), key
-    assert fo['done'].sum() > 0 and (fo['S']['HA']['spatial_edges'] != fo['S_prime']['HA']['spatial_edges']).any()
+    assert (fo['S']['HA']['spatial_edges'] != fo['S_prime']['HA']['spatial_edges']).any()
+    if (E, Nh) == (512, 6):
+        assert fo['done'].sum() > 0
     # sampling at chronological indices (storage.py:101-133), float64 and float32 hand-out
     idx = torch.randint(0, ours.valid_entries, (777,), device=env.device)
     a64 = ours.sample_from_buffer(777, idx)
@@ -69,7 +72,7 @@ def test_device_ring_equals_torch_ring(capacity):
         else:
             assert torch.equal(got, want) and torch.equal(got32, want.float())
     Sb = ours.sample_from_buffer(64)[0]
-    assert Sb['HA']['spatial_edges'].shape == (64, 6, 14) and Sb['PT']['PT_state'].shape == (64, 100)
+    assert Sb['HA']['spatial_edges'].shape == (64, Nh, 14) and Sb['PT']['PT_state'].shape == (64, 100)
 
 
 def test_float32_ring_and_insert_larger_than_the_ring():

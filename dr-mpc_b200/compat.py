@@ -1,5 +1,6 @@
 """Literal drop-in adapters: the reference's OWN call signatures, objects and return types (one env, numpy with a leading
-dim of 1, Python floats / bools / sets) on top of the C ABI of libdre.so. A maintainer swaps three imports:
+dim of 1, Python floats / bools / sets) on top of the C ABI of libdre.so. A maintainer swaps three imports (plus, if wanted,
+the replay buffer's):
 
     scripts/policy/policy_factory.py:8      policy_factory['orca'] = dr_mpc_b200.compat.ORCA
     environment/HA_and_PT/...env.py:47      self.MPC = dr_mpc_b200.compat.MPC(config_master, K, dt, continuous_task, v_max, w_max)
@@ -20,6 +21,9 @@ Reference interfaces mirrored (file:line under /root/reference):
      .cvmm_diverse_safety_pipeline(np(2,), num_steps, backup) -> (ActionRot, info)   :422-473
      .cvmm_safety_check(np(2,), num_steps) -> (bool, float)         :475-513
      .create_video_continuous_task / .no_video / .render            :88-118,515 (no-ops: rendering is out of scope)
+  ReplayBuffer(obs_example, config_master, buffer_size)             scripts/utils/storage.py:6-35
+     .insert(S, A, S_prime, R, done), .sample_from_buffer(batch_size, indices_to_sample=None), .grab_all_data(batch_size),
+     .full(), .valid_entries, .replay_buffer                        storage.py:37-38,54-145
 """
 import ctypes
 from collections import namedtuple
@@ -364,3 +368,59 @@ class HAAndPTEnv:
         else:
             info['RL_action_bool'] = f"{int(d['num_safe'][0])}:{int(d['chosen'][0])}:({act.v},{act.w})"
         return act, info
+
+
+class ReplayBuffer:
+    """scripts/utils/storage.py:6-145 with the reference's own signatures (one transition per insert, tensors with a leading
+    dim of 1, `indices_to_sample` chronological) on top of BatchedReplayBuffer's ring: a full buffer overwrites its oldest
+    row instead of rolling every tensor by one (storage.py:56-75), which is invisible through this interface --
+    `replay_buffer` presents the tensors in the reference's chronological order. Fourth import a maintainer can swap:
+    scripts/online_continuous_task.py `from scripts.utils.storage import ReplayBuffer`."""
+
+    def __init__(self, obs_example, config_master, buffer_size):
+        from .replay import BatchedReplayBuffer
+        self.config_master = config_master
+        self.buffer_size = buffer_size
+        self.device = config_master.config_general.device          # storage.py:12
+        self._ring = BatchedReplayBuffer(obs_example, buffer_size, device=self.device)
+
+    @property
+    def valid_entries(self):
+        return self._ring.valid_entries
+
+    def full(self):
+        return self._ring.full()
+
+    @property
+    def replay_buffer(self):
+        """The reference's dict of tensors, rows in insertion order (storage.py:18-35). Views while the ring has not
+        wrapped; gathered copies afterwards."""
+        import torch
+        rb = self._ring.replay_buffer
+        if not self._ring.full() or self._ring._head == 0:
+            return rb
+        order = self._ring.physical_index(torch.arange(self.buffer_size, device=self._ring.device))
+        pick = lambda v: {k: pick(x) for k, x in v.items()} if isinstance(v, dict) else v[order]
+        return {k: pick(v) for k, v in rb.items()}
+
+    def insert(self, S, A, S_prime, R, done):
+        import torch
+        t = lambda x, w: torch.as_tensor(x, dtype=torch.float64).reshape(1, w)
+        self._ring.insert(S, t(A, 2), S_prime, t(float(R), 1), t(float(done), 1))
+
+    def sample_from_buffer(self, batch_size, indices_to_sample=None):
+        import torch
+        if indices_to_sample is None:
+            if self.valid_entries < batch_size:                      # storage.py:103-106 only warns
+                print(f"Not enough entries in buffer to sample from. Only {self.valid_entries} entries in buffer")
+            indices_to_sample = torch.randint(0, self.valid_entries, (batch_size,))
+        return self._ring.sample_from_buffer(batch_size, indices_to_sample)
+
+    def grab_all_data(self, batch_size):
+        import torch
+        out, cur = [], 0
+        while cur < self.valid_entries:                              # storage.py:135-145
+            end = min(cur + batch_size, self.valid_entries)
+            out.append(self.sample_from_buffer(0, indices_to_sample=torch.arange(cur, end)))
+            cur = end
+        return out

@@ -103,3 +103,62 @@ def test_matches_reference_replay_buffer_on_the_same_trace():
     for k in a[0]:
         for kk in a[0][k]:
             assert torch.equal(a[0][k][kk], b[0][k][kk]) and torch.equal(a[2][k][kk], b[2][k][kk])
+
+
+def test_compat_replay_buffer_is_the_reference_class_call_for_call():
+    """dr_mpc_b200.compat.ReplayBuffer takes the reference's constructor and call signatures (storage.py:8,54,101,135): the
+    same single-transition trace through both, past an overflow, gives the same `replay_buffer` tensors in the same order,
+    the same samples for the same indices and the same `grab_all_data` batches."""
+    import os
+    import types
+    import importlib.util
+    import torch
+    ref_root = os.environ.get("DRE_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "scripts")):
+        pytest.skip("the reference tree is only in the build container")
+    spec = importlib.util.spec_from_file_location("ref_storage2", os.path.join(ref_root, "scripts", "utils", "storage.py"))
+    ref_storage = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_storage)
+    from dr_mpc_b200 import compat
+    gen = torch.Generator().manual_seed(11)
+    Nh, size = 4, 9
+
+    def obs():
+        return {'PT': {'PT_state': torch.randn(1, 100, generator=gen, dtype=torch.float64), 'MPC_actions': torch.randn(1, 8, generator=gen, dtype=torch.float64)},
+                'HA': {'spatial_edges': torch.randn(1, Nh, 14, generator=gen, dtype=torch.float64), 'percent_episode': torch.rand(1, 1, generator=gen, dtype=torch.float64),
+                       'detected_human_num': torch.full((1,), float(Nh), dtype=torch.float64)}}
+    cm = types.SimpleNamespace(config_general=types.SimpleNamespace(device='cpu'))
+    ex = obs()
+    ref, ours = ref_storage.ReplayBuffer(ex, cm, size), compat.ReplayBuffer(ex, cm, size)
+
+    def same():
+        assert ref.valid_entries == ours.valid_entries and ref.full() == ours.full()
+        a, b = ref.replay_buffer, ours.replay_buffer
+        for grp in ('S', 'S_prime'):
+            for k, v in a[grp].items():
+                for kk, vv in v.items():
+                    assert torch.equal(vv, b[grp][k][kk]), (grp, k, kk)
+        for k in ('rewards', 'actions', 'done'):
+            assert torch.equal(a[k], b[k]), k
+
+    for t in range(2 * size + 3):
+        S, Sp = obs(), obs()
+        A = torch.randn(1, 2, generator=gen, dtype=torch.float64)
+        R, done = float(torch.randn((), generator=gen)), bool(torch.rand((), generator=gen) < 0.3)
+        ref.insert(S, A, Sp, R, done)
+        ours.insert(S, A, Sp, R, done)
+        if t in (3, size - 1, size, 2 * size + 2):
+            same()
+    idx = torch.randint(0, size, (6,), generator=gen)
+    for a, b in zip(ref.sample_from_buffer(6, idx), ours.sample_from_buffer(6, idx)):
+        if isinstance(a, dict):
+            for k in a:
+                for kk in a[k]:
+                    assert torch.equal(a[k][kk], b[k][kk])
+        else:
+            assert torch.equal(a, b)
+    ga, gb = ref.grab_all_data(4), ours.grab_all_data(4)
+    assert len(ga) == len(gb) == 3
+    for x, y in zip(ga, gb):
+        assert torch.equal(x[1], y[1]) and torch.equal(x[3], y[3]) and torch.equal(x[0]['PT']['PT_state'], y[0]['PT']['PT_state'])
+    assert ours.sample_from_buffer(5)[1].shape == (5, 2)

@@ -100,6 +100,17 @@ class BatchedReplayBuffer:
                 rb['rewards'][idx], rb['done'][idx])
 
 
+    def grab_all_data(self, batch_size):
+        """storage.py:135-145 (the OOD model's pass over the whole buffer, scripts/utils/OOD.py:120): every valid row once, in
+        chronological order, in batches of `batch_size`."""
+        import torch
+        out, cur, n = [], 0, self.valid_entries
+        while cur < n:
+            end = min(cur + batch_size, n)
+            out.append(self.sample_from_buffer(0, indices_to_sample=torch.arange(cur, end, device=self.device)))
+            cur = end
+        return out
+
 class _ReplayHandle:
     """Owns the dre_replay handle (and keeps the env handle it reads from alive)."""
 
@@ -251,3 +262,14 @@ class DeviceReplayBuffer:
         batch.rows, batch.dtype = n, code
         _lib.check(self._L.dre_replay_sample(self._h, ctypes.c_void_p(idx.data_ptr()), n, code, ctypes.byref(batch), self._stream()))
         return S, A, Sp, R, D
+
+    def grab_all_data(self, batch_size):
+        """storage.py:135-145 (the OOD model's pass over the whole buffer, scripts/utils/OOD.py:120): every valid row once, in
+        chronological order, in batches of `batch_size`."""
+        import torch
+        out, cur, n = [], 0, self.valid_entries
+        while cur < n:
+            end = min(cur + batch_size, n)
+            out.append(self.sample_from_buffer(0, indices_to_sample=torch.arange(cur, end, device=self.device)))
+            cur = end
+        return out

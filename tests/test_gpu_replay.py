@@ -71,6 +71,9 @@ def test_device_ring_equals_torch_ring(E, Nh, capacity):
                 assert _flat(got32)[key].dtype == torch.float32 and torch.equal(_flat(got32)[key], w.float()), key
         else:
             assert torch.equal(got, want) and torch.equal(got32, want.float())
+    ga, gr = ours.grab_all_data(1000), ref.grab_all_data(1000)                # storage.py:135-145 (OOD.py:120)
+    assert len(ga) == len(gr) == -(-ours.valid_entries // 1000)
+    assert all(torch.equal(x[1], y[1]) and torch.equal(x[0]['HA']['spatial_edges'], y[0]['HA']['spatial_edges']) for x, y in zip(ga, gr))
     Sb = ours.sample_from_buffer(64)[0]
     assert Sb['HA']['spatial_edges'].shape == (64, Nh, 14) and Sb['PT']['PT_state'].shape == (64, 100)
 

@@ -990,9 +990,41 @@ static int dre_env_pick_group(const EnvDev &D)
 int dre_env_ha_envs_per_cta(const EnvDev &D)
 {
     const int G = dre_env_pick_group(D);
-    int EPB = (dre_ha_agents_per_group() * (dre_ha_threads() / G)) / D.Nh;
-    if (EPB > (D.E + 591) / 592) EPB = (D.E + 591) / 592;   // keep >= 4 CTAs per SM in flight for small batches
-    return EPB < 1 ? 1 : EPB;
+    const int NG = dre_ha_threads() / G;
+    const int cap = (D.E + 591) / 592;                       // keep >= 4 CTAs per SM in flight for small batches
+    int base = (dre_ha_agents_per_group() * NG) / D.Nh;
+    if (base > cap) base = cap;
+    if (base < 1) base = 1;
+    static const bool pinned = getenv("DRE_HA_AGENTS_PER_GROUP") != nullptr;   // measurement aid: no automatic choice
+    if (pinned || base < 4) return base;
+    // Wave quantisation: a grid just over a whole number of waves ends in an almost empty last wave. Measured on B200 at
+    // 16384 x 20 (9 CTAs per SM = 1332 slots): 6 envs per CTA = 2731 CTAs = 2.05 waves: ha_step 0.658 ms (dense window) /
+    // 0.482 (sparse); 7 envs = 1.76 waves: 0.632 / 0.474; 5 envs = 2.46 waves: 0.618 / 0.465; 8 envs (shared memory then
+    // allows 8 CTAs per SM): slower. One env more or less per CTA when that fills the last wave clearly better.
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    }
+    const int nA = D.Nh + (D.orca.robot_visible ? 1 : 0);
+    const bool cut = !D.orca_dedup && dre_orca_use_cutoff(D.orca);
+    auto fill = [&](int epb) {
+        const size_t smem = ha_layout(D.Nh, nA, NG, epb, cut).bytes + 1024;     // + the per-CTA reservation
+        int per_sm = (int)((size_t)227 * 1024 / smem);
+        if (per_sm > DRE_HA_MINB) per_sm = DRE_HA_MINB;                        // the register bound (__launch_bounds__)
+        if (per_sm < 1) per_sm = 1;
+        const double waves = (double)((D.E + epb - 1) / epb) / ((double)sms * per_sm);
+        return waves <= 1.0 ? 1.0 : waves / ceil(waves);
+    };
+    int best = base;
+    double bf = fill(base);
+    const int cand[2] = {base + 1, base - 1};
+    for (int c : cand) {
+        if (c < 1 || c > cap) continue;
+        const double f = fill(c);
+        if (f > bf + 0.05) { best = c; bf = f; }
+    }
+    return best;
 }
 
 template <int G, bool DEDUP, bool CUTOFF, bool PRUNE>

@@ -341,6 +341,7 @@ extern "C" dre_mpc *dre_env_mpc(dre_env *h) { return h ? h->mpc : nullptr; }
 
 const dre_env_config &dre_env_config_of(const dre_env *h) { return h->cfg; }
 int dre_env_mpc_actions_width(const dre_env *h) { return n_mpc_actions(h->cfg); }
+void dre_env_note_stream(dre_env *h, cudaStream_t s) { h->last_stream = s; h->last_stream_set = true; }
 
 static int env_solve_mpc(dre_env *h, const EnvDev &D, cudaStream_t s)
 {
@@ -687,6 +688,7 @@ extern "C" int dre_env_set_host_chunks(dre_env *h, int32_t chunks)
 extern "C" int dre_env_invalidate_orca_cache(dre_env *h, void *stream)
 {
     if (!h) return DRE_ERR_INVALID;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;
     DRE_CUDA_TRY(cudaMemsetAsync(h->D.cache_valid, 0, (size_t)h->D.E, (cudaStream_t)stream));
     return DRE_OK;
 }
@@ -696,6 +698,7 @@ extern "C" int dre_env_cvmm_filter(dre_env *h, const double *actions, int32_t lo
 {
     if (!h || !actions || !backup_actions || !safe_actions) return DRE_ERR_INVALID;
     if (!h->was_reset || !h->D.paths) return DRE_ERR_STATE;
+    h->last_stream = (cudaStream_t)stream; h->last_stream_set = true;   // reads the state: a later step_host must run after it
     return dre_env_launch_cvmm(h->D, actions, lookahead_steps, backup_actions, num_backup, safe_actions, info4, candidate_safe,
                                (cudaStream_t)stream);
 }
@@ -720,6 +723,7 @@ extern "C" int dre_env_stats(dre_env *h, int64_t *counters_dev16, double *sums_d
 {
     if (!h) return DRE_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s; h->last_stream_set = true;
     if (counters_dev16) DRE_CUDA_TRY(cudaMemcpyAsync(counters_dev16, h->D.stat_counters, 16 * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     if (sums_dev4) DRE_CUDA_TRY(cudaMemcpyAsync(sums_dev4, h->D.stat_sums, 4 * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (reset) {

@@ -82,6 +82,7 @@ int dre_env_launch_sr_decide(const EnvDev &D, int commit, uint8_t *scripted, dou
 struct dre_env;
 const dre_env_config &dre_env_config_of(const dre_env *h);
 int dre_env_mpc_actions_width(const dre_env *h);   // doubles per env in dre_step_out.mpc_actions
+void dre_env_note_stream(dre_env *h, cudaStream_t s); // work reading the env's state / slabs was queued on s: the next step_host runs after it
 
 // capi.cu accessors
 struct dre_mpc;

@@ -347,6 +347,7 @@ extern "C" int dre_replay_insert(dre_replay *rb, const double *actions, const ui
     int rc = dre_env_outputs_at(rb->env, cur, &now);
     if (rc) return rc;
     if ((rc = dre_env_outputs_at(rb->env, cur ^ 1, &before))) return rc;
+    dre_env_note_stream(rb->env, s);   // the gather reads both slabs: a dre_env_step_host that follows (own streams) must wait for it
     replay_select_kernel<<<(rb->E + RP_SEL - 1) / RP_SEL, RP_SEL, 0, s>>>(rb->E, rb->capacity, keep_mask, now.done_flags, skip_scripted ? 1 : 0,
                                                                         rb->words, rb->rows, rb->st);
     DRE_CUDA_TRY(cudaGetLastError());

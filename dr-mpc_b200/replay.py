@@ -234,9 +234,11 @@ class DeviceReplayBuffer:
         valid, head, _ = self._count()
         return chronological if valid < self.buffer_size else (chronological + head) % self.buffer_size
 
-    def sample_from_buffer(self, batch_size, indices_to_sample=None, dtype=None):
+    def sample_from_buffer(self, batch_size, indices_to_sample=None, dtype=None, check_indices=True):
         """storage.py:101-133: (S, actions, S_prime, rewards, done) at random valid rows, or at the given chronological
-        indices (0 = oldest). dtype torch.float32 hands the batch out in the networks' precision in the same pass."""
+        indices (0 = oldest). dtype torch.float32 hands the batch out in the networks' precision in the same pass.
+        Caller-supplied indices are range-checked against the ring's capacity (IndexError, like the reference's tensor
+        indexing; reading the two extrema back is one synchronisation -- check_indices=False skips it)."""
         import ctypes
         import torch
         from . import _lib
@@ -247,8 +249,13 @@ class DeviceReplayBuffer:
             if valid < batch_size:      # storage.py:103-106 only warns
                 print(f"Not enough entries in buffer to sample from. Only {valid} entries in buffer")
             indices_to_sample = torch.randint(0, max(valid, 1), (batch_size,), device=self.device)
+            check_indices = False
         idx = torch.as_tensor(indices_to_sample).to(device=self.device, dtype=torch.int64).contiguous()
         n = int(idx.numel())
+        if check_indices and n:     # the reference's tensor indexing raises on a bad index; the gather kernel would read past the ring
+            lo, hi = (int(v) for v in torch.stack((idx.min(), idx.max())).tolist())
+            if lo < 0 or hi >= self.buffer_size:
+                raise IndexError(f"replay index out of range: [{lo}, {hi}] not inside [0, {self.buffer_size})")
         batch = _lib.ReplayView()
         mk = lambda shape: torch.empty((n,) + shape, dtype=out_dtype, device=self.device)
         S, Sp = {'PT': {}, 'HA': {}}, {'PT': {}, 'HA': {}}
@@ -270,6 +277,6 @@ class DeviceReplayBuffer:
         out, cur, n = [], 0, self.valid_entries
         while cur < n:
             end = min(cur + batch_size, n)
-            out.append(self.sample_from_buffer(0, indices_to_sample=torch.arange(cur, end, device=self.device)))
+            out.append(self.sample_from_buffer(0, indices_to_sample=torch.arange(cur, end, device=self.device), check_indices=False))
             cur = end
         return out

@@ -126,3 +126,46 @@ def test_ring_outlives_the_python_objects():
     gc.collect()
     torch.zeros(1 << 20, device="cuda")
     assert torch.equal(t, want)
+
+
+def test_sample_rejects_indices_outside_the_ring():
+    """storage.py:108-133 indexes its tensors with the caller's indices, so a bad index raises; the gather kernel would read
+    past the ring instead, hence the host-side range check (IndexError) in front of it."""
+    import torch
+    import dr_mpc_b200 as d
+    env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=4), num_envs=32)
+    S = env.reset()
+    rb = d.DeviceReplayBuffer(env, 96)
+    env.step(S['PT']['MPC_actions'][:, :2].clone())
+    rb.insert()
+    for bad in ([0, 96], [-1, 3], torch.tensor([5, 1 << 40])):
+        with pytest.raises(IndexError):
+            rb.sample_from_buffer(2, indices_to_sample=bad)
+    assert rb.sample_from_buffer(3, indices_to_sample=[0, 31, 95])[1].shape == (3, 2)     # inside the ring: fine
+    assert len(rb.grab_all_data(10)) == 4 and rb.grab_all_data(10)[-1][1].shape == (2, 2)
+
+
+def test_insert_then_host_step_reads_the_slab_before_it_is_rewritten():
+    """dre_replay_insert (caller's stream) reads BOTH output slabs; the dre_env_step_host that follows runs on the engine's
+    own streams and writes the older slab: the engine orders it after the insert. Checked against the same loop with a
+    device-wide synchronise between the two calls."""
+    import numpy as np
+    import torch
+    import dr_mpc_b200 as d
+    rings = []
+    for sync in (False, True):
+        env = d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=20, seed=11), num_envs=2048)
+        S = env.reset()
+        rb = d.DeviceReplayBuffer(env, 4 * 2048)
+        a = S['PT']['MPC_actions'][:, :2].cpu().numpy().copy()
+        for t in range(4):
+            out = env.step_host(a)
+            rb.insert()
+            if sync:
+                torch.cuda.synchronize()
+            a = np.ascontiguousarray(out['mpc_actions'][:, :2]).copy()
+        torch.cuda.synchronize()
+        rings.append({k: v.clone() for k, v in _flat(rb.replay_buffer['S']).items()} | {('A', 'A'): rb.replay_buffer['actions'].clone()})
+        assert rb.valid_entries == 4 * 2048
+    for k in rings[0]:
+        assert torch.equal(rings[0][k], rings[1][k]), k

@@ -93,3 +93,33 @@ def test_full_size_properties():
     v = d.BatchedORCA(d.EngineConfig()).predict(hpos, torch.zeros((E, Nh, 2), device=dev), goal,
                                                  torch.full((E, 2), 1e4, device=dev, dtype=torch.float64))
     assert torch.allclose(v, torch.tensor([0.6, 0.8], device=dev).expand_as(v), atol=1e-7)
+
+
+def test_full_size_symmetries_are_bit_exact():
+    """C3 / C4 shard sizes, no oracle needed: the solve commutes with quarter turns, reflections and permutations of the humans
+    BIT FOR BIT (two-term dot products / determinants, norms and comparisons map to themselves in IEEE arithmetic, neighbours
+    are ranked by distance; tests/test_oracle_shims.py holds the same property for the CPU restatement), LP3 solves included."""
+    import torch
+    import dr_mpc_b200 as d
+    dev = "cuda:0"
+    quarter = lambda a: torch.stack([-a[..., 1], a[..., 0]], -1).contiguous()
+    mirror = lambda a: (a * torch.tensor([1, -1], device=dev, dtype=a.dtype)).contiguous()
+    for E, Nh, spread in ((16384, 20, 5.0), (8192, 50, 8.0)):
+        gen = torch.Generator(device=dev).manual_seed(7 * E + Nh)
+        hpos = (torch.rand((E, Nh, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 2 * spread
+        goal = (torch.rand((E, Nh, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 2 * spread
+        hvel = (torch.rand((E, Nh, 2), generator=gen, device=dev) - 0.5) * 1.4
+        rpos = (torch.rand((E, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 2 * spread
+        orca = d.BatchedORCA(d.EngineConfig())
+        v0 = orca.predict(hpos, hvel, goal, rpos, want_stats=True)
+        st = orca.last_stats
+        assert (st[..., 1] < st[..., 0]).double().mean() > 0.1          # the infeasible (LP3) branch is well represented
+        for name, g in (("quarter turn", quarter), ("half turn", lambda a: (-a).contiguous()), ("reflection", mirror)):
+            v = orca.predict(g(hpos), g(hvel), g(goal), g(rpos))
+            assert torch.equal(v, g(v0)), (E, Nh, name)              # exact float equality (a zero may change its sign)
+        perm = torch.randperm(Nh, generator=torch.Generator().manual_seed(Nh)).to(dev)
+        v = orca.predict(hpos[:, perm].contiguous(), hvel[:, perm].contiguous(), goal[:, perm].contiguous(), rpos)
+        # same bits, except where two neighbours sit at EXACTLY the same fp32 distance: RVO2's insertNeighbor then keeps index
+        # order, which a permutation changes (a dozen such agents are expected among 8192 x 50)
+        differ = (v.view(torch.int32) != v0[:, perm].contiguous().view(torch.int32)).any(-1).double().mean().item()
+        assert differ < 1e-4, (E, Nh, "permutation", differ)

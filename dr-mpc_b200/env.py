@@ -53,7 +53,8 @@ class BatchedHAAndPTEnv:
     def __init__(self, config_master=None, num_envs=None, seed_addition=0, device="cuda:0", **overrides):
         import torch
         if isinstance(config_master, EngineConfig):
-            cfg = config_master
+            import dataclasses
+            cfg = dataclasses.replace(config_master)    # the caller's object is not modified (num_envs / seed_addition below)
             for k, v in overrides.items():
                 setattr(cfg, k, v)
             self.config_master = None

@@ -57,3 +57,15 @@ def test_python_mirror_raises_on_failure():
     from dr_mpc_b200 import _lib
     with pytest.raises(_lib.DreError):
         d.BatchedHAAndPTEnv(d.EngineConfig(num_humans=65), num_envs=4)
+
+
+def test_env_does_not_modify_the_callers_config():
+    """Two envs built from ONE EngineConfig with different seed additions / sizes: the object the caller holds keeps its
+    values (the reference builds several envs from one ConfigMaster the same way, online_continuous_task.py:39)."""
+    import dr_mpc_b200 as d
+    cfg = d.EngineConfig(num_humans=5)
+    seed, n = cfg.seed, cfg.num_envs
+    a = d.BatchedHAAndPTEnv(cfg, num_envs=8, seed_addition=3)
+    b = d.BatchedHAAndPTEnv(cfg, num_envs=16, seed_addition=3, soft_reset_on_device=True)
+    assert (cfg.seed, cfg.num_envs, cfg.soft_reset_on_device) == (seed, n, False)
+    assert a.cfg.seed == b.cfg.seed == seed + 3 and (a.E, b.E) == (8, 16) and b.cfg.soft_reset_on_device

@@ -225,3 +225,98 @@ def test_two_rank_gloo_sharding_equals_single_process(oracle, tmp_path):
         assert np.array_equal(z["hpos"], a["hpos"][sl]) and np.array_equal(z["hgoal"], a["hgoal"][sl]) and np.array_equal(z["rewards"], a["rewards"][sl])
         assert np.array_equal(z["C"], C.numpy()) and np.allclose(z["S"], S.numpy(), rtol=1e-12)
     assert C[0] == TOTAL * STEPS
+
+
+# Golden solves on which the host build of the product header takes another LM branch than the reference did (explicit list;
+# 1 of 583). F10 #8 is a FAILING first solve after a reset whose accept / reject sequence sits on a threshold: the host build
+# (g++, no FMA contraction, another operation order than the oracle) finds an acceptable step where the reference raised and
+# retried. The oracle and the cooperative CUDA kernel reproduce the reference on it; the test below shows the reference's own
+# sequence flips under a 1e-13 perturbation of the input.
+HOST_ALLOWED_DIVERGENT = {"F10": (8,)}
+
+
+@pytest.mark.parametrize("K", [4, 10, 20, 40])
+def test_device_mpc_header_on_host_matches_reference_golden(golden_mpc, K):
+    """PRODUCT code on the CPU: the per-problem LM routine of dr-mpc_b200/csrc/mpc_device.cuh (the semantic reference the
+    cooperative kernel is tested against on the GPU, and what DRE_MPC_SERIAL=1 runs there), compiled for the host, on every
+    golden solve the reference's own MPC.act produced -- teacher-forced warm starts, all four paths, theta-wrap node, end-of-path
+    clamping -- and, for K = 4 / 10, on the forced-failure solves that went through `pose_error_scaling *= 5` (mpc.py:188-190).
+    Same bar as the GPU test: every solve within 1e-6, outer-iteration and retry counts equal, except the explicitly listed
+    chaotic solve (HOST_ALLOWED_DIVERGENT)."""
+    import dr_mpc_b200._lib as L
+    from dr_mpc_b200.mpc import MPC_STATUS_DTYPE
+    hh = os.path.join(REPO, "tests", "host_harness")
+    so = os.path.join(hh, "libmpc_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include",
+                           "-o", so, os.path.join(hh, "mpc_host.cpp")])
+    lib = ctypes.CDLL(so)
+    g = golden_mpc
+    _, tab, lens = mpc_path_table(g)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    prm = L.MpcParams(K, 0.25, 1.0, 1.0, 0.2, 1500, 1e-4, 1e-4, 0, 20)
+    for tag in ("K", "F") if K in (4, 10) else ("K",):
+        k = f"{tag}{K}"
+        n = g[f"{k}_u"].shape[0]
+        wT = np.ascontiguousarray(g[f"{k}_warm_T"], dtype=np.float64).copy()
+        wu = np.ascontiguousarray(g[f"{k}_warm_u"], dtype=np.float64).copy()
+        it0 = np.ascontiguousarray(g[f"{k}_it0"]).astype(np.uint8)
+        pid = np.ascontiguousarray(g[f"{k}_path_id"], dtype=np.int32)
+        idx = np.ascontiguousarray(g[f"{k}_interp"], dtype=np.float64)
+        pose = np.ascontiguousarray(g[f"{k}_pose"], dtype=np.float64)
+        u = np.zeros((n, 2 * K))
+        st = np.zeros(n, dtype=MPC_STATUS_DTYPE)
+        assert lib.host_mpc_act(ctypes.byref(prm), n, p(tab), tab.shape[2], p(lens), p(pid), p(idx), p(pose), p(wT), p(wu), p(it0), p(u), p(st)) == 0
+        d = np.abs(u - g[f"{k}_u"]).max(axis=1)
+        ok = np.ones(n, dtype=bool)
+        ok[list(HOST_ALLOWED_DIVERGENT.get(k, ()))] = False
+        print(f"{k}: {n} solves, max|du| = {d[ok].max():.2e}, listed divergent: {np.nonzero(~ok)[0].tolist()}")
+        assert d[ok].max() <= 1e-6, (k, np.nonzero(d > 1e-6)[0], d.max())
+        assert np.array_equal(st["iterations"][ok], g[f"{k}_iters"][ok]) and (st["term"] > 0).all()
+        if tag == "F":
+            assert np.array_equal(st["retries"][ok], g[f"{k}_retries"][ok]) and (st["retries"][ok] >= 1).all()
+        assert np.allclose(st["final_cost"][ok], g[f"{k}_cost"][ok], rtol=1e-6, atol=1e-9)
+        for i in np.nonzero(~ok)[0]:
+            # a listed solve must be one on which the REFERENCE's own decision sequence is unstable: the oracle (which reproduces
+            # the golden on it) flips its LM branch under 1e-13 perturbations of the pose
+            from oracle import oracle as O
+            rng, flips = np.random.default_rng(int(i)), 0
+            for _ in range(60):
+                mb = O.MpcBatch(1, O.mpc_params(K=K), tab, lens)
+                mb.warm_T[:] = g[f"{k}_warm_T"][i:i + 1]; mb.warm_u[:] = g[f"{k}_warm_u"][i:i + 1]; mb.iteration0[:] = g[f"{k}_it0"][i:i + 1]
+                _, so = mb.act(pid[i:i + 1], idx[i:i + 1], pose[i:i + 1] + rng.uniform(-1e-13, 1e-13, (1, 3)))
+                flips += int(so["retries"][0] != g[f"{k}_retries"][i] or so["iterations"][0] != g[f"{k}_iters"][i])
+            assert flips >= 6, (k, int(i), flips)             # measured: 70 of 200
+
+
+def test_robot_half_blocks_on_host_match_reference_rollout(golden_env, golden_mpc):
+    """PRODUCT code on the CPU: the robot / path building blocks pt_step_kernel is made of (dr-mpc_b200/csrc/env_device.cuh:
+    unicycle_step, localize_on_path, pt_state_gen), compiled for the host, on all 640 transitions the reference's own
+    HAAndPTEnv.step recorded: post pose = exact-arc step of (pre pose, executed action) <= 1e-12 (agent.py:169-176,
+    unicycle.py:89-126); 100-d PT state at the post pose <= 1e-9 (path_tracking_core.py:21-81,94-145). Measured: 4e-16 / 9e-16."""
+    hh = os.path.join(REPO, "tests", "host_harness")
+    so = os.path.join(hh, "libenv_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include",
+                           "-o", so, os.path.join(hh, "env_host.cpp")])
+    lib = ctypes.CDLL(so)
+    g = golden_env
+    _, tab, lens = mpc_path_table(golden_mpc)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    total = 0
+    for tag in ("h6", "h10", "h20"):
+        pre = np.ascontiguousarray(g[f"{tag}_pre_rpose"][:, :3])
+        post = np.ascontiguousarray(g[f"{tag}_post_rpose"][:, :3])
+        act = np.ascontiguousarray(g[f"{tag}_out_action"])
+        T = pre.shape[0]
+        total += T
+        out = np.zeros((T, 3))
+        assert lib.host_unicycle(T, p(pre), p(act), ctypes.c_double(0.25), p(out)) == 0
+        assert np.abs(out - post).max() <= 1e-12, (tag, np.abs(out - post).max())
+        pid = np.ascontiguousarray(g[f"{tag}_post_path_idx"].astype(np.int32))
+        lts = np.ascontiguousarray(g[f"{tag}_post_loc_to_start"].astype(np.uint8))
+        idx, pt = np.zeros(T), np.zeros((T, 100))
+        assert lib.host_pt_state(T, p(post), p(pid), p(lts), p(tab), tab.shape[2], p(lens), 20, 5, p(idx), p(pt)) == 0
+        assert np.abs(pt - g[f"{tag}_out_pt_state"]).max() <= 1e-9, (tag, np.abs(pt - g[f"{tag}_out_pt_state"]).max())
+        assert (idx >= 0).all() and (idx <= lens[pid] - 1).all()                    # a fractional node index of the env's own path
+    assert total == 640

@@ -14,6 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The suite needs dr-mpc_b200/libdre.so (built artefacts are not in git). The driver builds it with
+    __graft_entry__.build() before the tests; a fresh clone gets the same build here (nvcc cross-compiles without a GPU).
+    This builds the PRODUCT, it is not a fallback: without nvcc the library stays missing and the tests that load it fail loudly."""
+    so = os.path.join(REPO, "dr-mpc_b200", "libdre.so")
+    if not os.path.exists(so):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            import __graft_entry__ as g
+            g.build()
+    yield
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O

@@ -8,16 +8,21 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
 #include <functional>
 #include <vector>
 
+// (C++17 inline variables: ONE emulator state for all translation units of the emulated library)
 namespace emu {
 constexpr int MAXT = 1024;
-constexpr size_t STACK_BYTES = 384 * 1024;
+constexpr size_t STACK_BYTES = 512 * 1024;
 struct Lane {
     ucontext_t ctx;
     char *stack = nullptr;
@@ -27,17 +32,17 @@ struct Bar {
     int arrived = 0;
     unsigned gen = 0;
 };
-static Lane lanes[MAXT];
-static ucontext_t main_ctx;
-static int cur = 0, NT = 0, alive = 0;
-static uint64_t slot[MAXT];
-static unsigned exited[MAXT / 32];          // per warp: lanes that have returned from the kernel
-static Bar group_bar[MAXT], named_bar[16], cta_bar;
-static int or_acc[3] = {0, 0, 0};
-static uint3 tid3_v, bid3_v;
-static dim3 gdim_v(1, 1, 1), bdim_v(1, 1, 1);
-static unsigned char *dyn_smem = nullptr;
-static const std::function<void()> *body = nullptr;
+inline Lane lanes[MAXT];
+inline ucontext_t main_ctx;
+inline int cur = 0, NT = 0, alive = 0;
+inline uint64_t slot[MAXT];
+inline unsigned exited[MAXT / 32];          // per warp: lanes that have returned from the kernel
+inline Bar group_bar[MAXT], named_bar[16], cta_bar;
+inline int or_acc[3] = {0, 0, 0};
+inline uint3 tid3_v, bid3_v;
+inline dim3 gdim_v(1, 1, 1), bdim_v(1, 1, 1);
+inline unsigned char *dyn_smem = nullptr;
+inline const std::function<void()> *body = nullptr;
 
 inline void yield() { swapcontext(&lanes[cur].ctx, &main_ctx); }
 // every waiter re-evaluates the release condition: threads that exit while others wait are never waited for
@@ -95,6 +100,24 @@ struct Launcher {
     void operator()(const std::function<void()> &f) const
     {
         const int nt = (int)(block.x * block.y * block.z);
+        static const bool trace = getenv("DRE_EMU_TRACE") != nullptr;
+        if (trace) {
+            fprintf(stderr, "[emu] launch grid %u block %d smem %zu\n", grid.x, nt, smem);
+            static bool handler = false;
+            if (!handler) {
+                handler = true;
+                static char alt[64 * 1024];
+                stack_t ss; ss.ss_sp = alt; ss.ss_size = sizeof alt; ss.ss_flags = 0;
+                sigaltstack(&ss, nullptr);
+                struct sigaction sa; memset(&sa, 0, sizeof sa);
+                sa.sa_flags = SA_ONSTACK | SA_SIGINFO;
+                sa.sa_sigaction = [](int, siginfo_t *si, void *) {
+                    fprintf(stderr, "[emu] SIGSEGV at address %p, emulated thread %d of block %u\n", si->si_addr, cur, bid3_v.x);
+                    void *bt[48]; const int n = backtrace(bt, 48); backtrace_symbols_fd(bt, n, 2); _exit(139);
+                };
+                sigaction(SIGSEGV, &sa, nullptr);
+            }
+        }
         if (nt < 1 || nt > MAXT) abort();
         std::vector<unsigned char> sm(smem + 64, 0);
         dyn_smem = reinterpret_cast<unsigned char *>(((uintptr_t)sm.data() + 63) & ~(uintptr_t)63);
@@ -247,6 +270,9 @@ template <int G> inline thread_block_tile<G> tiled_partition(const thread_block 
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))   // crt/host_defines.h leaves it to nvcc under GCC
 #endif
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
 #ifndef __grid_constant__
 #define __grid_constant__
 #endif
@@ -254,3 +280,6 @@ template <int G> inline thread_block_tile<G> tiled_partition(const thread_block 
 #define blockIdx (emu::bid3_v)
 #define gridDim (emu::gdim_v)
 #define blockDim (emu::bdim_v)
+// __shared__ variables of a kernel: one CTA runs at a time, so a function-level static is the CTA's shared memory
+#undef __shared__
+#define __shared__ static

@@ -1,0 +1,246 @@
+"""CPU: the WHOLE product library on an emulated GPU. tests/host_harness/gen_emu.py compiles every translation unit of
+dr-mpc_b200/csrc -- the C ABI, the host pipelines and every CUDA kernel -- for the host after a handful of mechanical rewrites
+(launch syntax, dynamic shared memory, two PTX lines), against a SIMT emulator (simt_emu.h: a CTA's threads are coroutines, warp /
+CTA collectives are barrier exchanges) and a stand-in for the CUDA runtime calls of the host code (fake_cudart.h). The tests below
+call the REAL `dre_*` entry points of that build and hold them to the GPU suite's bars on the reference's golden fixtures: what the
+B200 executes -- pt_step_kernel, ha_step_kernel with both fused ORCA passes, mpc_coop_kernel, env_reset_kernel, cvmm_filter_kernel,
+the soft-reset machine, the chunk-flag host pipeline -- executes here, thread for thread.
+
+This is test infrastructure (nothing of it is shipped, the product path is the CUDA build and fails loudly without it); its point
+is that the `-m "not gpu"` run already exercises the product's own kernels end to end. The B200 runs of the same fixtures are in
+tests/test_gpu_*.py."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ORCA_KEYS, REPO, mpc_path_table
+import emu_driver as E_
+
+
+@pytest.fixture(scope="module")
+def L():
+    return E_.lib()
+
+
+def test_emulated_build_is_the_whole_c_abi(L):
+    """every function include/dre.h declares is exported by the emulated build too (it IS the product's source, all six units)"""
+    hdr = open(os.path.join(REPO, "include", "dre.h")).read()
+    names = sorted(set(re.findall(r"\b(dre_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.dre_version() >= 100
+
+
+@pytest.mark.parametrize("lanes", [0, 8, 32])
+def test_orca_predict_kernels_bit_exact_on_golden(L, golden_orca, lanes):
+    """dre_orca_predict -> orca_predict_kernel<G> (auto / 8 / 32 lanes per agent) on all 248 golden crowds"""
+    from dr_mpc_b200.config import EngineConfig
+    g = golden_orca
+    for key in ORCA_KEYS:
+        hpos, hvel = np.ascontiguousarray(g[key + "_hpos"]), np.ascontiguousarray(g[key + "_hvel"])
+        goal, rpos = np.ascontiguousarray(g[key + "_goal"]), np.ascontiguousarray(g[key + "_rpos"])
+        n, Nh, _ = hpos.shape
+        prm = EngineConfig(group_lanes=lanes).orca_params()
+        v = np.zeros((n, Nh, 2), np.float32)
+        E_.check(L.dre_orca_predict(ctypes.byref(prm), n, Nh, E_.ptr(hpos), E_.ptr(hvel), E_.ptr(goal), E_.ptr(rpos), None, E_.ptr(v), None, None))
+        assert np.array_equal(v.view(np.uint32), g[key + "_vnew"].view(np.uint32)), (key, lanes)
+
+
+@pytest.mark.parametrize("key", ["K4", "F4", "K10", "F10", "K20", "K40"])
+def test_mpc_act_host_on_golden(L, golden_mpc, key):
+    """dre_mpc_create / set_paths / set_warm / act_host -> the persistent mpc_coop_kernel on a multi-CTA grid"""
+    import dr_mpc_b200._lib as LL
+    from dr_mpc_b200.mpc import MPC_STATUS_DTYPE
+    g = golden_mpc
+    K = int(key[1:])
+    _, tab, lens = mpc_path_table(g)
+    n = g[f"{key}_u"].shape[0]
+    prm = LL.MpcParams(K, 0.25, 1.0, 1.0, 0.2, 1500, 1e-4, 1e-4, 0, 20)
+    h = ctypes.c_void_p()
+    E_.check(L.dre_mpc_create(ctypes.byref(prm), n, ctypes.byref(h)))
+    try:
+        E_.check(L.dre_mpc_set_paths(h, E_.ptr(tab), 4, tab.shape[2], E_.ptr(lens)))
+        wT, wu = np.ascontiguousarray(g[f"{key}_warm_T"], dtype=np.float64), np.ascontiguousarray(g[f"{key}_warm_u"], dtype=np.float64)
+        it0 = np.ascontiguousarray(g[f"{key}_it0"]).astype(np.uint8)
+        E_.check(L.dre_mpc_set_warm(h, E_.ptr(wT), E_.ptr(wu), E_.ptr(it0)))
+        pid, idx = np.ascontiguousarray(g[f"{key}_path_id"], dtype=np.int32), np.ascontiguousarray(g[f"{key}_interp"], dtype=np.float64)
+        pose = np.ascontiguousarray(g[f"{key}_pose"], dtype=np.float64)
+        u, st = np.zeros((n, 2 * K)), np.zeros(n, dtype=MPC_STATUS_DTYPE)
+        E_.check(L.dre_mpc_act_host(h, E_.ptr(pid), E_.ptr(idx), E_.ptr(pose), E_.ptr(u), E_.ptr(st)))
+    finally:
+        L.dre_mpc_destroy(h)
+    ok = np.ones(n, dtype=bool)
+    if key == "F10":
+        ok[8] = False                          # the listed chaotic solve (tests/test_host.py: HOST_ALLOWED_DIVERGENT)
+    d = np.abs(u - g[f"{key}_u"]).max(1)
+    assert d[ok].max() <= 1e-6 and np.array_equal(st["iterations"][ok], g[f"{key}_iters"][ok]) and (st["term"] > 0).all()
+    if key[0] == "F":
+        assert np.array_equal(st["retries"][ok], g[f"{key}_retries"][ok])
+
+
+@pytest.mark.parametrize("tag,Nh,count", [("h6", 6, 500), ("h10", 10, 90), ("h20", 20, 50)])
+def test_env_step_matches_reference_teacher_forced(golden_env, tag, Nh, count):
+    """tests/test_gpu_env.py::test_step_matches_reference_teacher_forced on the emulated build: every recorded transition of the
+    reference's own HAAndPTEnv.step is one env of a batch -- upload the reference's pre-step state, ONE dre_env_step (pt_step,
+    ha_step with both ORCA passes, the MPC solve next to it), compare observations / rewards / done reasons / post-step state."""
+    g = golden_env
+    T = min(count, g[f"{tag}_out_action"].shape[0])
+    sel = slice(0, T)
+    env = E_.EmuEnv(T, num_humans=Nh, auto_path_switch=False)
+    env.reset()
+    env.upload(g, tag, "pre", sel)
+    o = env.step(g[f"{tag}_out_action"][sel])
+    st = env.state
+    assert np.array_equal(st["hvel"].view(np.uint32), g[f"{tag}_post_hvel"][sel].view(np.uint32))
+    assert np.abs(st["hpos"] - g[f"{tag}_post_hpos"][sel]).max() <= 1e-12
+    assert np.abs(st["hhist"] - g[f"{tag}_post_hhist"][sel]).max() <= 1e-12
+    assert np.array_equal(st["hvalid"], g[f"{tag}_post_hvalid"][sel])
+    assert np.abs(st["rpose"][:, :3] - g[f"{tag}_post_rpose"][sel][:, :3]).max() <= 1e-12
+    assert np.abs(st["rhist"][:, :, :3] - g[f"{tag}_post_rhist"][sel][:, :, :3]).max() <= 1e-12
+    assert np.abs(st["rpastv"] - g[f"{tag}_post_rpastv"][sel]).max() <= 1e-15
+    assert np.abs(st["gtime"] - g[f"{tag}_post_gtime"][sel]).max() <= 1e-12
+    assert np.array_equal(st["loc_to_start"], g[f"{tag}_post_loc_to_start"][sel])
+    changed = np.abs(g[f"{tag}_post_hgoal"][sel] - g[f"{tag}_pre_hgoal"][sel]).max(-1) > 0
+    assert np.array_equal(st["hgoal"][~changed], g[f"{tag}_post_hgoal"][sel][~changed])
+    for name, tol in (("pt_state", 1e-9), ("robot_node", 1e-9), ("past_robot_vel", 1e-15), ("percent_episode", 1e-12),
+                      ("spatial_edges", 1e-9), ("human_valid", 0), ("detected_humans", 0)):
+        ref = g[f"{tag}_out_{name}"][sel].reshape(o[name].shape)
+        assert np.abs(o[name] - ref).max() <= tol, name
+    assert np.abs(o["rewards"] - g[f"{tag}_out_rewards"][sel]).max() <= 1e-9
+    for col, name in enumerate(("disturbance_v", "disturbance_th", "path_advancement", "deviation")):
+        assert np.abs(o["info"][:, col] - g[f"{tag}_out_{name}"][sel]).max() <= 1e-9, name
+    bits = g[f"{tag}_out_bits"][sel].astype(np.int64)
+    assert np.array_equal(o["done_bits"] & 0xFF, bits & 0xFF)
+    fl = env.flags()
+    assert np.array_equal(fl["done_HA"], g[f"{tag}_out_done_HA"][sel].astype(bool)) and np.array_equal(fl["done_PT"], g[f"{tag}_out_done_PT"][sel].astype(bool))
+    assert np.array_equal(fl["done"], (bits & 0xFF) != 0) and np.array_equal(fl["success"], (bits & 16) != 0)
+    d = np.abs(o["mpc_actions"] - g[f"{tag}_out_mpc_actions"][sel]).max(1)
+    assert d.max() <= 1e-6, d.max()
+
+
+@pytest.mark.parametrize("tag,Nh", [("h6", 6), ("h10", 10), ("h20", 20)])
+def test_env_reset_matches_reference(golden_env, tag, Nh):
+    """dre_env_reset: env_reset_kernel, the first MPC solve and the six warm-start passes of ha_step_kernel, from the reference's spawn"""
+    g = golden_env
+    env = E_.EmuEnv(3, num_humans=Nh, end_goal_changing=False)
+    o = env.reset(np.broadcast_to(g[f"{tag}_reset_hpos"], (3, Nh, 2)).copy(), np.broadcast_to(g[f"{tag}_reset_hgoal"], (3, Nh, 2)).copy())
+    st = env.state
+    assert np.array_equal(st["hvel"][0].view(np.uint32), g[f"{tag}_postreset_hvel"].view(np.uint32))
+    assert np.abs(st["hpos"][0] - g[f"{tag}_postreset_hpos"]).max() <= 1e-12
+    assert np.abs(st["hhist"][0] - g[f"{tag}_postreset_hhist"]).max() <= 1e-12
+    assert np.abs(st["rhist"][0, :, :3] - g[f"{tag}_postreset_rhist"][:, :3]).max() <= 1e-12
+    assert st["rvalid"][0] == g[f"{tag}_postreset_rvalid"] and np.array_equal(st["hvalid"][0], g[f"{tag}_postreset_hvalid"])
+    for name, tol in (("pt_state", 1e-9), ("robot_node", 1e-9), ("past_robot_vel", 0), ("percent_episode", 0), ("spatial_edges", 1e-9),
+                      ("human_valid", 0), ("mpc_actions", 1e-6)):
+        ref = g[f"{tag}_reset_{name}"].reshape(o[name][0].shape)
+        assert np.abs(o[name][0] - ref).max() <= tol, name
+    assert (o["pt_state"][0] == o["pt_state"][2]).all()
+
+
+@pytest.mark.parametrize("tag,Nh,count", [("h6", 6, 10 ** 6), ("h10", 10, 10 ** 6), ("h6s", 6, 10 ** 6)])
+def test_soft_reset_machine_follows_reference(tag, Nh, count):
+    """tests/test_gpu_soft_reset.py on the emulated build: the device-side machine (pt_step_kernel: soft_reset_decide) has to walk,
+    from its own done bits, through the waits / back-ups / turns / creeps the reference's HAAndPTEnv.soft_reset issued; the physical
+    state is teacher-forced before every call, the machine's state is not."""
+    g = np.load(os.path.join(GOLDEN, "soft_reset.npz"))
+    T = min(count, g[f"{tag}_action"].shape[0])
+    env = E_.EmuEnv(1, num_humans=Nh, soft_reset_on_device=True)
+    env.reset()
+    kinds = {"caller": 0, "wait": 0, "backup": 0, "turn": 0, "creep": 0}
+    for t in range(T):
+        env.upload(g, tag, "pre", slice(t, t + 1))
+        soft, ref_a = bool(g[f"{tag}_soft"][t]), g[f"{tag}_action"][t]
+        o = env.step(np.array([[0.777, -0.555]]) if soft else ref_a[None])      # a scripted call gets a poison action from the caller
+        fl = env.flags()
+        assert bool(fl["soft_reset"][0]) == soft, (t, "scripted flag")
+        assert np.array_equal(o["actions_used"][0], ref_a), (t, o["actions_used"][0], ref_a)
+        assert not fl["soft_reset_stuck"][0]
+        assert (int(o["done_bits"][0]) & 0xFF) == (int(g[f"{tag}_bits"][t]) & 0xFF), t
+        assert np.abs(o["rewards"][0] - g[f"{tag}_rewards"][t]).max() <= 1e-9, t
+        assert np.abs(env.state["rpose"][0, :3] - g[f"{tag}_post_rpose"][t, :3]).max() <= 1e-12
+        assert np.array_equal(env.state["hvel"][0].view(np.uint32), g[f"{tag}_post_hvel"][t].view(np.uint32))
+        kinds["caller" if not soft else "backup" if ref_a[0] == -0.3 else "creep" if ref_a[0] == 0.5 else "turn" if ref_a[1] != 0 else "wait"] += 1
+    print(tag, T, "calls", kinds)
+    assert kinds["caller"] > 0 and kinds["wait"] > 0
+    if tag == "h6":
+        assert kinds["turn"] > 0 and kinds["creep"] > 0
+    if tag == "h6s":
+        assert kinds["backup"] > 20
+
+
+@pytest.mark.parametrize("tag,Nh", [("h6", 6), ("h10", 10)])
+def test_cvmm_filter_matches_reference(tag, Nh):
+    """dre_env_cvmm_filter -> cvmm_filter_kernel (one warp per env, lane = candidate) on the recorded queries of the reference's
+    cvmm_diverse_safety_pipeline: per-candidate safety flags and the selected action exact"""
+    g = np.load(os.path.join(GOLDEN, "cvmm.npz"))
+    Q = g[f"{tag}_action"].shape[0]
+    sel = slice(0, Q)
+    env = E_.EmuEnv(Q, num_humans=Nh)
+    env.reset()
+    for name in E_.STATE:
+        env.state[name][...] = np.asarray(g[f"{tag}_pre_{name}"][sel]).reshape(env.state[name].shape)
+    before = {k: v.copy() for k, v in env.state.items()}
+    out, info = env.cvmm(g[f"{tag}_action"][sel], int(g["lookahead_steps"]), g["action_set"])
+    assert np.array_equal(info["candidate_safe"], g[f"{tag}_cand_safe"][sel])
+    rnd = g[f"{tag}_random"][sel].astype(bool)
+    assert np.array_equal(info["random"].astype(bool), rnd)
+    assert np.array_equal(out[~rnd], g[f"{tag}_safe_action"][sel][~rnd])
+    kept = info["chosen"] == -1
+    assert np.array_equal(kept, g[f"{tag}_cand_safe"][sel][:, 0].astype(bool)) and np.array_equal(out[kept], g[f"{tag}_action"][sel][kept])
+    for k, v in env.state.items():
+        assert np.array_equal(v, before[k]), k                                   # a pure query
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_step_host_pipeline_equals_device_step(chunks):
+    """dre_env_step_host (one crowd-half launch whose CTAs raise chunk flags in mapped host memory, the host thread polling them
+    and queueing each chunk's copy) returns the device step's slab bit for bit, for a ragged chunking"""
+    Ee, Nh = 75, 7
+    a_env, b_env = E_.EmuEnv(Ee, num_humans=Nh), E_.EmuEnv(Ee, num_humans=Nh)
+    b_env.set_host_chunks(chunks)
+    act = a_env.reset()["mpc_actions"][:, :2].copy()
+    b_env.reset()
+    for t in range(3):
+        oa = a_env.step(act)
+        ob = b_env.step_host(act)
+        for name in oa:
+            assert np.array_equal(oa[name].view(np.uint8), ob[name].view(np.uint8)), (t, name)
+        for name in ("hpos", "hvel", "hgoal", "rpose", "hhist"):
+            assert np.array_equal(a_env.state[name], b_env.state[name]), (t, name)
+        act = oa["mpc_actions"][:, :2].copy()
+
+
+def test_free_run_double_buffer_masked_reset_and_sharding():
+    """a short free run on the emulated build: outputs finite, the slab alternates (S of step t-1 intact while S' of step t exists),
+    a masked reset touches only its envs, and two shards keyed by the global env id equal the unsharded batch bit for bit"""
+    Ee, Nh = 48, 6
+    env = E_.EmuEnv(Ee, num_humans=Nh)
+    S0 = env.reset()
+    first = {k: v.copy() for k, v in S0.items()}
+    a = S0["mpc_actions"][:, :2].copy()
+    o1 = env.step(a)
+    assert o1 is not S0 and all(np.array_equal(S0[k], first[k]) for k in first)      # the reset slab survived the step
+    for _ in range(4):
+        o1 = env.step(o1["mpc_actions"][:, :2].copy())
+    assert np.isfinite(o1["rewards"]).all() and np.isfinite(o1["spatial_edges"]).all() and (env.state["step_count"] == 5).all()
+    keep = {k: v.copy() for k, v in env.state.items()}
+    mask = np.zeros(Ee, np.uint8)
+    mask[::3] = 1
+    env.reset(env_mask=mask)
+    on = mask.astype(bool)
+    assert (env.state["step_count"][on] == 0).all() and np.array_equal(env.state["step_count"][~on], keep["step_count"][~on])
+    assert np.array_equal(env.state["hpos"][~on], keep["hpos"][~on]) and not np.array_equal(env.state["hpos"][on], keep["hpos"][on])
+    # sharding: envs [0, 20) and [20, 48) as separate handles with env_id_offset == one handle of 48
+    whole = E_.EmuEnv(Ee, num_humans=Nh, seed=7)
+    parts = [E_.EmuEnv(20, num_humans=Nh, seed=7, env_id_offset=0), E_.EmuEnv(28, num_humans=Nh, seed=7, env_id_offset=20)]
+    ow = whole.reset()
+    op = [p.reset() for p in parts]
+    for _ in range(3):
+        ow = whole.step(ow["mpc_actions"][:, :2].copy())
+        op = [p.step(o["mpc_actions"][:, :2].copy()) for p, o in zip(parts, op)]
+    for name in ("spatial_edges", "rewards", "pt_state", "done_bits"):
+        assert np.array_equal(ow[name], np.concatenate([o[name] for o in op])), name

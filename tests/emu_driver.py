@@ -163,3 +163,67 @@ class EmuEnv:
         cand = np.zeros((self.E, bk.shape[0] + 1), dtype=np.uint8)
         check(self.L.dre_env_cvmm_filter(self.h, ptr(a), int(num_steps), ptr(bk), int(bk.shape[0]), ptr(out), ptr(info), ptr(cand), None))
         return out, {"original_safe": info[:, 0], "num_safe": info[:, 1], "chosen": info[:, 2], "random": info[:, 3], "candidate_safe": cand}
+
+    def mpc_get_warm(self):
+        m = self.L.dre_env_mpc(self.h)
+        K = self.cfg.horizon
+        T, u, it0 = np.empty((self.E, K, 4)), np.empty((self.E, K, 2)), np.empty(self.E, dtype=np.uint8)
+        check(self.L.dre_mpc_get_warm(m, ptr(T), ptr(u), ptr(it0)))
+        return T, u, it0
+
+    def invalidate_orca_cache(self):
+        check(self.L.dre_env_invalidate_orca_cache(self.h, None))
+
+
+OBS_KEYS = ("pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
+
+
+class EmuReplay:
+    """DeviceReplayBuffer's calls (dr_mpc_b200/replay.py) on the emulated library: dre_replay_create / insert / sample / count."""
+
+    def __init__(self, env, capacity, dtype=np.float64):
+        self.env, self.cap, self.dtype = env, int(capacity), np.dtype(dtype)
+        self.L, self.LL = env.L, env.LL
+        code = 0 if self.dtype == np.float64 else 1
+        self.h = ctypes.c_void_p()
+        check(self.L.dre_replay_create(env.h, self.cap, code, ctypes.byref(self.h)))
+        v = self.LL.ReplayView()
+        widths = (ctypes.c_int32 * 8)()
+        nbytes = ctypes.c_size_t()
+        check(self.L.dre_replay_storage(self.h, ctypes.byref(v), widths, ctypes.byref(nbytes)))
+        self.widths = list(widths)
+        self.ring = {"S": {k: view(getattr(v.S, k), (self.cap, w), self.dtype) for k, w in zip(OBS_KEYS, self.widths)},
+                     "S_prime": {k: view(getattr(v.S_prime, k), (self.cap, w), self.dtype) for k, w in zip(OBS_KEYS, self.widths)},
+                     "rewards": view(v.rewards, (self.cap, 1), self.dtype), "actions": view(v.actions, (self.cap, 2), self.dtype),
+                     "done": view(v.done, (self.cap, 1), self.dtype)}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.dre_replay_destroy(self.h)
+            self.h = None
+
+    def insert(self, actions=None, mask=None, skip_scripted=True):
+        a = np.ascontiguousarray(actions, dtype=np.float64) if actions is not None else None
+        m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+        check(self.L.dre_replay_insert(self.h, ptr(a), ptr(m), int(bool(skip_scripted)), None))
+
+    def count(self):
+        v, hd, last = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(self.L.dre_replay_count(self.h, ctypes.byref(v), ctypes.byref(hd), ctypes.byref(last), None))
+        return int(v.value), int(hd.value), int(last.value)
+
+    def sample(self, indices, dtype=None):
+        dt = np.dtype(dtype or self.dtype)
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        n = idx.size
+        b = self.LL.ReplayView()
+        out = {"S": {}, "S_prime": {}}
+        for grp, fields in (("S", b.S), ("S_prime", b.S_prime)):
+            for k, w in zip(OBS_KEYS, self.widths):
+                out[grp][k] = np.zeros((n, w), dtype=dt)
+                setattr(fields, k, out[grp][k].ctypes.data)
+        out["actions"], out["rewards"], out["done"] = np.zeros((n, 2), dt), np.zeros((n, 1), dt), np.zeros((n, 1), dt)
+        b.actions, b.rewards, b.done = out["actions"].ctypes.data, out["rewards"].ctypes.data, out["done"].ctypes.data
+        b.rows, b.dtype = n, 0 if dt == np.float64 else 1
+        check(self.L.dre_replay_sample(self.h, ptr(idx), n, b.dtype, ctypes.byref(b), None))
+        return out

@@ -244,3 +244,146 @@ def test_free_run_double_buffer_masked_reset_and_sharding():
         op = [p.step(o["mpc_actions"][:, :2].copy()) for p, o in zip(parts, op)]
     for name in ("spatial_edges", "rewards", "pt_state", "done_bits"):
         assert np.array_equal(ow[name], np.concatenate([o[name] for o in op])), name
+
+
+@pytest.mark.parametrize("tag,Nh", [("h6", 6), ("h10", 10)])
+def test_sensor_restriction_matches_reference(tag, Nh):
+    """tests/test_gpu_sensor.py on the emulated build: humans beyond sensor_range lose their history and the observation lists the
+    visible ones first (human_avoidance_env.py:53-72,102-105,161-164), step and reset"""
+    g = np.load(os.path.join(GOLDEN, "sensor_restriction.npz"))
+    T = g[f"{tag}_out_action"].shape[0]
+    env = E_.EmuEnv(T, num_humans=Nh, robot_sensor_restriction=True, auto_path_switch=False)
+    env.reset()
+    env.upload(g, tag, "pre")
+    o = env.step(g[f"{tag}_out_action"])
+    st = env.state
+    assert np.array_equal(st["hvalid"], g[f"{tag}_post_hvalid"]) and np.abs(st["hhist"] - g[f"{tag}_post_hhist"]).max() <= 1e-12
+    assert np.array_equal(o["detected_humans"], g[f"{tag}_out_detected_humans"].reshape(-1))
+    assert np.array_equal(o["human_valid"], g[f"{tag}_out_human_valid"].reshape(o["human_valid"].shape))
+    assert np.abs(o["spatial_edges"] - g[f"{tag}_out_spatial_edges"].reshape(o["spatial_edges"].shape)).max() <= 1e-9
+    assert np.abs(o["rewards"] - g[f"{tag}_out_rewards"]).max() <= 1e-9
+    assert (st["hvalid"].sum(1) == 0).any() and ((g[f"{tag}_pre_hvalid"] > 0) & (st["hvalid"] == 0)).any()
+    env2 = E_.EmuEnv(3, num_humans=Nh, robot_sensor_restriction=True)
+    o2 = env2.reset(np.broadcast_to(g[f"{tag}_reset_hpos"], (3, Nh, 2)).copy(), np.broadcast_to(g[f"{tag}_reset_hgoal"], (3, Nh, 2)).copy())
+    assert np.array_equal(o2["detected_humans"], np.full(3, g[f"{tag}_reset_detected_humans"]))
+    assert np.array_equal(o2["human_valid"][0], g[f"{tag}_reset_human_valid"])
+    assert np.abs(o2["spatial_edges"][0] - g[f"{tag}_reset_spatial_edges"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("Ee,Nh,variant", [(64, 20, {}), (24, 50, {}), (40, 12, {"robot_visible": False}), (40, 16, {"neighbor_dist": 3.0}),
+                                           (32, 6, {"horizon": 10}), (10, 6, {"horizon": 40}),
+                                           (64, 6, {"soft_reset_on_device": True, "static_humans": ((-4.0, 0.0), (0.0, 0.0))}),
+                                           (40, 10, {"robot_sensor_restriction": True})])
+def test_free_running_step_matches_oracle(oracle, golden_mpc, Ee, Nh, variant):
+    """tests/test_gpu_env.py::test_step_matches_oracle_at_scale on the emulated build: states the free-running engine itself
+    reaches (Philox spawning and goal resampling, path switches, the soft-reset machine, static humans, the sensor restriction,
+    the 3 m neighbour cut-off variant, horizons on 16-lane and two-warp groups) are copied into oracle/env_ref.c, both take the
+    same step: velocities bit-exact, positions / goals 1e-12, rewards / observations 1e-9, done reasons and executed actions equal."""
+    _, tab, lens = mpc_path_table(golden_mpc)
+    env = E_.EmuEnv(Ee, num_humans=Nh, **variant)
+    o = env.reset()
+    ov = dict(variant)
+    ref_kw = {k: ov.pop(k) for k in ("neighbor_dist", "static_humans") if k in ov}
+    if "horizon" in ov: ref_kw["K"] = ov.pop("horizon")
+    if "soft_reset_on_device" in ov: ref_kw["soft_reset"] = ov.pop("soft_reset_on_device")
+    if "robot_sensor_restriction" in ov: ref_kw["sensor_restriction"] = ov.pop("robot_sensor_restriction")
+    ref = oracle.EnvRef(Ee, Nh, tab, lens, **ref_kw, **{k: int(v) for k, v in ov.items()})
+    ref.reset()
+    rng = np.random.default_rng(7)
+    checked = lm_div = scripted = 0
+    steps = 90 if variant.get("soft_reset_on_device") else 26
+    for t in range(steps):
+        a = o["mpc_actions"][:, :2] + rng.normal(size=(Ee, 2)) * 0.15
+        a[:, 0] = a[:, 0].clip(0, 1); a[:, 1] = a[:, 1].clip(-1, 1)
+        probe = t % 5 == 3
+        if probe:
+            for k in ("hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime",
+                      "path_idx", "loc_to_start", "step_count", "sr_state"):
+                ref.a[k][...] = env.state[k].reshape(ref.a[k].shape)
+            ref.a["done_bits"][...] = o["done_bits"]
+            ref.a["reset_epoch"][...] = 1
+            ref.a["warm_T"][...], ref.a["warm_u"][...], ref.a["iteration0"][...] = env.mpc_get_warm()
+        o = env.step(a)
+        if not probe:
+            continue
+        r = ref.step(a, nthreads=0)
+        st = env.state
+        assert np.array_equal(st["hvel"].view(np.uint32), r["hvel"].view(np.uint32)), t
+        assert np.abs(st["hpos"] - r["hpos"]).max() <= 1e-12 and np.abs(st["hgoal"] - r["hgoal"]).max() <= 1e-12
+        assert np.abs(st["rpose"][:, :3] - r["rpose"][:, :3]).max() <= 1e-12 and np.array_equal(st["path_idx"], r["path_idx"])
+        assert np.array_equal(o["done_bits"], r["done_bits"]) and np.array_equal(o["actions_used"], r["actions_used"]), t
+        if variant.get("soft_reset_on_device"):
+            assert np.array_equal(o["done_flags"][:, 12], r["soft_flags"][:, 0]) and np.array_equal(st["sr_state"], r["sr_state"]), t
+            scripted += int(r["soft_flags"][:, 0].sum())
+        assert np.array_equal(st["hvalid"], r["hvalid"]) and np.array_equal(o["detected_humans"], r["detected_humans"]), t
+        assert np.abs(o["rewards"] - r["rewards"]).max() <= 1e-9
+        for name in ("pt_state", "robot_node", "past_robot_vel", "spatial_edges", "human_valid"):
+            assert np.abs(o[name] - r[name].reshape(o[name].shape)).max() <= 1e-9, (t, name)
+        stat = o["mpc_status"]
+        same = (stat[:, 0] == r["mpc_status"]["iterations"]) & (stat[:, 2] == r["mpc_status"]["lm_solves"]) & (stat[:, 3] == r["mpc_status"]["cost_evals"])
+        assert np.abs(o["mpc_actions"] - r["mpc_actions"]).max(1)[same].max() <= 1e-6
+        checked += Ee
+        lm_div += int((~same).sum())
+    assert checked >= 5 * Ee and lm_div <= max(2, 0.02 * checked)
+    if variant.get("soft_reset_on_device"):
+        assert scripted > 10
+
+
+@pytest.mark.parametrize("flag", ["orca_dedup", "orca_lookahead_prune"])
+def test_orca_variants_are_bit_identical(flag):
+    """the two opt-in ORCA variants against the reference's two full passes, free-running with goal resamplings: every output
+    and state array equal bit for bit (tests/test_gpu_env.py: test_orca_dedup_is_bit_identical / test_lookahead_prune_is_bit_identical)"""
+    Ee, Nh = 40, 10
+    a_env, b_env = E_.EmuEnv(Ee, num_humans=Nh), E_.EmuEnv(Ee, num_humans=Nh, **{flag: True})
+    oa = a_env.reset()
+    b_env.reset()
+    resampled = 0
+    for t in range(40):
+        act = oa["mpc_actions"][:, :2].copy()
+        g0 = a_env.state["hgoal"].copy()
+        oa, ob = a_env.step(act), b_env.step(act)
+        resampled += int((a_env.state["hgoal"] != g0).any(-1).sum())
+        for k in oa:
+            assert np.array_equal(oa[k].view(np.uint8), ob[k].view(np.uint8)), (t, k)
+        for k in ("hpos", "hvel", "hgoal", "hhist", "rpose", "path_idx"):
+            assert np.array_equal(a_env.state[k], b_env.state[k]), (t, k)
+    assert resampled > 2
+
+
+@pytest.mark.parametrize("Ee,Nh,cap,dtype", [(64, 6, 150, np.float64), (40, 7, 1000, np.float64), (50, 5, 30, np.float32)])
+def test_replay_ring_against_a_numpy_ring(Ee, Nh, cap, dtype):
+    """dre_replay_insert / sample (replay_select_kernel + replay_gather_kernel) against the reference buffer's semantics written
+    out in numpy (storage.py:54-133: rows in insertion order, the oldest rows fall out when full): masked inserts with the
+    soft-reset machine on (scripted steps stay out), wrap-arounds, odd-width fields, an insert larger than the ring, float32 storage"""
+    env = E_.EmuEnv(Ee, num_humans=Nh, soft_reset_on_device=True)
+    rb = E_.EmuReplay(env, cap, dtype)
+    S = {k: v.copy() for k, v in env.reset().items()}
+    rows = []                                    # chronological list of (S, A, S', R, done) rows, the newest `cap` survive
+    rng = np.random.default_rng(Ee)
+    for t in range(12):
+        a = S["mpc_actions"][:, :2].copy()
+        a[:, 1] = (a[:, 1] + 0.4 * np.sin(np.arange(Ee) * 0.37 + t)).clip(-1, 1)      # a sloppy policy: terminations happen
+        o = env.step(a)
+        mask = rng.uniform(size=Ee) < 0.8
+        rb.insert(a, mask)
+        keep = mask & (o["done_flags"][:, 12] == 0)
+        for e in np.nonzero(keep)[0]:
+            rows.append(({k: S[k][e].ravel().copy() for k in E_.OBS_KEYS}, a[e].copy(), {k: o[k][e].ravel().copy() for k in E_.OBS_KEYS},
+                         o["rewards"][e, 2], float(o["done_flags"][e, 3] != 0)))
+        assert rb.count()[2] == min(int(keep.sum()), cap)
+        S = {k: v.copy() for k, v in o.items()}
+    rows = rows[-cap:]
+    valid, head, _ = rb.count()
+    assert valid == len(rows)
+    chron = rb.sample(np.arange(valid))
+    for j, (s, a, sp, r, dn) in enumerate(rows):
+        for k in E_.OBS_KEYS:
+            assert np.array_equal(chron["S"][k][j], s[k].astype(dtype)), (j, k)
+            assert np.array_equal(chron["S_prime"][k][j], sp[k].astype(dtype)), (j, k)
+        assert np.array_equal(chron["actions"][j], a.astype(dtype)) and chron["rewards"][j, 0] == dtype(r) and chron["done"][j, 0] == dn
+    # the ring's own storage holds the same rows at (head + j) % cap once full
+    phys = (np.arange(valid) + (head if valid == cap else 0)) % cap
+    assert np.array_equal(rb.ring["S_prime"]["spatial_edges"][phys], chron["S_prime"]["spatial_edges"])
+    if dtype == np.float64:
+        half = rb.sample(np.arange(valid), dtype=np.float32)
+        assert np.array_equal(half["S"]["pt_state"], chron["S"]["pt_state"].astype(np.float32))

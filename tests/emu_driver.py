@@ -19,7 +19,7 @@ def lib():
         spec = importlib.util.spec_from_file_location("dre_gen_emu", os.path.join(REPO, "tests", "host_harness", "gen_emu.py"))
         gen = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(gen)
-        so = gen.build()
+        so = gen.build(sanitize=os.environ.get("DRE_EMU_SANITIZE") or None)     # tools/emu_memcheck.sh: the same suite under ASan
         import dr_mpc_b200._lib as LL
         saved = (LL.LIB_PATH, LL._lib)
         try:                                   # borrow the product's own prototype table for the emulated binary

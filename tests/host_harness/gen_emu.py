@@ -115,7 +115,12 @@ def generate():
             o.write(f"// GENERATED by tests/host_harness/gen_emu.py from dr-mpc_b200/csrc/{f} -- do not edit, not committed\n" + src)
 
 
-def build(force=False):
+def build(force=False, sanitize=None):
+    """sanitize="address": the same build under AddressSanitizer (tools/emu_memcheck.sh) -- a memcheck of every kernel and of the host
+    code on every fixture: "device" allocations and the dynamic shared memory of each launch are exact-size heap blocks."""
+    global OUT
+    if sanitize:
+        OUT = os.path.join(HH, f"libdre_emu_{sanitize}.so")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HH, f) for f in ("simt_emu.h", "fake_cudart.h", "gen_emu.py")] + \
            [os.path.join(REPO, "include", "dre.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
@@ -126,10 +131,14 @@ def build(force=False):
     # simt_emu.h does it; -ffp-contract=off = the CUDA units' -fmad=false (x86-64 has no contraction anyway)
     flags = ["-O2", "-ffp-contract=off", "-fPIC", "-std=c++17", "-Wno-unknown-pragmas", "-Wno-attributes", "-I/usr/local/cuda/include",
              "-include", os.path.join(HH, "simt_emu.h"), "-include", os.path.join(HH, "fake_cudart.h")]
+    link = []
+    if sanitize:
+        flags = ["-O1" if f == "-O2" else f for f in flags] + ["-g", "-fno-omit-frame-pointer", f"-fsanitize={sanitize}"]
+        link = [f"-fsanitize={sanitize}"]
     procs = []
     for u in UNITS:
         cpp = os.path.join(GEN, u.replace(".cu", ".cpp"))
-        obj = cpp.replace(".cpp", ".o")
+        obj = cpp.replace(".cpp", f".{sanitize or 'plain'}.o")
         procs.append((u, obj, subprocess.Popen([cxx] + flags + ["-c", cpp, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for u, obj, p in procs:
@@ -137,9 +146,10 @@ def build(force=False):
         if p.returncode != 0:
             raise RuntimeError(f"emulated build of {u} failed:\n{out[-6000:]}")
         objs.append(obj)
-    subprocess.check_call([cxx, "-shared", "-o", OUT] + objs + ["-ldl"])
+    subprocess.check_call([cxx, "-shared", "-o", OUT] + objs + link + ["-ldl"])
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build(force=True, sanitize=sys.argv[1] if len(sys.argv) > 1 else None))

@@ -159,8 +159,10 @@ struct Launcher {
             }
         }
         if (nt < 1 || nt > MAXT) abort();
-        std::vector<unsigned char> sm(smem + 64, 0);
-        dyn_smem = reinterpret_cast<unsigned char *>(((uintptr_t)sm.data() + 63) & ~(uintptr_t)63);
+        void *sm = nullptr;                     // an exact-size block: an overrun of the launch's shared memory is a heap overrun (ASan build)
+        if (posix_memalign(&sm, 64, smem ? smem : 1) != 0) abort();
+        memset(sm, 0, smem ? smem : 1);
+        dyn_smem = static_cast<unsigned char *>(sm);
         body = &f;
         NT = nt;
         bdim_v = block;
@@ -190,6 +192,8 @@ struct Launcher {
             }
         }
         body = nullptr;
+        dyn_smem = nullptr;
+        free(sm);
     }
 };
 }  // namespace emu

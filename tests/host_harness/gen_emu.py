@@ -9,7 +9,7 @@ match), then compiled with g++ against
   * fake_cudart.h -- the CUDA runtime calls the host code makes (device memory = host memory, streams / events are no-ops).
 Rewrites:
   1. `kernel<<<grid, block, smem, stream>>>(args);`        -> `emu::Launcher(grid, block, smem, stream)([&] { kernel(args); });`
-  2. `extern __shared__ [__align__(n)] T name[];`          -> `T *name = reinterpret_cast<T *>(emu::dyn_smem);`
+  2. `extern __shared__ [__align__(n)] T name[];`          -> `T *name = reinterpret_cast<T *>(emu::shared_base());`
   3. `#include <cooperative_groups.h>` dropped (the two headers above are force-included in front of every unit: g++ -include)
   4. `#if defined(__CUDACC__)` / `__CUDA_ARCH__`           -> the CUDA side of the guard (`#if 1`)
   5. the two inline-PTX statements of mpc_coop.cuh         -> dre_emul_rcp_approx / dre_emul_bar_sync (simt_emu.h)
@@ -85,7 +85,7 @@ def transform(name, src):
     notes = {}
     src, notes["launches"] = rewrite_launches(src)
     src, notes["dyn_smem"] = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];",
-                                     lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(emu::dyn_smem);", src)
+                                     lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(emu::shared_base());", src)
     src, notes["includes"] = re.subn(r"#include <cooperative_groups\.h>\n", "", src)
     src, notes["guards"] = re.subn(r"#if defined\(__CUDACC__\)|#if defined\(__CUDA_ARCH__\)", "#if 1", src)
     for pat, rep in (('asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));', "r = dre_emul_rcp_approx(x);"),

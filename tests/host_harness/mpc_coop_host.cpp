@@ -21,7 +21,7 @@ template <int G> void run_cta(const dre_mpc_params &prm, const CoopBatch &B)
 {
     const size_t smem = ((size_t)CS_SLOTS * DRE_MPC_CTA + (G == 64 ? 64 : 0)) * sizeof(double);
     emu::Launcher(1, DRE_MPC_CTA, smem)([&] {
-        double *coop_smem = reinterpret_cast<double *>(emu::dyn_smem);
+        double *coop_smem = reinterpret_cast<double *>(emu::shared_base());
         LaneGroup<G> g;
         g.attach(coop_smem + CS_SLOTS * DRE_MPC_CTA);   // exchange area of the two-warp groups (K > 32)
         mpc_coop_persistent<G, false>(g, prm, B, coop_smem);

@@ -19,6 +19,21 @@
 #include <functional>
 #include <vector>
 
+// Race check (tools/emu_racecheck.sh): built with -fsanitize=thread, every emulated CUDA thread is a ThreadSanitizer FIBER that is
+// concurrent with all others (switches carry no synchronisation); only what CUDA's memory model orders is annotated as ordering:
+// __syncthreads / __syncthreads_or / __syncwarp / tile.sync() / the named barrier (release on arrival, acquire on exit, among the
+// participants), kernel boundaries (host -> kernel -> host), and atomics (real __atomic operations). Shuffles and ballots exchange
+// VALUES but order no memory, exactly like shfl.sync / vote.sync. The emulator's own bookkeeping is excluded from instrumentation.
+#if defined(__SANITIZE_THREAD__)
+#include <sanitizer/tsan_interface.h>
+#define DRE_EMU_TSAN 1
+#include <sys/mman.h>
+#define DRE_EMU_NOTSAN __attribute__((no_sanitize("thread"), noinline))
+#else
+#define DRE_EMU_TSAN 0
+#define DRE_EMU_NOTSAN
+#endif
+
 // (C++17 inline variables: ONE emulator state for all translation units of the emulated library)
 namespace emu {
 constexpr int MAXT = 1024;
@@ -26,6 +41,7 @@ constexpr size_t STACK_BYTES = 512 * 1024;
 struct Lane {
     ucontext_t ctx;
     void *sp = nullptr;         // x86-64 fast path: the suspended coroutine's stack pointer
+    void *fiber = nullptr;      // ThreadSanitizer build: the fiber that stands for this CUDA thread
     char *stack = nullptr;
     bool done = false;
 };
@@ -46,6 +62,22 @@ inline unsigned char *dyn_smem = nullptr;
 inline const std::function<void()> *body = nullptr;
 
 inline void *main_sp = nullptr;
+inline void *main_fiber = nullptr;
+inline char launch_token, done_token;      // ThreadSanitizer build: kernel boundaries (host writes -> kernel, kernel writes -> host)
+DRE_EMU_NOTSAN inline void tsan_to_lane(int t)
+{
+#if DRE_EMU_TSAN
+    __tsan_switch_to_fiber(lanes[t].fiber, __tsan_switch_to_fiber_no_sync);
+#else
+    (void)t;
+#endif
+}
+DRE_EMU_NOTSAN inline void tsan_to_main()
+{
+#if DRE_EMU_TSAN
+    __tsan_switch_to_fiber(main_fiber, __tsan_switch_to_fiber_no_sync);
+#endif
+}
 #if defined(__x86_64__) && !defined(DRE_EMU_UCONTEXT)
 // A coroutine switch is a dozen instructions: push the callee-saved registers, swap the stack pointer, pop, return. swapcontext
 // does the same plus two sigprocmask system calls per switch, which was a third of the suite's run time.
@@ -61,8 +93,8 @@ __asm__(".text\n"
         "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
         "    ret\n"
         ".size dre_emu_switch, .-dre_emu_switch\n");
-inline void yield() { dre_emu_switch(&lanes[cur].sp, main_sp); }
-inline void resume(int t) { dre_emu_switch(&main_sp, lanes[t].sp); }
+DRE_EMU_NOTSAN inline void yield() { tsan_to_main(); dre_emu_switch(&lanes[cur].sp, main_sp); }
+DRE_EMU_NOTSAN inline void resume(int t) { tsan_to_lane(t); dre_emu_switch(&main_sp, lanes[t].sp); }
 inline void prepare(Lane &L, void (*entry)())
 {
     // [r15 r14 r13 r12 rbx rbp | entry | 0]: after the six pops and the ret, rsp = 8 mod 16 as at any function entry
@@ -74,8 +106,8 @@ inline void prepare(Lane &L, void (*entry)())
     L.sp = sp;
 }
 #else
-inline void yield() { swapcontext(&lanes[cur].ctx, &main_ctx); }
-inline void resume(int t) { swapcontext(&main_ctx, &lanes[t].ctx); }
+DRE_EMU_NOTSAN inline void yield() { tsan_to_main(); swapcontext(&lanes[cur].ctx, &main_ctx); }
+DRE_EMU_NOTSAN inline void resume(int t) { tsan_to_lane(t); swapcontext(&main_ctx, &lanes[t].ctx); }
 inline void prepare(Lane &L, void (*entry)())
 {
     getcontext(&L.ctx);
@@ -86,46 +118,94 @@ inline void prepare(Lane &L, void (*entry)())
 }
 #endif
 // every waiter re-evaluates the release condition: threads that exit while others wait are never waited for
-template <class Expected> inline void barrier(Bar &b, Expected expected)
+// `orders_memory`: a CUDA barrier (bar.sync / __syncwarp) -- the participants' earlier accesses happen before their later ones;
+// false for the rendezvous inside a shuffle / vote, which moves values but orders nothing.
+template <class Expected> DRE_EMU_NOTSAN inline void barrier(Bar &b, Expected expected, bool orders_memory)
 {
     const unsigned gen = b.gen;
+#if DRE_EMU_TSAN
+    if (orders_memory) __tsan_release(&b);
+#endif
     ++b.arrived;
     for (;;) {
-        if (b.gen != gen) return;
-        if (b.arrived >= expected()) { b.arrived = 0; ++b.gen; return; }
+        if (b.gen != gen) break;
+        if (b.arrived >= expected()) { b.arrived = 0; ++b.gen; break; }
         yield();
     }
+#if DRE_EMU_TSAN
+    if (orders_memory) __tsan_acquire(&b);
+#endif
+    (void)orders_memory;
 }
-inline int lane_id() { return cur & 31; }
-inline int warp_base() { return cur & ~31; }
-inline unsigned warp_members()              // lanes of this thread's warp that exist in the CTA
+DRE_EMU_NOTSAN inline int lane_id() { return cur & 31; }
+DRE_EMU_NOTSAN inline int warp_base() { return cur & ~31; }
+DRE_EMU_NOTSAN inline int warp_index() { return cur >> 5; }
+DRE_EMU_NOTSAN inline unsigned warp_members()              // lanes of this thread's warp that exist in the CTA
 {
-    const int n = NT - warp_base();
+    const int n = NT - (cur & ~31);
     return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
 }
-inline Bar &bar_of(unsigned mask) { return group_bar[warp_base() + __builtin_ctz(mask)]; }
-inline void warp_barrier(unsigned mask)
+DRE_EMU_NOTSAN inline unsigned warp_exited() { return exited[cur >> 5]; }
+DRE_EMU_NOTSAN inline void warp_barrier(unsigned mask, bool orders_memory)
 {
-    mask &= warp_members();
+    // positive control of the race check: DRE_EMU_DROP_SYNCWARP=1 makes __syncwarp / tile.sync() wait without ordering memory, as if
+    // the kernels had none -- the accesses they separate must then be reported
+    static const bool drop = getenv("DRE_EMU_DROP_SYNCWARP") != nullptr;
+    if (drop) orders_memory = false;
+    const int n = NT - (cur & ~31);
+    mask &= n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
     const int w = cur >> 5;
-    barrier(bar_of(mask), [mask, w] { return __builtin_popcount(mask & ~exited[w]); });
+    barrier(group_bar[(cur & ~31) + __builtin_ctz(mask)], [mask, w] { return __builtin_popcount(mask & ~exited[w]); }, orders_memory);
 }
-inline uint64_t exchange(unsigned mask, uint64_t v, int src_lane)
+DRE_EMU_NOTSAN inline uint64_t exchange(unsigned mask, uint64_t v, int src_lane)
 {
     slot[cur] = v;
-    warp_barrier(mask);
-    const uint64_t o = slot[warp_base() + src_lane];
-    warp_barrier(mask);
+    warp_barrier(mask, false);
+    const uint64_t o = slot[(cur & ~31) + src_lane];
+    warp_barrier(mask, false);
     return o;
 }
-inline void cta_barrier() { barrier(cta_bar, [] { return alive; }); }
+DRE_EMU_NOTSAN inline unsigned vote(unsigned mask, bool p)
+{
+    slot[cur] = p ? 1u : 0u;
+    warp_barrier(mask, false);
+    unsigned out = 0;
+    const int n = NT - (cur & ~31);
+    const unsigned live = mask & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) & ~exited[cur >> 5];
+    for (int l = 0; l < 32; ++l)
+        if ((live >> l) & 1u) out |= (unsigned)slot[(cur & ~31) + l] << l;
+    warp_barrier(mask, false);
+    return out;
+}
+DRE_EMU_NOTSAN inline void cta_barrier() { barrier(cta_bar, [] { return alive; }, true); }
+DRE_EMU_NOTSAN inline int cta_barrier_or(int x)
+{
+    // three rotating accumulators: arrivals at barrier g clear the one of barrier g + 1 (nobody can be there before g releases),
+    // while threads that have not yet resumed from barrier g - 1 still read theirs
+    const int idx = (int)(cta_bar.gen % 3u);
+    or_acc[idx] |= x;
+    or_acc[(idx + 1) % 3] = 0;
+    barrier(cta_bar, [] { return alive; }, true);
+    return or_acc[idx];
+}
+DRE_EMU_NOTSAN inline void named_barrier(int id, int count) { barrier(named_bar[id & 15], [count] { return count; }, true); }
 template <class T> inline uint64_t bits(T v) { uint64_t u = 0; memcpy(&u, &v, sizeof(T)); return u; }
 template <class T> inline T unbits(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
-inline const uint3 &tid3() { tid3_v.x = (unsigned)cur; tid3_v.y = tid3_v.z = 0; return tid3_v; }
+DRE_EMU_NOTSAN inline uint3 tid3() { uint3 v; v.x = (unsigned)cur; v.y = v.z = 0; return v; }
+DRE_EMU_NOTSAN inline uint3 bid3() { return bid3_v; }
+DRE_EMU_NOTSAN inline dim3 gdim() { return gdim_v; }
+DRE_EMU_NOTSAN inline dim3 bdim() { return bdim_v; }
+DRE_EMU_NOTSAN inline unsigned char *shared_base() { return dyn_smem; }
 
-inline void lane_entry()
+DRE_EMU_NOTSAN inline void lane_entry()
 {
+#if DRE_EMU_TSAN
+    __tsan_acquire(&launch_token);
+#endif
     (*body)();
+#if DRE_EMU_TSAN
+    __tsan_release(&done_token);
+#endif
     lanes[cur].done = true;
     exited[cur >> 5] |= 1u << (cur & 31);
     --alive;
@@ -137,7 +217,7 @@ struct Launcher {
     dim3 grid, block;
     size_t smem;
     Launcher(dim3 g, dim3 b, size_t s = 0, const void * = nullptr) : grid(g), block(b), smem(s) {}
-    void operator()(const std::function<void()> &f) const
+    DRE_EMU_NOTSAN void operator()(const std::function<void()> &f) const
     {
         const int nt = (int)(block.x * block.y * block.z);
         static const bool trace = getenv("DRE_EMU_TRACE") != nullptr;
@@ -159,15 +239,22 @@ struct Launcher {
             }
         }
         if (nt < 1 || nt > MAXT) abort();
-        void *sm = nullptr;                     // an exact-size block: an overrun of the launch's shared memory is a heap overrun (ASan build)
-        if (posix_memalign(&sm, 64, smem ? smem : 1) != 0) abort();
-        memset(sm, 0, smem ? smem : 1);
-        dyn_smem = static_cast<unsigned char *>(sm);
         body = &f;
         NT = nt;
         bdim_v = block;
         gdim_v = grid;
+#if DRE_EMU_TSAN
+        main_fiber = __tsan_get_current_fiber();
+        __tsan_release(&launch_token);          // everything the host did so far happens before the kernel's threads
+#endif
+        std::vector<void *> held;               // race-check build: blocks are freed after the kernel boundary, not between concurrent CTAs
         for (unsigned b = 0; b < grid.x; ++b) {
+            // an exact-size block per CTA: an overrun of the shared memory is a heap overrun (ASan build), and the CTAs of a grid,
+            // which are concurrent for the race check, do not share it
+            void *sm = nullptr;
+            if (posix_memalign(&sm, 64, smem ? smem : 1) != 0) abort();
+            memset(sm, 0, smem ? smem : 1);
+            dyn_smem = static_cast<unsigned char *>(sm);
             bid3_v.x = b; bid3_v.y = bid3_v.z = 0;
             cta_bar = Bar();
             or_acc[0] = or_acc[1] = or_acc[2] = 0;
@@ -177,9 +264,17 @@ struct Launcher {
             alive = nt;
             for (int t = 0; t < nt; ++t) {
                 Lane &L = lanes[t];
+#if DRE_EMU_TSAN
+                if (!L.stack) L.stack = (char *)mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+                if (L.stack == (char *)MAP_FAILED) abort();
+#else
                 if (!L.stack) L.stack = (char *)malloc(STACK_BYTES);
+#endif
                 L.done = false;
                 prepare(L, lane_entry);
+#if DRE_EMU_TSAN
+                L.fiber = __tsan_create_fiber(0);
+#endif
             }
             for (bool any = true; any;) {
                 any = false;
@@ -190,83 +285,97 @@ struct Launcher {
                     resume(t);
                 }
             }
+#if DRE_EMU_TSAN
+            for (int t = 0; t < nt; ++t) {
+                __tsan_destroy_fiber(lanes[t].fiber);
+                lanes[t].fiber = nullptr;
+                munmap(lanes[t].stack, STACK_BYTES);   // the next CTA's thread t gets a fresh mapping: ThreadSanitizer forgets the accesses
+                lanes[t].stack = nullptr;              // of this CTA's thread t to the same addresses (the CTAs are concurrent for it)
+            }
+#endif
+            dyn_smem = nullptr;
+#if DRE_EMU_TSAN
+            held.push_back(sm);
+#else
+            free(sm);
+#endif
         }
+#if DRE_EMU_TSAN
+        __tsan_acquire(&done_token);            // ... and everything the kernel's threads did happens before what the host does next
+#endif
+        for (void *q : held) free(q);
         body = nullptr;
-        dyn_smem = nullptr;
-        free(sm);
     }
 };
 }  // namespace emu
 
 // ---- warp collectives -----------------------------------------------------------------------------------------------------
-template <class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+template <class T> DRE_EMU_NOTSAN static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
 {
     const int lane = emu::lane_id();
     return emu::unbits<T>(emu::exchange(mask, emu::bits(v), (lane & ~(width - 1)) | (src & (width - 1))));
 }
-template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+template <class T> DRE_EMU_NOTSAN static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
 {
     const int lane = emu::lane_id();
     int s = lane - (int)delta;
     if (s < (lane & ~(width - 1))) s = lane;
     return emu::unbits<T>(emu::exchange(mask, emu::bits(v), s));
 }
-template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+template <class T> DRE_EMU_NOTSAN static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
 {
     const int lane = emu::lane_id();
     int s = lane + (int)delta;
     if (s > (lane | (width - 1))) s = lane;
     return emu::unbits<T>(emu::exchange(mask, emu::bits(v), s));
 }
-template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int o, int width = 32)
+template <class T> DRE_EMU_NOTSAN static inline T __shfl_xor_sync(unsigned mask, T v, int o, int width = 32)
 {
     const int lane = emu::lane_id();
     int s = lane ^ o;
     if ((s & ~(width - 1)) != (lane & ~(width - 1))) s = lane;
     return emu::unbits<T>(emu::exchange(mask, emu::bits(v), s));
 }
-static inline unsigned __ballot_sync(unsigned mask, bool p)
-{
-    emu::slot[emu::cur] = p ? 1u : 0u;
-    emu::warp_barrier(mask);
-    unsigned out = 0;
-    const unsigned live = mask & emu::warp_members() & ~emu::exited[emu::cur >> 5];
-    for (int l = 0; l < 32; ++l)
-        if ((live >> l) & 1u) out |= (unsigned)emu::slot[emu::warp_base() + l] << l;
-    emu::warp_barrier(mask);
-    return out;
-}
-static inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0u; }
-static inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, !p) == 0u; }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask); }
+static inline unsigned __ballot_sync(unsigned mask, bool p) { return emu::vote(mask, p); }
+static inline bool __any_sync(unsigned mask, bool p) { return emu::vote(mask, p) != 0u; }
+static inline bool __all_sync(unsigned mask, bool p) { return emu::vote(mask, !p) == 0u; }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask, true); }
 static inline void __syncthreads() { emu::cta_barrier(); }
-static inline int __syncthreads_or(int x)
-{
-    // three rotating accumulators: arrivals at barrier g clear the one of barrier g + 1 (nobody can be there before g releases),
-    // while threads that have not yet resumed from barrier g - 1 still read theirs
-    const int idx = (int)(emu::cta_bar.gen % 3u);
-    emu::or_acc[idx] |= x;
-    emu::or_acc[(idx + 1) % 3] = 0;
-    emu::cta_barrier();
-    return emu::or_acc[idx];
-}
-static inline void dre_emul_bar_sync(int id, int count) { emu::barrier(emu::named_bar[id & 15], [count] { return count; }); }
-static inline void __threadfence() {}
-static inline void __threadfence_block() {}
-static inline void __threadfence_system() {}
+static inline int __syncthreads_or(int x) { return emu::cta_barrier_or(x); }
+static inline void dre_emul_bar_sync(int id, int count) { emu::named_barrier(id, count); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
-// ---- atomics, loads, bit helpers (one OS thread: plain operations) -------------------------------------------------------------
-template <class T, class U> static inline T atomicAdd(T *p, U v) { const T o = *p; *p = (T)(o + (T)v); return o; }
-template <class T, class U> static inline T atomicMax(T *p, U v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
-template <class T, class U> static inline T atomicMin(T *p, U v) { const T o = *p; if ((T)v < o) *p = (T)v; return o; }
-template <class T, class U> static inline T atomicOr(T *p, U v) { const T o = *p; *p = (T)(o | (T)v); return o; }
-template <class T, class U> static inline T atomicExch(T *p, U v) { const T o = *p; *p = (T)v; return o; }
+// ---- atomics (real atomic operations: the race check must see them as such), loads, bit helpers ----------------------------------
+template <class T> struct dre_emu_word { typedef T type; };
+template <> struct dre_emu_word<float> { typedef uint32_t type; };
+template <> struct dre_emu_word<double> { typedef uint64_t type; };
+template <class T, class F> static inline T dre_emu_rmw(T *p, F f)
+{
+    typedef typename dre_emu_word<T>::type W;
+    static_assert(sizeof(W) == sizeof(T), "atomic word");
+    W *w = reinterpret_cast<W *>(p);
+    W old = __atomic_load_n(w, __ATOMIC_ACQUIRE), neu;
+    T o;
+    do {
+        memcpy(&o, &old, sizeof(T));
+        const T n = f(o);
+        memcpy(&neu, &n, sizeof(T));
+    } while (!__atomic_compare_exchange_n(w, &old, neu, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE));
+    return o;
+}
+template <class T, class U> static inline T atomicAdd(T *p, U v) { return dre_emu_rmw(p, [v](T o) { return (T)(o + (T)v); }); }
+template <class T, class U> static inline T atomicMax(T *p, U v) { return dre_emu_rmw(p, [v](T o) { return (T)v > o ? (T)v : o; }); }
+template <class T, class U> static inline T atomicMin(T *p, U v) { return dre_emu_rmw(p, [v](T o) { return (T)v < o ? (T)v : o; }); }
+template <class T, class U> static inline T atomicOr(T *p, U v) { return dre_emu_rmw(p, [v](T o) { return (T)(o | (T)v); }); }
+template <class T, class U> static inline T atomicExch(T *p, U v) { return dre_emu_rmw(p, [v](T) { return (T)v; }); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 static inline long long clock64() { return 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
-static inline unsigned __activemask() { return emu::warp_members() & ~emu::exited[emu::cur >> 5]; }
+static inline unsigned __activemask() { return emu::warp_members() & ~emu::warp_exited(); }
 static inline unsigned __float_as_uint(float f) { return (unsigned)emu::bits(f); }
 static inline float __uint_as_float(unsigned u) { return emu::unbits<float>(u); }
 static inline int __float_as_int(float f) { return (int)emu::bits(f); }
@@ -287,13 +396,13 @@ static inline double dre_emul_rcp_approx(double x)
 namespace cooperative_groups {
 struct thread_block {
     void sync() const { __syncthreads(); }
-    unsigned thread_rank() const { return (unsigned)emu::cur; }
+    unsigned thread_rank() const { return emu::tid3().x; }
 };
 inline thread_block this_thread_block() { return thread_block(); }
 template <int G> struct thread_block_tile {
     unsigned mask() const { return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (emu::lane_id() & ~(G - 1))); }
     unsigned thread_rank() const { return (unsigned)(emu::lane_id() & (G - 1)); }
-    unsigned meta_group_rank() const { return (unsigned)(emu::cur / G); }
+    unsigned meta_group_rank() const { return emu::tid3().x / G; }
     unsigned size() const { return G; }
     unsigned ballot(bool p) const { return (__ballot_sync(mask(), p) >> (emu::lane_id() & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u)); }
     bool any(bool p) const { return ballot(p) != 0u; }
@@ -302,7 +411,7 @@ template <int G> struct thread_block_tile {
     template <class T> T shfl_xor(T v, int m) const { return __shfl_xor_sync(mask(), v, m, G); }
     template <class T> T shfl_up(T v, int d) const { return __shfl_up_sync(mask(), v, (unsigned)d, G); }
     template <class T> T shfl_down(T v, int d) const { return __shfl_down_sync(mask(), v, (unsigned)d, G); }
-    void sync() const { __syncwarp(mask()); }
+    void sync() const { emu::warp_barrier(mask(), true); }
 };
 template <int G> inline thread_block_tile<G> tiled_partition(const thread_block &) { return thread_block_tile<G>(); }
 }  // namespace cooperative_groups
@@ -317,9 +426,9 @@ template <int G> inline thread_block_tile<G> tiled_partition(const thread_block 
 #define __grid_constant__
 #endif
 #define threadIdx (emu::tid3())
-#define blockIdx (emu::bid3_v)
-#define gridDim (emu::gdim_v)
-#define blockDim (emu::bdim_v)
+#define blockIdx (emu::bid3())
+#define gridDim (emu::gdim())
+#define blockDim (emu::bdim())
 // __shared__ variables of a kernel: one CTA runs at a time, so a function-level static is the CTA's shared memory
 #undef __shared__
 #define __shared__ static

@@ -155,3 +155,66 @@ def test_adapter_types_and_state_packing(reference_with_adapters):
     assert np.allclose(s8[4:6], [0.6, 0.8])
     many = pol.predict_many([js, js])
     assert many[0] == a and many[1] == a
+
+
+@pytest.fixture()
+def reference_on_emulated_library(monkeypatch):
+    """The same plugs, but nothing stands in for the C ABI: dr_mpc_b200._lib loads the EMULATED build of the product library
+    (tests/host_harness/gen_emu.py: every .cu compiled for the CPU, CUDA threads as coroutines), so compat.ORCA's
+    dre_orca_solve_host and compat.MPC's dre_mpc_create / set_paths / reset / act_host run the product's own kernels."""
+    for p in (os.path.join(REPO, "oracle", "shims"), REF):
+        if p not in sys.path:
+            monkeypatch.syspath_prepend(p)
+    import emu_driver
+    import dr_mpc_b200._lib as LL
+    emu = emu_driver.lib()
+    monkeypatch.setattr(LL, "_lib", emu)
+    from dr_mpc_b200 import compat
+    from scripts.policy import policy_factory as PF
+    monkeypatch.setitem(PF.policy_factory, 'orca', compat.ORCA)
+    return compat
+
+
+@pytest.mark.parametrize("tag,Nh,seed,steps", [("h6", 6, 0, 500), ("h10", 10, 1, 90), ("h20", 20, 2, 50)])
+def test_reference_env_runs_on_the_products_kernels(reference_on_emulated_library, golden_env, tag, Nh, seed, steps):
+    """The reference's UNMODIFIED HAAndPTEnv / HAEnv / PTEnv / Human / CrowdSim, with policy_factory['orca'] = compat.ORCA and
+    env.MPC = compat.MPC, stepping on the product's own orca_joint_kernel and mpc_coop_kernel (emulated GPU): the recorded
+    rollout -- resets, path switches and the reference's own soft_reset() loop included -- is reproduced: human velocities
+    bit-exact, positions 1e-12, observations / rewards 1e-9, done reasons equal, MPC controls 1e-6."""
+    compat = reference_on_emulated_library
+    from environment.HA_and_PT.human_avoidance_and_path_tracking_env import HAAndPTEnv
+    from environment.human_avoidance.utils.action import ActionRot
+    g = golden_env
+    cm = _config(Nh)
+    env = HAAndPTEnv(cm, seed_addition=seed)
+    env.MPC = compat.MPC(cm, cm.config_PT.MPC.planning_horizon, env.time_step, env.continuous_task, cm.config_general.robot.v_max, cm.config_general.robot.w_max)
+    env.case_counter['train'] = seed
+    S = env.reset()
+    assert isinstance(env.HA_env.humans[0].policy, compat.ORCA)
+    assert np.abs(S['HA']['spatial_edges'][0] - g[f"{tag}_reset_spatial_edges"]).max() <= 1e-9
+    assert np.abs(S['PT']['MPC_actions'][0] - g[f"{tag}_reset_mpc_actions"]).max() <= 1e-6
+    T = min(steps, g[f"{tag}_out_action"].shape[0])
+    done_return, info = {'done': False}, None
+    worst = {"mpc": 0.0, "obs": 0.0, "rew": 0.0}
+    mpc = env.MPC._mpc                          # the product's BatchedMPC over the emulated C ABI
+    for t in range(T):
+        if done_return['done']:
+            S = env.soft_reset(done_return, info, S)
+            assert S is not None
+        a = g[f"{tag}_out_action"][t]
+        wT, wu, it0 = mpc.get_warm()
+        assert int(it0[0]) == int(g[f"{tag}_pre_it0"][t]), t            # the adapter followed the reference's MPC.reset() calls
+        if not g[f"{tag}_pre_it0"][t]:                                   # teacher forcing of the warm start, as in every MPC parity test
+            mpc.set_warm(g[f"{tag}_pre_warm_T"][t][None], g[f"{tag}_pre_warm_u"][t][None], None)
+        S, R, done_return, info, eps = env.step(ActionRot(float(a[0]), float(a[1])))
+        hv = np.array([[h.vx, h.vy] for h in env.HA_env.humans], dtype=np.float32)
+        assert np.array_equal(hv.view(np.uint32), g[f"{tag}_post_hvel"][t].view(np.uint32)), t
+        hp = np.array([[h.px, h.py] for h in env.HA_env.humans])
+        assert np.abs(hp - g[f"{tag}_post_hpos"][t]).max() <= 1e-12, t
+        assert sum(b for name, b in _BITS.items() if name in info['done']) == int(g[f"{tag}_out_bits"][t]), t
+        worst["rew"] = max(worst["rew"], np.abs(np.array([R['R_PT'], R['R_DO'], R['R']]) - g[f"{tag}_out_rewards"][t]).max())
+        worst["obs"] = max(worst["obs"], np.abs(S['HA']['spatial_edges'][0] - g[f"{tag}_out_spatial_edges"][t]).max(),
+                           np.abs(S['PT']['PT_state'][0] - g[f"{tag}_out_pt_state"][t]).max())
+        worst["mpc"] = max(worst["mpc"], np.abs(S['PT']['MPC_actions'][0] - g[f"{tag}_out_mpc_actions"][t]).max())
+    print(f"{tag}: {T} steps of the reference's env on the emulated product kernels: max |dMPC| {worst['mpc']:.2e}, |dobs| {worst['obs']:.2e}, |dR| {worst['rew']:.2e}")
+    assert worst["mpc"] <= 1e-6 and worst["obs"] <= 1e-9 and worst["rew"] <= 1e-9

@@ -387,3 +387,81 @@ def test_replay_ring_against_a_numpy_ring(Ee, Nh, cap, dtype):
     if dtype == np.float64:
         half = rb.sample(np.arange(valid), dtype=np.float32)
         assert np.array_equal(half["S"]["pt_state"], chron["S"]["pt_state"].astype(np.float32))
+
+
+def test_switch_path_masked_observe_and_soft_reset_decide():
+    """tests/test_gpu_api.py on the emulated build: the host-driven form of soft_reset's path switch (dre_env_switch_path +
+    dre_env_observe_masked) equals a second engine put on the new path by hand; dre_env_soft_reset_decide(commit=0) predicts
+    what the device machine does in the next step and leaves its state alone."""
+    Ee = 40
+    a_env = E_.EmuEnv(Ee, num_humans=6, auto_path_switch=False)
+    o = a_env.reset()
+    for _ in range(4):
+        o = a_env.step(o["mpc_actions"][:, :2].copy())
+    mask = np.zeros(Ee, bool)
+    mask[1::2] = True
+    pre = {k: v.copy() for k, v in o.items()}
+    T0, u0, _ = a_env.mpc_get_warm()
+    a_env.switch_path(mask)
+    o2 = a_env.observe(solve_mpc=True, env_mask=mask)
+    st = a_env.state
+    assert (st["path_idx"][mask] == 1).all() and (st["path_idx"][~mask] == 0).all() and (st["loc_to_start"][mask] == 1).all()
+    for k in pre:
+        assert np.array_equal(o2[k][~mask], pre[k][~mask]), k
+    T1, u1, it1 = a_env.mpc_get_warm()
+    assert np.array_equal(T0[~mask], T1[~mask]) and (it1 == 0).all() and not np.array_equal(o2["pt_state"][mask], pre["pt_state"][mask])
+    b_env = E_.EmuEnv(Ee, num_humans=6, auto_path_switch=False)
+    b_env.reset()
+    for k in a_env.state:
+        b_env.state[k][...] = a_env.state[k]
+    b_env.mpc_set_warm(T0, u0, np.ones(Ee, np.uint8))
+    ob = b_env.observe(solve_mpc=True)
+    assert np.array_equal(ob["pt_state"][mask], o2["pt_state"][mask]) and np.array_equal(ob["mpc_actions"][mask], o2["mpc_actions"][mask])
+    env = E_.EmuEnv(96, num_humans=10, soft_reset_on_device=True)
+    o = env.reset()
+    seen = 0
+    for t in range(70):
+        sr0 = env.state["sr_state"].copy()
+        scripted, act, stuck = env.soft_reset_decide(commit=False)
+        assert np.array_equal(env.state["sr_state"], sr0)
+        a = o["mpc_actions"][:, :2].copy()
+        a[:, 1] = (a[:, 1] + 0.5 * np.sin(np.arange(96) * 0.37 + t)).clip(-1, 1)
+        o = env.step(a)
+        assert np.array_equal(env.flags()["soft_reset"], scripted), t
+        assert np.array_equal(o["actions_used"][scripted], act[scripted]) and not stuck.any()
+        seen += int(scripted.sum())
+    assert seen > 5
+
+
+def test_host_output_modes_cvmm_check_crowd_step_and_stats():
+    """dre_env_set_host_outputs (float32 observations through cvt32_kernel = the float64 results rounded once; control fields
+    only), dre_env_cvmm_check against the filter's verdict on the original action, dre_env_crowd_step (BASELINE config 4's
+    ORCA-only step) and the episode statistics"""
+    Ee, Nh = 45, 10
+    envs = {m: E_.EmuEnv(Ee, num_humans=Nh) for m in ("full", "f32", "ctl")}
+    envs["f32"].set_host_outputs(1)
+    envs["ctl"].set_host_outputs(2)
+    act = envs["full"].reset()["mpc_actions"][:, :2].copy()
+    envs["f32"].reset(); envs["ctl"].reset()
+    obs = ("pt_state", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
+    for t in range(3):
+        v = {m: e.step_host_mode(act) for m, e in envs.items()}
+        for name in obs:
+            assert v["f32"][name].dtype == np.float32 and name not in v["ctl"]
+            assert np.array_equal(v["f32"][name], v["full"][name].astype(np.float32)), (t, name)
+        for name in ("actions_used", "mpc_actions", "rewards", "info", "done_bits", "mpc_status", "done_flags"):
+            for m in ("f32", "ctl"):
+                assert np.array_equal(v[m][name].view(np.uint8), v["full"][name].view(np.uint8)), (t, m, name)
+        for m in ("f32", "ctl"):
+            assert np.array_equal(envs[m].out["spatial_edges"], envs["full"].out["spatial_edges"])      # the device slab stays float64
+        act = v["full"]["mpc_actions"][:, :2].copy()
+    env = envs["full"]
+    safe, dist = env.cvmm_check(act, 8)
+    _, info = env.cvmm(act, 8, np.array([[0.05, -0.8], [0.6, 0.0], [0.15, 0.2]]))
+    assert np.array_equal(safe, info["original_safe"].astype(bool)) and np.isfinite(dist).all()
+    c, s = env.stats()
+    assert c[0] == 3 * Ee and np.isfinite(s).all()
+    before = {k: env.state[k].copy() for k in ("hpos", "rpose", "step_count")}
+    env.crowd_step(write_obs=True)
+    assert not np.array_equal(env.state["hpos"], before["hpos"]) and np.array_equal(env.state["rpose"], before["rpose"])
+    assert np.abs(env.state["hpos"] - (before["hpos"] + env.state["hvel"].astype(np.float64) * 0.25)).max() <= 1e-15

@@ -206,7 +206,11 @@ def test_two_rank_gloo_sharding_equals_single_process(oracle, tmp_path):
     from dr_mpc_b200.parallel import episode_stats_from_step
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sk:                  # a free rendezvous port instead of a fixed one
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", OMP_NUM_THREADS="1")
     procs = [subprocess.Popen([sys.executable, str(script), REPO, str(tmp_path)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r))) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=240) == 0

@@ -465,3 +465,32 @@ def test_host_output_modes_cvmm_check_crowd_step_and_stats():
     env.crowd_step(write_obs=True)
     assert not np.array_equal(env.state["hpos"], before["hpos"]) and np.array_equal(env.state["rpose"], before["rpose"])
     assert np.abs(env.state["hpos"] - (before["hpos"] + env.state["hvel"].astype(np.float64) * 0.25)).max() <= 1e-15
+
+
+@pytest.mark.parametrize("Ee,Nh,K", [(1, 1, 4), (3, 64, 4), (37, 63, 1), (5, 5, 40), (2, 6, 33), (130, 3, 8)])
+def test_edge_shapes_against_the_oracle(oracle, golden_mpc, Ee, Nh, K):
+    """the corners of the supported range -- a single env with a single human, the largest crowd (64 humans: the shared-memory
+    layout at its limit, the thread-per-agent ORCA fallback), horizons 1 / 33 / 40 (one lane, the two-warp groups), env counts that
+    are no multiple of any tile -- free-running for a few steps, every step compared with oracle/env_ref.c from the same state"""
+    _, tab, lens = mpc_path_table(golden_mpc)
+    env = E_.EmuEnv(Ee, num_humans=Nh, horizon=K)
+    o = env.reset()
+    ref = oracle.EnvRef(Ee, Nh, tab, lens, K=K)
+    ref.reset()
+    for t in range(5):
+        a = o["mpc_actions"][:, :2].copy()
+        for k in ("hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime",
+                  "path_idx", "loc_to_start", "step_count", "sr_state"):
+            ref.a[k][...] = env.state[k].reshape(ref.a[k].shape)
+        ref.a["done_bits"][...] = o["done_bits"]
+        ref.a["reset_epoch"][...] = 1
+        ref.a["warm_T"][...], ref.a["warm_u"][...], ref.a["iteration0"][...] = env.mpc_get_warm()
+        o = env.step(a)
+        r = ref.step(a, nthreads=1)
+        assert np.array_equal(env.state["hvel"].view(np.uint32), r["hvel"].view(np.uint32)), t
+        assert np.abs(env.state["hpos"] - r["hpos"]).max() <= 1e-12 and np.array_equal(o["done_bits"], r["done_bits"])
+        assert np.abs(o["rewards"] - r["rewards"]).max() <= 1e-9
+        for name in ("pt_state", "robot_node", "spatial_edges", "human_valid"):
+            assert np.abs(o[name] - r[name].reshape(o[name].shape)).max() <= 1e-9, (t, name)
+        same = o["mpc_status"][:, 0] == r["mpc_status"]["iterations"]
+        assert same.mean() >= 0.9 and np.abs(o["mpc_actions"] - r["mpc_actions"]).max(1)[same].max() <= 5e-6

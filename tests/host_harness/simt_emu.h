@@ -38,20 +38,24 @@
 namespace emu {
 constexpr int MAXT = 1024;
 constexpr size_t STACK_BYTES = 512 * 1024;
-struct Lane {
-    ucontext_t ctx;
-    void *sp = nullptr;         // x86-64 fast path: the suspended coroutine's stack pointer
-    void *fiber = nullptr;      // ThreadSanitizer build: the fiber that stands for this CUDA thread
-    char *stack = nullptr;
-    bool done = false;
-};
 struct Bar {
     int arrived = 0;
     unsigned gen = 0;
 };
+struct Lane {
+    ucontext_t ctx;
+    void *sp = nullptr;         // x86-64 fast path: the suspended coroutine's stack pointer
+    void *fiber = nullptr;      // ThreadSanitizer build: the fiber that stands for this CUDA thread
+    // what a thread blocked in a barrier last saw: the scheduler resumes it only when that can have changed
+    Bar *wait = nullptr;
+    unsigned wait_gen = 0;
+    int wait_arrived = 0, wait_exits = 0;
+    char *stack = nullptr;
+    bool done = false;
+};
 inline Lane lanes[MAXT];
 inline ucontext_t main_ctx;
-inline int cur = 0, NT = 0, alive = 0;
+inline int cur = 0, NT = 0, alive = 0, exits = 0;
 inline uint64_t slot[MAXT];
 inline unsigned exited[MAXT / 32];          // per warp: lanes that have returned from the kernel
 inline Bar group_bar[MAXT], named_bar[16], cta_bar;
@@ -130,8 +134,11 @@ template <class Expected> DRE_EMU_NOTSAN inline void barrier(Bar &b, Expected ex
     for (;;) {
         if (b.gen != gen) break;
         if (b.arrived >= expected()) { b.arrived = 0; ++b.gen; break; }
+        Lane &me = lanes[cur];
+        me.wait = &b; me.wait_gen = gen; me.wait_arrived = b.arrived; me.wait_exits = exits;
         yield();
     }
+    lanes[cur].wait = nullptr;
 #if DRE_EMU_TSAN
     if (orders_memory) __tsan_acquire(&b);
 #endif
@@ -209,6 +216,7 @@ DRE_EMU_NOTSAN inline void lane_entry()
     lanes[cur].done = true;
     exited[cur >> 5] |= 1u << (cur & 31);
     --alive;
+    ++exits;
     for (;;) yield();
 }
 
@@ -271,6 +279,7 @@ struct Launcher {
                 if (!L.stack) L.stack = (char *)malloc(STACK_BYTES);
 #endif
                 L.done = false;
+                L.wait = nullptr;
                 prepare(L, lane_entry);
 #if DRE_EMU_TSAN
                 L.fiber = __tsan_create_fiber(0);
@@ -279,8 +288,11 @@ struct Launcher {
             for (bool any = true; any;) {
                 any = false;
                 for (int t = 0; t < nt; ++t) {
-                    if (lanes[t].done) continue;
+                    Lane &L = lanes[t];
+                    if (L.done) continue;
                     any = true;
+                    // blocked in a barrier that nobody has reached or left since it last looked, and no thread has exited: still blocked
+                    if (L.wait && L.wait->gen == L.wait_gen && L.wait->arrived == L.wait_arrived && exits == L.wait_exits) continue;
                     cur = t;
                     resume(t);
                 }

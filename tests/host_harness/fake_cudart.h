@@ -8,7 +8,13 @@
 #include <string.h>
 
 namespace emu_rt {
-inline cudaError_t Malloc(void **p, size_t n) { *p = n ? malloc(n) : nullptr; return (*p || !n) ? cudaSuccess : cudaErrorMemoryAllocation; }
+// cudaMalloc does not zero: poison the block, so that host code or kernels that rely on zeros fail in the emulated suite
+inline cudaError_t Malloc(void **p, size_t n)
+{
+    *p = n ? malloc(n) : nullptr;
+    if (*p) memset(*p, 0xA5, n);
+    return (*p || !n) ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T> inline cudaError_t Malloc(T **p, size_t n) { return Malloc((void **)p, n); }
 inline cudaError_t Free(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t HostAlloc(void **p, size_t n, unsigned) { return Malloc(p, n); }

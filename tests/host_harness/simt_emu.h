@@ -261,7 +261,7 @@ struct Launcher {
             // which are concurrent for the race check, do not share it
             void *sm = nullptr;
             if (posix_memalign(&sm, 64, smem ? smem : 1) != 0) abort();
-            memset(sm, 0, smem ? smem : 1);
+            memset(sm, 0xA5, smem ? smem : 1);   // shared memory is NOT zero on the GPU: poison it, a kernel that relies on zeros must fail here
             dyn_smem = static_cast<unsigned char *>(sm);
             bid3_v.x = b; bid3_v.y = bid3_v.z = 0;
             cta_bar = Bar();

@@ -1,0 +1,93 @@
+"""tools/emu_fuzz.py [seeds...] -- randomised configurations of the env step on the EMULATED build of the product library
+(tests/host_harness) against the CPU oracle (oracle/env_ref.c), free-running, every probed step from the same state. Shapes, horizon,
+neighbour range, robot visibility, static humans, sensor restriction, soft reset, goal policy, path switching and the action noise
+are drawn per seed. Prints one line per seed; exits non-zero on the first mismatch. Test infrastructure (no GPU needed)."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import emu_driver as E_                      # noqa: E402
+from oracle import oracle as O               # noqa: E402
+from conftest import mpc_path_table          # noqa: E402
+
+STATE = ("hpos", "hgoal", "hhist", "hvel", "hstatic", "hvalid", "rpose", "rprev", "rhist", "rpastv", "rvalid", "gtime", "path_idx",
+         "loc_to_start", "step_count", "sr_state")
+
+
+def one(seed, steps=40):
+    rng = np.random.default_rng(seed)
+    g = np.load(os.path.join(REPO, "tests", "golden", "mpc_sequences.npz"))
+    _, tab, lens = mpc_path_table(g)
+    Nh = int(rng.choice([1, 2, 3, 5, 6, 7, 10, 13, 20, 33, 50, 64]))
+    Ee = int(rng.integers(1, max(2, 400 // max(Nh, 4))))
+    K = int(rng.choice([1, 2, 3, 4, 4, 4, 5, 8, 10, 16, 20, 33, 40]))
+    if K > 16:
+        Ee = min(Ee, 12)
+    variant = {}
+    if rng.uniform() < 0.3: variant["robot_visible"] = False
+    if rng.uniform() < 0.3: variant["neighbor_dist"] = float(rng.choice([1.5, 3.0, 6.0]))
+    if rng.uniform() < 0.3: variant["end_goal_changing"] = False
+    if rng.uniform() < 0.2: variant["auto_path_switch"] = False
+    if rng.uniform() < 0.3 and "auto_path_switch" not in variant: variant["soft_reset_on_device"] = True
+    if rng.uniform() < 0.25: variant["robot_sensor_restriction"] = True
+    if rng.uniform() < 0.25 and Nh >= 3: variant["static_humans"] = ((-4.0, 0.0), (0.0, 0.0))[: int(rng.integers(1, 3))]
+    if rng.uniform() < 0.2: variant["time_limit"] = float(rng.choice([2.0, 5.0]))          # timeouts inside the run
+    noise = float(rng.choice([0.0, 0.15, 0.5]))
+    env = E_.EmuEnv(Ee, num_humans=Nh, horizon=K, seed=int(seed) * 7919 + 11, **variant)
+    o = env.reset()
+    ov = dict(variant)
+    ref_kw = {k: ov.pop(k) for k in ("neighbor_dist", "static_humans") if k in ov}
+    if "soft_reset_on_device" in ov: ref_kw["soft_reset"] = ov.pop("soft_reset_on_device")
+    if "robot_sensor_restriction" in ov: ref_kw["sensor_restriction"] = ov.pop("robot_sensor_restriction")
+    tl = ov.pop("time_limit", None)
+    ref = O.EnvRef(Ee, Nh, tab, lens, K=K, seed=int(seed) * 7919 + 11, **ref_kw, **{k: int(v) for k, v in ov.items()})
+    if tl is not None:
+        ref.cfg.time_limit = tl
+    ref.reset()
+    checked = div = events = 0
+    for t in range(steps):
+        a = o["mpc_actions"][:, :2] + rng.normal(size=(Ee, 2)) * noise
+        a[:, 0] = a[:, 0].clip(0, 1); a[:, 1] = a[:, 1].clip(-1, 1)
+        probe = t % 3 == 1
+        if probe:
+            for k in STATE:
+                ref.a[k][...] = env.state[k].reshape(ref.a[k].shape)
+            ref.a["done_bits"][...] = o["done_bits"]
+            ref.a["reset_epoch"][...] = 1
+            ref.a["warm_T"][...], ref.a["warm_u"][...], ref.a["iteration0"][...] = env.mpc_get_warm()
+        o = env.step(a)
+        if not probe:
+            continue
+        r = ref.step(a, nthreads=1)
+        st = env.state
+        ok = (np.array_equal(st["hvel"].view(np.uint32), r["hvel"].view(np.uint32)) and np.abs(st["hpos"] - r["hpos"]).max() <= 1e-12
+              and np.abs(st["hgoal"] - r["hgoal"]).max() <= 1e-12 and np.abs(st["rpose"][:, :3] - r["rpose"][:, :3]).max() <= 1e-12
+              and np.array_equal(st["path_idx"], r["path_idx"]) and np.array_equal(o["done_bits"], r["done_bits"])
+              and np.array_equal(o["actions_used"], r["actions_used"]) and np.array_equal(st["hvalid"], r["hvalid"])
+              and np.array_equal(o["detected_humans"], r["detected_humans"]) and np.abs(o["rewards"] - r["rewards"]).max() <= 1e-9
+              and all(np.abs(o[n] - r[n].reshape(o[n].shape)).max() <= 1e-9 for n in ("pt_state", "robot_node", "past_robot_vel", "spatial_edges", "human_valid")))
+        if variant.get("soft_reset_on_device"):
+            ok = ok and np.array_equal(o["done_flags"][:, 12], r["soft_flags"][:, 0]) and np.array_equal(st["sr_state"], r["sr_state"])
+        stat = o["mpc_status"]
+        same = (stat[:, 0] == r["mpc_status"]["iterations"]) & (stat[:, 2] == r["mpc_status"]["lm_solves"])
+        du = np.abs(o["mpc_actions"] - r["mpc_actions"]).max(1)
+        ok = ok and (du[same].max() if same.any() else 0.0) <= 5e-6
+        if not ok:
+            print(f"seed {seed}: MISMATCH at step {t}: E={Ee} Nh={Nh} K={K} {variant} noise={noise}")
+            return False
+        checked += Ee
+        div += int((~same).sum())
+        events += int((o["done_bits"] & 0xFF != 0).sum())
+    print(f"seed {seed}: ok  E={Ee} Nh={Nh} K={K} noise={noise} {variant}: {checked} transitions, {events} terminations, LM-branch divergences {div}")
+    return div <= max(2, 0.05 * checked)
+
+
+if __name__ == "__main__":
+    seeds = [int(s) for s in sys.argv[1:]] or list(range(20))
+    bad = [s for s in seeds if not one(s)]
+    print("mismatching seeds:", bad)
+    sys.exit(1 if bad else 0)

@@ -256,7 +256,23 @@ struct Launcher {
         __tsan_release(&launch_token);          // everything the host did so far happens before the kernel's threads
 #endif
         std::vector<void *> held;               // race-check build: blocks are freed after the kernel boundary, not between concurrent CTAs
-        for (unsigned b = 0; b < grid.x; ++b) {
+        // The hardware starts CTAs in no particular order: DRE_EMU_CTA_ORDER=reverse | shuffle runs them last-to-first / in a
+        // pseudo-random order, so that the suite also shows that no result depends on the order (last-CTA patterns, chunk flags,
+        // the persistent kernels' static first assignment).
+        std::vector<unsigned> order(grid.x);
+        for (unsigned b = 0; b < grid.x; ++b) order[b] = b;
+        static const char *ord = getenv("DRE_EMU_CTA_ORDER");
+        if (ord && ord[0] == 'r') { for (unsigned b = 0; b < grid.x / 2; ++b) { const unsigned t = order[b]; order[b] = order[grid.x - 1 - b]; order[grid.x - 1 - b] = t; } }
+        if (ord && ord[0] == 's') {
+            static uint64_t lcg = 0x9E3779B97F4A7C15ull;
+            for (unsigned b = grid.x; b > 1; --b) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                const unsigned j = (unsigned)((lcg >> 33) % b), t = order[b - 1];
+                order[b - 1] = order[j]; order[j] = t;
+            }
+        }
+        for (unsigned bi = 0; bi < grid.x; ++bi) {
+            const unsigned b = order[bi];
             // an exact-size block per CTA: an overrun of the shared memory is a heap overrun (ASan build), and the CTAs of a grid,
             // which are concurrent for the race check, do not share it
             void *sm = nullptr;

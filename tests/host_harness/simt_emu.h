@@ -301,9 +301,12 @@ struct Launcher {
                 L.fiber = __tsan_create_fiber(0);
 #endif
             }
+            static const char *lord = getenv("DRE_EMU_THREAD_ORDER");      // "reverse": the scheduler visits threads last-to-first
+            const bool rev = lord && lord[0] == 'r';
             for (bool any = true; any;) {
                 any = false;
-                for (int t = 0; t < nt; ++t) {
+                for (int ti = 0; ti < nt; ++ti) {
+                    const int t = rev ? nt - 1 - ti : ti;
                     Lane &L = lanes[t];
                     if (L.done) continue;
                     any = true;

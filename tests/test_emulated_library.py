@@ -350,17 +350,18 @@ def test_orca_variants_are_bit_identical(flag):
     assert resampled > 2
 
 
-@pytest.mark.parametrize("Ee,Nh,cap,dtype", [(64, 6, 150, np.float64), (40, 7, 1000, np.float64), (50, 5, 30, np.float32)])
+@pytest.mark.parametrize("Ee,Nh,cap,dtype", [(64, 6, 150, np.float64), (40, 7, 1000, np.float64), (50, 5, 30, np.float32), (1100, 3, 5000, np.float64)])
 def test_replay_ring_against_a_numpy_ring(Ee, Nh, cap, dtype):
     """dre_replay_insert / sample (replay_select_kernel + replay_gather_kernel) against the reference buffer's semantics written
     out in numpy (storage.py:54-133: rows in insertion order, the oldest rows fall out when full): masked inserts with the
-    soft-reset machine on (scripted steps stay out), wrap-arounds, odd-width fields, an insert larger than the ring, float32 storage"""
+    soft-reset machine on (scripted steps stay out), wrap-arounds, odd-width fields, an insert larger than the ring, float32 storage,
+    1100 envs = two selection CTAs (the last-CTA scan)"""
     env = E_.EmuEnv(Ee, num_humans=Nh, soft_reset_on_device=True)
     rb = E_.EmuReplay(env, cap, dtype)
     S = {k: v.copy() for k, v in env.reset().items()}
     rows = []                                    # chronological list of (S, A, S', R, done) rows, the newest `cap` survive
     rng = np.random.default_rng(Ee)
-    for t in range(12):
+    for t in range(12 if Ee < 1000 else 6):
         a = S["mpc_actions"][:, :2].copy()
         a[:, 1] = (a[:, 1] + 0.4 * np.sin(np.arange(Ee) * 0.37 + t)).clip(-1, 1)      # a sloppy policy: terminations happen
         o = env.step(a)

@@ -174,6 +174,56 @@ class EmuEnv:
     def invalidate_orca_cache(self):
         check(self.L.dre_env_invalidate_orca_cache(self.h, None))
 
+    def observe(self, solve_mpc=False, env_mask=None):
+        m = np.ascontiguousarray(env_mask, dtype=np.uint8) if env_mask is not None else None
+        check(self.L.dre_env_observe_masked(self.h, ptr(m), int(solve_mpc), None))
+        return self.out
+
+    def switch_path(self, env_mask=None):
+        m = np.ascontiguousarray(env_mask, dtype=np.uint8) if env_mask is not None else None
+        check(self.L.dre_env_switch_path(self.h, ptr(m), None))
+
+    def soft_reset_decide(self, commit=True):
+        sc, a, st = np.zeros(self.E, np.uint8), np.zeros((self.E, 2)), np.zeros(self.E, np.uint8)
+        check(self.L.dre_env_soft_reset_decide(self.h, int(commit), ptr(sc), ptr(a), ptr(st), None))
+        return sc.astype(bool), a, st.astype(bool)
+
+    def cvmm_check(self, actions, num_steps=8):
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        safe, dist = np.zeros(self.E, np.uint8), np.zeros(self.E)
+        check(self.L.dre_env_cvmm_check(self.h, ptr(a), int(num_steps), ptr(safe), ptr(dist), None))
+        return safe.astype(bool), dist
+
+    def crowd_step(self, write_obs=False):
+        check(self.L.dre_env_crowd_step(self.h, int(write_obs), None))
+
+    def set_host_outputs(self, mode):
+        check(self.L.dre_env_set_host_outputs(self.h, int(mode)))
+        self._host_mode = int(mode)
+
+    def step_host_mode(self, actions):
+        """step_host with the configured output mode: {name: array} of what travelled (float32 observations in mode 1, control
+        fields only in mode 2), decoded like BatchedHAAndPTEnv._make_host_views"""
+        mode = getattr(self, "_host_mode", 0)
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.E, 2)
+        if not hasattr(self, "_host_slab"):
+            self._host_slab = np.zeros(self.slab_bytes, dtype=np.uint8)
+        check(self.L.dre_env_step_host(self.h, ptr(a), ptr(self._host_slab)))
+        obs = ("pt_state", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
+        out = {}
+        for n, shp, dt in self._spec:
+            if mode == 2 and n in obs:
+                continue
+            d = np.dtype("f4") if (mode == 1 and n in obs) else np.dtype(dt)
+            cnt = int(np.prod(shp)) * d.itemsize
+            out[n] = self._host_slab[self._offsets[n]:self._offsets[n] + cnt].view(d).reshape(shp).copy()
+        return out
+
+    def stats(self, reset=False):
+        c, s = np.zeros(16, np.int64), np.zeros(4)
+        check(self.L.dre_env_stats(self.h, ptr(c), ptr(s), int(reset), None))
+        return c, s
+
 
 OBS_KEYS = ("pt_state", "mpc_actions", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
 
@@ -227,62 +277,3 @@ class EmuReplay:
         b.rows, b.dtype = n, 0 if dt == np.float64 else 1
         check(self.L.dre_replay_sample(self.h, ptr(idx), n, b.dtype, ctypes.byref(b), None))
         return out
-
-
-def _env_extra():
-    """the rest of BatchedHAAndPTEnv's calls (dr_mpc_b200/env.py), attached to EmuEnv"""
-    def observe(self, solve_mpc=False, env_mask=None):
-        m = np.ascontiguousarray(env_mask, dtype=np.uint8) if env_mask is not None else None
-        check(self.L.dre_env_observe_masked(self.h, ptr(m), int(solve_mpc), None))
-        return self.out
-
-    def switch_path(self, env_mask=None):
-        m = np.ascontiguousarray(env_mask, dtype=np.uint8) if env_mask is not None else None
-        check(self.L.dre_env_switch_path(self.h, ptr(m), None))
-
-    def soft_reset_decide(self, commit=True):
-        sc, a, st = np.zeros(self.E, np.uint8), np.zeros((self.E, 2)), np.zeros(self.E, np.uint8)
-        check(self.L.dre_env_soft_reset_decide(self.h, int(commit), ptr(sc), ptr(a), ptr(st), None))
-        return sc.astype(bool), a, st.astype(bool)
-
-    def cvmm_check(self, actions, num_steps=8):
-        a = np.ascontiguousarray(actions, dtype=np.float64)
-        safe, dist = np.zeros(self.E, np.uint8), np.zeros(self.E)
-        check(self.L.dre_env_cvmm_check(self.h, ptr(a), int(num_steps), ptr(safe), ptr(dist), None))
-        return safe.astype(bool), dist
-
-    def crowd_step(self, write_obs=False):
-        check(self.L.dre_env_crowd_step(self.h, int(write_obs), None))
-
-    def set_host_outputs(self, mode):
-        check(self.L.dre_env_set_host_outputs(self.h, int(mode)))
-        self._host_mode = int(mode)
-
-    def step_host_mode(self, actions):
-        """step_host with the configured output mode: {name: array} of what travelled (float32 observations in mode 1, control
-        fields only in mode 2), decoded like BatchedHAAndPTEnv._make_host_views"""
-        mode = getattr(self, "_host_mode", 0)
-        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.E, 2)
-        if not hasattr(self, "_host_slab"):
-            self._host_slab = np.zeros(self.slab_bytes, dtype=np.uint8)
-        check(self.L.dre_env_step_host(self.h, ptr(a), ptr(self._host_slab)))
-        obs = ("pt_state", "robot_node", "past_robot_vel", "percent_episode", "spatial_edges", "human_valid", "detected_humans")
-        out = {}
-        for n, shp, dt in self._spec:
-            if mode == 2 and n in obs:
-                continue
-            d = np.dtype("f4") if (mode == 1 and n in obs) else np.dtype(dt)
-            cnt = int(np.prod(shp)) * d.itemsize
-            out[n] = self._host_slab[self._offsets[n]:self._offsets[n] + cnt].view(d).reshape(shp).copy()
-        return out
-
-    def stats(self, reset=False):
-        c, s = np.zeros(16, np.int64), np.zeros(4)
-        check(self.L.dre_env_stats(self.h, ptr(c), ptr(s), int(reset), None))
-        return c, s
-
-    for f in (observe, switch_path, soft_reset_decide, cvmm_check, crowd_step, set_host_outputs, step_host_mode, stats):
-        setattr(EmuEnv, f.__name__, f)
-
-
-_env_extra()

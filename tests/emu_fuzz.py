@@ -1,4 +1,4 @@
-"""tools/emu_fuzz.py [seeds...] -- randomised configurations of the env step on the EMULATED build of the product library
+"""tests/emu_fuzz.py [seeds...] -- randomised configurations of the env step on the EMULATED build of the product library
 (tests/host_harness) against the CPU oracle (oracle/env_ref.c), free-running, every probed step from the same state. Shapes, horizon,
 neighbour range, robot visibility, static humans, sensor restriction, soft reset, goal policy, path switching and the action noise
 are drawn per seed. Prints one line per seed; exits non-zero on the first mismatch. Test infrastructure (no GPU needed)."""
@@ -9,7 +9,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, os.path.join(REPO, "tests"))     # (this file lives in tests/: only tests may execute the oracle)
 import emu_driver as E_                      # noqa: E402
 from oracle import oracle as O               # noqa: E402
 from conftest import mpc_path_table          # noqa: E402

@@ -499,11 +499,11 @@ def test_edge_shapes_against_the_oracle(oracle, golden_mpc, Ee, Nh, K):
 
 @pytest.mark.parametrize("seed", [1, 5, 7, 23, 47, 52])
 def test_fuzzed_configurations_against_the_oracle(seed):
-    """tools/emu_fuzz.py: shape, horizon, neighbour range, robot visibility, static humans, sensor restriction, soft reset, goal
+    """tests/emu_fuzz.py: shape, horizon, neighbour range, robot visibility, static humans, sensor restriction, soft reset, goal
     policy, path switching, time limit and action noise drawn per seed; free-running, every third step compared with
     oracle/env_ref.c from the same state (400 seeds run clean when this was written: profiles/r2_emu_fuzz.txt)"""
     import importlib.util
-    spec = importlib.util.spec_from_file_location("dre_emu_fuzz", os.path.join(REPO, "tools", "emu_fuzz.py"))
+    spec = importlib.util.spec_from_file_location("dre_emu_fuzz", os.path.join(REPO, "tests", "emu_fuzz.py"))
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     assert fz.one(seed, steps=25)
